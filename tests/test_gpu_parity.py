@@ -1,0 +1,333 @@
+"""GPU parity tests: the CUDA path (through the reference-facing Python API -> C ABI) against the CPU oracle
+and against the fixtures generated from the reference's own source.  Run on the B200 box: pytest -m gpu.
+
+Tolerances: STFT / mel 1e-4 relative (Frobenius and max-abs relative to max|ref|);
+Griffin-Lim waveform rel-L2 <= 1e-3 and |delta spectral convergence| <= 1e-4 given the same initial phase;
+loss value 1e-5 relative; loss gradient 1e-4 rel-L2.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import max_rel, rel_fro
+from oracle import spectral_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def sb():
+    import transtacos_retunegan_b200 as sb
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    sb._lib.load()   # fail loudly if the extension is missing
+    return sb
+
+
+def _close(a, b, tol=TOL):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert rel_fro(a, b) < tol, rel_fro(a, b)
+    assert max_rel(a, b) < tol, max_rel(a, b)
+
+
+# ------------------------------------------------------------------ STFT (complex) ------------
+
+@pytest.mark.parametrize("n_fft,win,hop", [(2048, 1024, 256), (2048, 1024, 240), (1024, 512, 120), (512, 256, 60),
+                                           (1024, 512, 128), (512, 256, 64)])
+@pytest.mark.parametrize("L", [22050, 4097, 8192])
+def test_stft_complex_vs_oracle(sb, n_fft, win, hop, L):
+    y = O.synth_noise(L, 11)
+    plan = sb.core.get_plan(sb.RETUNEGAN, n_fft, win, hop)
+    batch = sb.core.SignalBatch(plan, y)
+    mag, mel, D = sb.core.stft_features(plan, batch, want_spec=True)
+    ref = O.stft(y.astype(np.float64), n_fft, hop, win)
+    assert D.shape == (ref.shape[1], ref.shape[0])
+    _close(D.cpu().numpy().T, ref, 2e-6)
+    _close(mag.cpu().numpy().T, np.abs(ref), 2e-6)
+    melref = O.mel_filterbank(22050, n_fft, 80, 125, 7600).astype(np.float64) @ np.abs(ref)
+    _close(mel.cpu().numpy().T, melref, 5e-6)
+
+
+def test_mel_basis_matches_oracle(sb):
+    for n_fft, win, hop in O.HP.multi_stft_params:
+        plan = sb.core.get_plan(sb.RETUNEGAN, n_fft, win, hop)
+        np.testing.assert_array_equal(plan.mel_basis(), O.mel_filterbank(22050, n_fft, 80, 125, 7600))
+        np.testing.assert_allclose(plan.window(), O.get_window("hann", win).astype(np.float32), atol=1e-7)
+    cfg = sb.RETUNEGAN.replace(mel_scale="htk")
+    np.testing.assert_array_equal(sb.core.get_plan(cfg).mel_basis(), O.mel_filterbank(22050, 2048, 80, 125, 7600, htk=True))
+
+
+# ------------------------------------------------------------------ TransTacoS get_specs ------
+
+@pytest.mark.parametrize("tag", ["speech", "noise"])
+def test_get_specs_golden(sb, golden, tag):
+    S, M = sb.transtacos_audio.get_specs(golden[f"y_{tag}"])
+    assert S.dtype == np.float64 and S.shape == (1025, 24) and M.shape == (80, 24)
+    assert not S.flags.c_contiguous      # frame-major memory, like librosa's order='F'
+    _close(S, golden[f"tt_get_specs_S_{tag}"])
+    _close(M, golden[f"tt_get_specs_M_{tag}"])
+
+
+def test_get_specs_5s_vs_oracle_and_floor(sb):
+    L = 431 * 256 - 1
+    y = O.synth_speechlike(L, 114514)
+    S, M = sb.transtacos_audio.get_specs(y)
+    So, Mo = O.tt_get_specs(y)
+    assert S.shape == (1025, 431) and M.shape == (80, 431)
+    _close(S, So)
+    _close(M, Mo)
+    Sz, Mz = sb.transtacos_audio.get_specs(np.zeros(256 * 8 - 1, np.float32))
+    assert np.abs(Sz + 5.6).max() < 1e-5 and np.abs(Mz + 5.6).max() < 1e-5   # stats/DataBaker.stats:13,15
+
+
+def test_get_specs_ragged_and_uniform_batches(sb):
+    ys = [O.synth_noise(L, 20 + i) for i, L in enumerate([256 * 30 - 1, 256 * 101 - 1, 5000, 256 * 7])]
+    outs_S, outs_M = sb.transtacos_audio.get_specs(ys)
+    for y, S, M in zip(ys, outs_S, outs_M):
+        S1, M1 = sb.transtacos_audio.get_specs(y)
+        assert S.shape == (1025, 1 + len(y) // 256)
+        np.testing.assert_array_equal(S, S1)     # batching never changes results (utterances are independent)
+        np.testing.assert_array_equal(M, M1)
+    yb = np.stack([O.synth_noise(256 * 40 - 1, 40 + i) for i in range(5)])
+    Sb, Mb = sb.transtacos_audio.get_specs(yb)
+    for i in range(5):
+        S1, M1 = sb.transtacos_audio.get_specs(yb[i])
+        np.testing.assert_array_equal(Sb[i], S1)
+        np.testing.assert_array_equal(Mb[i], M1)
+
+
+def test_torch_input_returns_cuda_views(sb):
+    y = torch.from_numpy(O.synth_noise(256 * 20 - 1, 3)).cuda()
+    S, M = sb.transtacos_audio.get_specs(y)
+    assert S.is_cuda and S.shape == (1025, 20) and S.stride() == (1, 1025) and M.stride() == (1, 80)
+    So, _ = O.tt_get_specs(y.cpu().numpy())
+    _close(S.cpu().numpy(), So)
+
+
+def test_error_conventions(sb):
+    with pytest.raises(ValueError):
+        sb.transtacos_audio.get_specs(np.array([0.0, np.nan] * 2000, np.float32))     # librosa ParameterError
+    with pytest.raises(ValueError):
+        sb.transtacos_audio.get_specs(np.zeros(100, np.float32))                      # too short to reflect-pad
+    with pytest.raises((ValueError, NotImplementedError)):
+        sb.core.get_plan(sb.TRANSTACOS, 2048, 2048, 256)                              # win != n_fft/2
+    with pytest.raises(ValueError):
+        sb.SpectralConfig(fmax=11025)                                                 # transtacos/audio.py:160
+    with pytest.raises(RuntimeError):
+        sb.multi_stft_loss(torch.zeros(2, 4096).cuda(), torch.zeros(2, 4096).cuda())  # loss.py:62
+
+
+# ------------------------------------------------------------------ RetuneGAN get_mag / get_mel --
+
+@pytest.mark.parametrize("tag", ["speech", "noise"])
+def test_get_mag_mel_golden(sb, golden, tag):
+    y = golden[f"y_{tag}"]
+    mag, mel = sb.retunegan_audio.get_mag(y), sb.retunegan_audio.get_mel(y)
+    assert mag.dtype == np.float32 and mag.shape == (1025, 24) and mel.shape == (80, 24)
+    # ln-domain outputs: compare amplitudes (1e-4 relative), and the logs absolutely where they are well conditioned
+    _close(np.exp(mag), np.exp(golden[f"rtg_get_mag_{tag}"]))
+    _close(np.exp(mel), np.exp(golden[f"rtg_get_mel_{tag}"]))
+    assert np.abs(mel - golden[f"rtg_get_mel_{tag}"]).max() < 1e-3
+    m2, l2 = sb.retunegan_audio.get_mag_mel(y)
+    np.testing.assert_array_equal(m2, mag)
+    np.testing.assert_array_equal(l2, mel)
+
+
+def test_get_mag_clamp(sb):
+    y = np.zeros(256 * 10 - 1, np.float32)
+    assert np.allclose(sb.retunegan_audio.get_mag(y), np.log(1e-5), atol=1e-5)
+    assert np.all(np.isneginf(sb.retunegan_audio.get_mag(y, clamp_low=False)))
+
+
+def test_mag_to_mel(sb, golden):
+    mag = golden["rtg_get_mag_speech"]
+    out = sb.retunegan_audio.mag_to_mel(mag)
+    _close(out, golden["rtg_mag_to_mel_speech"], 1e-5)
+    np.testing.assert_array_equal(sb.retunegan_audio.mel_basis, golden["rtg_mel_basis"])
+
+
+# ------------------------------------------------------------------ filters -------------------
+
+def test_preemphasis_filters(sb, golden):
+    y = golden["y_speech"]
+    _close(sb.transtacos_audio.preemphasis(y), golden["tt_preemphasis_speech"], 1e-6)
+    _close(sb.transtacos_audio.inv_preemphasis(y), golden["tt_inv_preemphasis_speech"], 1e-5)
+    long = O.synth_noise(110335, 9)
+    _close(sb.transtacos_audio.inv_preemphasis(long), O.tt_inv_preemphasis(long), 1e-5)
+    rt = sb.transtacos_audio.inv_preemphasis(sb.transtacos_audio.preemphasis(long).astype(np.float32))
+    _close(rt, long, 1e-5)
+
+
+# ------------------------------------------------------------------ ISTFT / Griffin-Lim --------
+
+@pytest.mark.parametrize("n_fft,win,hop", [(2048, 1024, 256), (1024, 512, 120), (512, 256, 64)])
+def test_istft_vs_oracle_and_roundtrip(sb, n_fft, win, hop):
+    L = hop * 50
+    y = O.synth_speechlike(L, 5)
+    D = O.stft(y.astype(np.float64), n_fft, hop, win)
+    T = D.shape[1]
+    plan = sb.core.get_plan(sb.RETUNEGAN, n_fft, win, hop)
+    spec = torch.from_numpy(np.ascontiguousarray(D.T).astype(np.complex64)).cuda()
+    fb = sb.core.FramesBatch(plan, [T], None, spec.device)
+    out = sb.core.istft(plan, spec, fb).cpu().numpy()
+    ref = O.istft(D, hop, win)
+    assert out.shape == ref.shape == (hop * (T - 1),)
+    _close(out, ref, 1e-5)
+    _close(out, y[:len(out)], 1e-5)             # ISTFT(STFT(y)) == y
+    fb2 = sb.core.FramesBatch(plan, [T], [hop * (T - 1) + 7], spec.device)     # librosa length=: trim / zero-pad
+    out2 = sb.core.istft(plan, spec, fb2).cpu().numpy()
+    _close(out2, O.istft(D, hop, win, length=len(out2)), 1e-5)
+    # random (inconsistent) spectrogram: exercises the normalised overlap-add proper
+    rs = np.random.RandomState(0)
+    R = (rs.randn(n_fft // 2 + 1, 23) + 1j * rs.randn(n_fft // 2 + 1, 23)).astype(np.complex64)
+    fb3 = sb.core.FramesBatch(plan, [23], None, spec.device)
+    out3 = sb.core.istft(plan, torch.from_numpy(np.ascontiguousarray(R.T)).cuda(), fb3).cpu().numpy()
+    _close(out3, O.istft(R.astype(np.complex128), hop, win), 1e-5)
+
+
+def _gl_check(y_gpu, y_ref, S_target, hp_cfg):
+    assert y_gpu.shape == y_ref.shape
+    rel = rel_fro(y_gpu, y_ref)
+    assert rel <= 1e-3, rel
+    sc_g = O.spectral_convergence(S_target, y_gpu)
+    sc_r = O.spectral_convergence(S_target, y_ref)
+    assert abs(sc_g - sc_r) <= 1e-4, (sc_g, sc_r)
+
+
+def test_inv_spec_golden(sb, golden):
+    S, _ = O.tt_get_specs(golden["y_speech"])
+    ph = golden["tt_inv_spec_phase1025"]
+    w = sb.transtacos_audio.inv_spec(S, init_phase=ph)
+    assert w.dtype == np.float32 and w.shape == (256 * 23,)
+    target = O.tt_spec_to_natural_scale(S) ** 1.2
+    # compare before de-emphasis amplifies low frequencies: undo it with the oracle FIR
+    _gl_check(O.tt_preemphasis(w), O.tt_preemphasis(golden["tt_inv_spec_speech"]), target, None)
+    assert rel_fro(w, golden["tt_inv_spec_speech"]) <= 1e-3
+    w2 = sb.transtacos_audio.inv_spec(S[1:], init_phase=ph)
+    assert rel_fro(w2, golden["tt_inv_spec_speech_F1024"]) <= 1e-3
+    np.random.seed(114514)       # default path draws np.random.rand(F, T) from the global RNG like the reference
+    w3 = sb.transtacos_audio.inv_spec(S)
+    np.testing.assert_array_equal(w3, w)
+
+
+def test_inv_mag_golden(sb, golden):
+    mag = golden["rtg_get_mag_speech"]
+    L = len(golden["y_speech"])
+    w = sb.retunegan_audio.inv_mag(mag, wavlen=L)
+    assert w.dtype == np.float32 and len(w) == L
+    _gl_check(w, golden["rtg_inv_mag_speech"], np.exp(mag.astype(np.float64)) ** 1.2, None)
+    w2 = sb.retunegan_audio.inv_mag(mag[1:], wavlen=L)
+    assert rel_fro(w2, golden["rtg_inv_mag_speech_F1024"]) <= 1e-3
+    w3 = sb.retunegan_audio.inv_mag(mag)
+    assert len(w3) == 256 * 23 and rel_fro(w3, golden["rtg_inv_mag_speech_nolen"]) <= 1e-3
+
+
+@pytest.mark.parametrize("form", ["tt", "rtg"])
+def test_griffinlim_5s_vs_oracle(sb, form):
+    L = 431 * 256 - 1
+    y = O.synth_speechlike(L, 114514)
+    S = np.abs(O.stft(y, 2048, 256, 1024)).astype(np.float32)
+    u = np.random.RandomState(114514).rand(1025, 431)
+    if form == "tt":
+        ref = O.tt_griffin_lim(S.astype(np.float64) ** 1.2, init_phase=u)
+        out = sb.transtacos_audio._griffin_lim(S.astype(np.float64) ** 1.2, init_phase=u)
+        assert out.shape == ref.shape == (110080,)
+    else:
+        ref = O.rtg_griffinlim(S, wavlen=L, init_angles=np.exp(2j * np.pi * u))
+        out = sb.retunegan_audio._griffinlim(S, wavlen=L)
+        assert out.shape == ref.shape == (L,)
+    _gl_check(out, ref, S.astype(np.float64) ** 1.2, None)
+
+
+# ------------------------------------------------------------------ get_stft_torch / mstft -----
+
+@pytest.mark.parametrize("ri", [0, 1, 2])
+def test_get_stft_torch_golden(sb, golden, ri):
+    n_fft, win, hop = O.HP.multi_stft_params[ri]
+    S, M, P = sb.retunegan_audio.get_stft_torch(torch.from_numpy(golden["loss_y"]).cuda(), n_fft, win, hop)
+    gS, gM, gP = golden[f"stft_torch_S_{ri}"], golden[f"stft_torch_M_{ri}"], golden[f"stft_torch_P_{ri}"]
+    assert tuple(S.shape) == gS.shape and tuple(M.shape) == gM.shape and tuple(P.shape) == gP.shape
+    _close(S.cpu().numpy(), gS, 1e-5)
+    _close(M.cpu().numpy(), gM, 1e-5)
+    d = np.abs(np.exp(1j * P.cpu().numpy().astype(np.float64)) - np.exp(1j * gP.astype(np.float64))) * gS
+    assert d.max() < 1e-4 * gS.max()
+
+
+def _loss_inputs(golden):
+    y = torch.from_numpy(golden["loss_y"]).cuda().unsqueeze(1)
+    yg = torch.from_numpy(golden["loss_yg"]).cuda().unsqueeze(1).requires_grad_(True)
+    return y, yg
+
+
+def test_multi_stft_loss_value_and_grad_golden(sb, golden):
+    y, yg = _loss_inputs(golden)
+    loss = sb.multi_stft_loss(y, yg, ret_loss=True)
+    assert loss.dim() == 0
+    ref = float(golden["loss_value_f64"])
+    assert abs(loss.item() - ref) <= 1e-5 * abs(ref), (loss.item(), ref)
+    (g,) = torch.autograd.grad(loss, yg)
+    assert g.shape == yg.shape
+    gref = golden["loss_grad_lossonly_f64"]
+    assert rel_fro(g.cpu().numpy(), gref) <= 1e-4, rel_fro(g.cpu().numpy(), gref)
+
+
+def test_multi_stft_loss_specs_and_training_grad_golden(sb, golden):
+    y, yg = _loss_inputs(golden)
+    loss, (sr, sg) = sb.multi_stft_loss(y, yg, ret_loss=True, ret_specs=True)
+    rs = np.random.RandomState(7)
+    total = loss * 8
+    for ri in range(3):
+        for ours, ref in ((sr[ri], golden[f"loss_specs_r_{ri}"]), (sg[ri], golden[f"loss_specs_g_{ri}"])):
+            assert tuple(ours.shape) == ref.shape
+            o = ours.detach().cpu().numpy()
+            _close(np.exp(o[:, 0]), np.exp(ref[:, 0]), 1e-5)                        # ln|D+1e-9|
+            S = np.exp(ref[:, 0].astype(np.float64))
+            d = np.abs(np.exp(1j * np.pi * o[:, 1].astype(np.float64)) - np.exp(1j * np.pi * ref[:, 1])) * S
+            assert d.max() < 1e-4 * S.max()                                           # angle(D)/PI
+        up = torch.from_numpy(rs.randn(*golden[f"loss_specs_g_{ri}"].shape) * 1e-3).float().cuda()
+        total = total + (up * sg[ri]).sum()
+    assert not sr[0].requires_grad and sg[0].requires_grad
+    (g,) = torch.autograd.grad(total, yg)
+    gref = golden["loss_grad_train_f64"]
+    assert rel_fro(g.cpu().numpy(), gref) <= 1e-4, rel_fro(g.cpu().numpy(), gref)
+    only = sb.multi_stft_loss(y, yg, ret_specs=True)
+    assert len(only) == 2 and len(only[0]) == 3
+
+
+def test_multi_stft_loss_reference_shapes(sb):
+    y = torch.from_numpy(np.stack([O.synth_noise(8192, i) for i in range(16)])).cuda().unsqueeze(1)
+    yg = torch.tanh(y * 1.1).requires_grad_(True)
+    loss, (sr, sg) = sb.multi_stft_loss(y, yg, ret_loss=True, ret_specs=True)
+    assert [tuple(s.shape) for s in sg] == [(16, 2, 1025, 35), (16, 2, 513, 69), (16, 2, 257, 137)]   # train.py:136-138
+    ref = O.rtg_multi_stft_loss(y.cpu().numpy(), yg.detach().cpu().numpy(), ret_loss=True)
+    assert abs(loss.item() - ref) <= 1e-5 * abs(ref)
+    loss.backward()
+    gref = O.rtg_multi_stft_loss_backward(y.cpu().numpy()[:2], yg.detach().cpu().numpy()[:2], g_loss=2.0 / 16)
+    assert rel_fro(yg.grad[:2, 0].cpu().numpy(), gref) <= 1e-4
+
+
+# ------------------------------------------------------------------ full-size properties -------
+
+def test_full_size_properties_config3(sb):
+    """64 x 5 s (BASELINE.json configs[2]): linearity, batch independence, STFT -> ISTFT round trip."""
+    B, L = 64, 431 * 256 - 1
+    g = torch.Generator(device="cuda").manual_seed(114514)
+    y = (0.1 * torch.randn(B, L, device="cuda", generator=g)).clamp_(-0.999, 0.999)
+    plan = sb.core.get_plan(sb.RETUNEGAN)
+    batch = sb.core.SignalBatch(plan, y)
+    mag, mel, D = sb.core.stft_features(plan, batch, want_spec=True)
+    assert mag.shape == (B * 431, 1025) and mel.shape == (B * 431, 80)
+    assert torch.isfinite(mag).all() and torch.isfinite(mel).all()
+    # Parseval-type checksum against the time domain is window dependent; use linearity instead
+    D2 = sb.core.stft_features(plan, sb.core.SignalBatch(plan, 2.0 * y), want_mag=False, want_mel=False, want_spec=True)[2]
+    assert (D2 - 2.0 * D).abs().max() <= 1e-5 * D.abs().max()
+    one = sb.core.stft_features(plan, sb.core.SignalBatch(plan, y[17]), want_spec=True)[2]
+    assert torch.equal(one, D[17 * 431:18 * 431])
+    fb = sb.core.FramesBatch(plan, [431] * B, [L] * B, y.device)
+    rec = sb.core.istft(plan, D, fb).view(B, L)
+    assert (rec - y).abs().max() <= 1e-5
+    # mel == banded projection of mag
+    mel2 = sb.core.mel_project(plan, mag)
+    assert (mel2 - mel).abs().max() <= 1e-5 * mel.abs().max()

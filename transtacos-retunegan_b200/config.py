@@ -1,0 +1,83 @@
+"""Immutable configuration of the spectral path.
+
+Mirrors exactly the hparam.py attributes the hot path reads (transtacos/hparam.py:5-17,90-95;
+retunegan/hparam.py:3-15,36-40,72-81,97).  The reference configures everything through a global
+``hparam`` module; ``SpectralConfig.from_hparam(module)`` adapts such a module.
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import Tuple
+
+PI = 3.14159265358979  # retunegan/utils.py:12
+EPS = 1e-5             # transtacos/audio.py:13, retunegan/audio.py:19
+
+_WINDOWS = {"hann": 0, "hamming": 1, "blackman": 2, "bartlett": 3}
+
+
+@dataclasses.dataclass(frozen=True)
+class SpectralConfig:
+    sample_rate: int = 22050
+    n_fft: int = 2048
+    win_length: int = 1024
+    hop_length: int = 256
+    n_mel: int = 80
+    n_freq: int = 1025
+    preemphasis: float = 0.97
+    ref_level_db: float = 20
+    min_level_db: float = -100
+    max_abs_value: float = 4
+    fmin: float = 125
+    fmax: float = 7600
+    window_fn: str = "hann"
+    mel_scale: str = "slaney"
+    gl_iters: int = 30
+    gl_power: float = 1.2
+    gl_momentum: float = 0.0
+    randseed: int = 114514
+    multi_stft_params: Tuple[Tuple[int, int, int], ...] = ((2048, 1024, 240), (1024, 512, 120), (512, 256, 60))
+    phd_input: str = "stft"
+
+    def __post_init__(self):
+        if self.window_fn not in _WINDOWS:
+            # retunegan/hparam.py:36 also lists 'kaiser', which scipy.get_window cannot build without beta
+            raise ValueError(f"unsupported window_fn {self.window_fn!r}; supported: {sorted(_WINDOWS)}")
+        if self.mel_scale not in ("slaney", "htk"):
+            raise ValueError("mel_scale must be 'slaney' or 'htk'")
+        if self.n_freq != self.n_fft // 2 + 1:
+            raise ValueError("n_freq must equal n_fft // 2 + 1")
+        if not self.fmax < self.sample_rate // 2:
+            raise ValueError("fmax must be < sample_rate // 2 (transtacos/audio.py:160)")
+
+    @property
+    def window_id(self) -> int:
+        return _WINDOWS[self.window_fn]
+
+    def plan_key(self, n_fft=None, win_length=None, hop_length=None):
+        n_fft = self.n_fft if n_fft is None else int(n_fft)
+        win_length = self.win_length if win_length is None else int(win_length)
+        hop_length = self.hop_length if hop_length is None else int(hop_length)
+        return (self.sample_rate, n_fft, win_length, hop_length, self.n_mel, float(self.fmin), float(self.fmax),
+                int(self.mel_scale == "htk"), self.window_id)
+
+    def replace(self, **kw) -> "SpectralConfig":
+        return dataclasses.replace(self, **kw)
+
+    @classmethod
+    def from_hparam(cls, hp, **overrides) -> "SpectralConfig":
+        """Build from a reference-style ``hparam`` module / namespace (missing attributes keep defaults)."""
+        kw = {}
+        for f in dataclasses.fields(cls):
+            if hasattr(hp, f.name):
+                v = getattr(hp, f.name)
+                if f.name == "multi_stft_params":
+                    v = tuple(tuple(int(a) for a in p) for p in v)
+                kw[f.name] = v
+        kw.update(overrides)
+        return cls(**kw)
+
+
+# transtacos/hparam.py:90-91 -- 30 iterations, angle form (no momentum)
+TRANSTACOS = SpectralConfig(gl_iters=30, gl_power=1.2, gl_momentum=0.0)
+# retunegan/hparam.py:38-40 -- 4 iterations, momentum 0.7
+RETUNEGAN = SpectralConfig(gl_iters=4, gl_power=1.2, gl_momentum=0.7)

@@ -1,0 +1,275 @@
+"""Host-side plumbing over the C ABI: plan cache, tensor marshalling, batch descriptors.
+
+PyTorch is used only for device memory and streams; every arithmetic step of the path is a kernel in
+libspectral_b200.so.  All spectrogram-shaped tensors handled here are FRAME-MAJOR ``[frames, F]``; the
+reference-facing modules hand out ``[F, T]`` views of them (strides (1, F), the memory order librosa's
+``order='F'`` STFT has).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import threading
+from typing import List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Batch, Config, Scale, RAW, check
+from .config import SpectralConfig
+
+ArrayLike = Union[np.ndarray, torch.Tensor]
+
+_plans = {}
+_plans_lock = threading.Lock()
+
+
+def require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("transtacos-retunegan_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+class Plan:
+    """Opaque handle of the immutable tables of one (sr, n_fft, win, hop, n_mel, fmin, fmax, scale, window)."""
+
+    def __init__(self, key, device_index: int):
+        lib = _lib.load()
+        cfg = Config(*key)
+        h = C.c_void_p()
+        with torch.cuda.device(device_index):
+            check(lib.sb200_plan_create(C.byref(cfg), C.byref(h)), "plan_create")
+        self.handle = h
+        self.key = key
+        self.device_index = device_index
+        self.sample_rate, self.n_fft, self.win_length, self.hop_length, self.n_mel = key[:5]
+        self.F = self.n_fft // 2 + 1
+        self.Q = int(lib.sb200_plan_frames_per_pass(h))
+        self._mel = None
+
+    def mel_basis(self) -> np.ndarray:
+        """float32 [n_mel, F], equal to librosa.filters.mel(sr, n_fft, n_mel, fmin, fmax)."""
+        if self._mel is None:
+            out = np.empty((self.n_mel, self.F), np.float32)
+            check(_lib.load().sb200_plan_mel_basis_host(self.handle, out.ctypes.data_as(C.c_void_p)))
+            self._mel = out
+        return self._mel
+
+    def window(self) -> np.ndarray:
+        out = np.empty(self.win_length, np.float32)
+        check(_lib.load().sb200_plan_window_host(self.handle, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+
+def get_plan(cfg: SpectralConfig, n_fft=None, win_length=None, hop_length=None) -> Plan:
+    """Plan cache keyed by configuration AND device (the reference pins its caches to the first device seen,
+    retunegan/audio.py:153-159)."""
+    dev = require_cuda()
+    key = cfg.plan_key(n_fft, win_length, hop_length)
+    ck = (key, dev.index)
+    p = _plans.get(ck)
+    if p is None:
+        with _plans_lock:
+            p = _plans.get(ck)
+            if p is None:
+                p = Plan(key, dev.index)
+                _plans[ck] = p
+    return p
+
+
+def stream_ptr() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def to_device_f32(x: ArrayLike, pinned_copy: bool = False) -> torch.Tensor:
+    """numpy / torch (any device, any float dtype) -> contiguous float32 CUDA tensor on the current device."""
+    dev = require_cuda()
+    if isinstance(x, np.ndarray):
+        if not np.isfinite(x).all():
+            raise ValueError("Audio buffer is not finite everywhere")   # librosa.util.valid_audio (ParameterError)
+        t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+        return t.to(dev, non_blocking=False)
+    if not isinstance(x, torch.Tensor):
+        raise TypeError(f"expected numpy.ndarray or torch.Tensor, got {type(x).__name__}")
+    return x.detach().to(device=dev, dtype=torch.float32).contiguous()
+
+
+class SignalBatch:
+    """Device-side description of a batch of utterances (uniform [B, L] or ragged list)."""
+
+    def __init__(self, plan: Plan, ys):
+        self.plan = plan
+        hop, Q = plan.hop_length, plan.Q
+        if isinstance(ys, (list, tuple)):
+            parts = [to_device_f32(y).reshape(-1) for y in ys]
+            if not parts:
+                raise ValueError("empty batch")
+            lens = np.array([p.numel() for p in parts], np.int64)
+            if lens.min() < plan.n_fft // 4 + 1:
+                raise ValueError("signal shorter than n_fft/4 + 1 samples: reflect padding undefined")
+            self.x = torch.cat(parts)
+            self.B = len(parts)
+            self.lens = lens
+            frames = 1 + lens // hop
+            items = (frames + Q - 1) // Q
+            tbl = np.zeros((4, self.B + 1), np.int64)
+            tbl[0, 1:] = np.cumsum(lens)
+            tbl[1, :-1] = lens
+            tbl[2, 1:] = np.cumsum(frames)
+            tbl[3, 1:] = np.cumsum(items)
+            self.frames = frames
+            self.total_frames = int(tbl[2, -1])
+            self.tables = torch.from_numpy(tbl).to(self.x.device)
+            self.c = Batch(self.B, 0, 0, self.tables[0].data_ptr(), self.tables[1].data_ptr(),
+                           self.tables[2].data_ptr(), self.tables[3].data_ptr(), self.total_frames, int(tbl[3, -1]))
+            self.uniform = False
+        else:
+            x = to_device_f32(ys)
+            if x.dim() == 1:
+                x = x.unsqueeze(0)
+            if x.dim() != 2:
+                raise ValueError(f"expected [L] or [B, L] samples, got shape {tuple(x.shape)}")
+            self.x = x
+            self.B, L = x.shape
+            if L < plan.n_fft // 4 + 1:
+                raise ValueError("signal shorter than n_fft/4 + 1 samples: reflect padding undefined")
+            T = 1 + L // hop
+            self.lens = np.full(self.B, L, np.int64)
+            self.frames = np.full(self.B, T, np.int64)
+            self.total_frames = self.B * T
+            self.c = Batch(self.B, L, L, None, None, None, None, 0, 0)
+            self.uniform = True
+
+
+def log_scale(a: float, b: float, floor: float) -> Scale:
+    return Scale(1, a, b, floor)
+
+
+def stft_features(plan: Plan, batch: SignalBatch, preemph: float = 0.0, mag_scale: Optional[Scale] = None,
+                  mel_scale: Optional[Scale] = None, want_mag=True, want_mel=True, want_spec=False):
+    """One fused launch.  Returns (mag [frames, F] | None, mel [frames, n_mel] | None, spec [frames, F] complex64 | None)."""
+    dev = batch.x.device
+    n = batch.total_frames
+    mag = torch.empty((n, plan.F), device=dev, dtype=torch.float32) if want_mag else None
+    mel = torch.empty((n, plan.n_mel), device=dev, dtype=torch.float32) if want_mel else None
+    spec = torch.empty((n, plan.F, 2), device=dev, dtype=torch.float32) if want_spec else None
+    check(_lib.load().sb200_stft_features(plan.handle, ptr(batch.x), C.byref(batch.c), float(preemph),
+                                          mag_scale or RAW, mel_scale or RAW, ptr(mag), ptr(mel), ptr(spec),
+                                          stream_ptr()), "stft_features")
+    return mag, mel, (torch.view_as_complex(spec) if want_spec else None)
+
+
+def mel_project(plan: Plan, x_fm: torch.Tensor, scale: Optional[Scale] = None) -> torch.Tensor:
+    """[frames, F] float32 (frame-major) -> [frames, n_mel]."""
+    assert x_fm.is_cuda and x_fm.dtype == torch.float32 and x_fm.is_contiguous() and x_fm.shape[-1] == plan.F
+    frames = x_fm.numel() // plan.F
+    out = torch.empty((frames, plan.n_mel), device=x_fm.device, dtype=torch.float32)
+    check(_lib.load().sb200_mel_project(plan.handle, ptr(x_fm), frames, scale or RAW, ptr(out), stream_ptr()))
+    return out
+
+
+def spec_to_amplitude(x: torch.Tensor, mode: int, p0=0.0, p1=0.0, p2=0.0, power=1.0) -> torch.Tensor:
+    out = torch.empty_like(x)
+    check(_lib.load().sb200_spec_to_amplitude(ptr(x), x.numel(), mode, float(p0), float(p1), float(p2), float(power),
+                                              ptr(out), stream_ptr()))
+    return out
+
+
+def _rows_batch(x: torch.Tensor) -> Batch:
+    B, L = x.shape
+    return Batch(B, L, L, None, None, None, None, 0, 0)
+
+
+def preemphasis(x: torch.Tensor, k: float) -> torch.Tensor:
+    out = torch.empty_like(x)
+    check(_lib.load().sb200_preemphasis(ptr(x), C.byref(_rows_batch(x)), float(k), ptr(out), stream_ptr()))
+    return out
+
+
+def inv_preemphasis(x: torch.Tensor, k: float) -> torch.Tensor:
+    out = torch.empty_like(x)
+    check(_lib.load().sb200_inv_preemphasis(ptr(x), C.byref(_rows_batch(x)), float(k), ptr(out), stream_ptr()))
+    return out
+
+
+class FramesBatch:
+    """Batch of spectrograms described by frame counts (ISTFT / Griffin-Lim direction)."""
+
+    def __init__(self, plan: Plan, frames: Sequence[int], lengths: Optional[Sequence[int]], device):
+        frames = np.asarray(frames, np.int64)
+        hop, Q = plan.hop_length, plan.Q
+        self.B = len(frames)
+        out_len = np.asarray(lengths, np.int64) if lengths is not None else hop * (frames - 1)
+        self.out_len = out_len
+        self.has_length = lengths is not None
+        if lengths is not None and np.any(1 + out_len // hop != frames):
+            raise ValueError("length inconsistent with the number of frames: need 1 + length // hop == n_frames")
+        if out_len.min() < plan.n_fft // 4 + 1:
+            raise ValueError("output signal shorter than n_fft/4 + 1 samples")
+        self.total_frames = int(frames.sum())
+        if np.all(frames == frames[0]) and np.all(out_len == out_len[0]):
+            self.uniform = True
+            self.c = Batch(self.B, int(frames[0]), int(out_len[0]), None, None, None, None, 0, 0)
+            self.length_arg = int(out_len[0]) if lengths is not None else 0
+            self.total_out = int(out_len[0]) * self.B
+            self.out_off = np.arange(self.B + 1, dtype=np.int64) * int(out_len[0])
+        else:
+            self.uniform = False
+            items = (frames + Q - 1) // Q
+            tbl = np.zeros((4, self.B + 1), np.int64)
+            tbl[0, 1:] = np.cumsum(out_len)
+            tbl[1, :-1] = out_len
+            tbl[2, 1:] = np.cumsum(frames)
+            tbl[3, 1:] = np.cumsum(items)
+            self.tables = torch.from_numpy(tbl).to(device)
+            self.c = Batch(self.B, int(out_len.max()), 0, self.tables[0].data_ptr(), self.tables[1].data_ptr(),
+                           self.tables[2].data_ptr(), self.tables[3].data_ptr(), self.total_frames, int(tbl[3, -1]))
+            # ragged rows always carry explicit lengths (hop*(T-1) when none was asked for: same value librosa returns)
+            self.length_arg = 1
+            self.total_out = int(tbl[0, -1])
+            self.out_off = tbl[0].copy()
+
+
+_ws_cache = {}
+
+
+def _workspace(nbytes: int, device, tag: str) -> torch.Tensor:
+    """Grow-only per-device scratch buffer (caller-allocated workspace of the C ABI)."""
+    key = (device.index, tag)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes), device=device, dtype=torch.uint8)
+        _ws_cache[key] = buf
+    return buf
+
+
+def istft(plan: Plan, spec_fm: torch.Tensor, fb: FramesBatch) -> torch.Tensor:
+    """spec_fm: complex64 [total_frames, F] frame-major -> flat float32 [sum out_len]."""
+    lib = _lib.load()
+    sp = torch.view_as_real(spec_fm.contiguous())
+    y = torch.empty(fb.total_out, device=spec_fm.device, dtype=torch.float32)
+    ws = _workspace(lib.sb200_griffinlim_workspace_bytes(plan.handle, fb.total_frames, 0), spec_fm.device, "gl")
+    check(lib.sb200_istft(plan.handle, ptr(sp), C.byref(fb.c), fb.length_arg, ptr(y), ptr(ws), stream_ptr()), "istft")
+    return y
+
+
+def griffinlim(plan: Plan, S_fm: torch.Tensor, phase_fm: torch.Tensor, fb: FramesBatch, n_iter: int, momentum: float,
+               form: int, inv_preemph: float = 0.0) -> torch.Tensor:
+    """S_fm, phase_fm: float32 [total_frames, F] -> flat float32 [sum out_len]."""
+    lib = _lib.load()
+    assert S_fm.is_contiguous() and phase_fm.is_contiguous() and S_fm.shape == phase_fm.shape == (fb.total_frames, plan.F)
+    y = torch.empty(fb.total_out, device=S_fm.device, dtype=torch.float32)
+    ws = _workspace(lib.sb200_griffinlim_workspace_bytes(plan.handle, fb.total_frames, form), S_fm.device, "gl")
+    pre_in_call = inv_preemph if fb.uniform else 0.0
+    check(lib.sb200_griffinlim(plan.handle, ptr(S_fm), ptr(phase_fm), C.byref(fb.c), fb.length_arg, int(n_iter),
+                               float(momentum), int(form), float(pre_in_call), ptr(y), ptr(ws), stream_ptr()),
+          "griffinlim")
+    if inv_preemph and not fb.uniform:
+        b = Batch(fb.B, 0, 0, fb.tables[0].data_ptr(), fb.tables[1].data_ptr(), None, None, 0, 0)
+        check(lib.sb200_inv_preemphasis(ptr(y), C.byref(b), float(inv_preemph), ptr(y), stream_ptr()))
+    return y

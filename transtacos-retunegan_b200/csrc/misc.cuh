@@ -1,0 +1,145 @@
+// Small kernels around the FFT path: banded mel projection of an arbitrary spectrogram, the
+// element-wise inverse scalings, and the pre-emphasis FIR / de-emphasis IIR (parallel scan).
+#pragma once
+#include "feat.cuh"
+
+namespace sb200 {
+
+// out[t, m] = sum_k basis[m, k] in[t, k]   (retunegan/audio.py:21, transtacos/audio.py:154-155)
+template <int N>
+__global__ void __launch_bounds__(kFeatWarps * 32) mel_project_kernel(const PlanDev p, const float* __restrict__ in,
+                                                                      long long frames, const ScaleDev sc,
+                                                                      float* __restrict__ out) {
+  using C = FftCfg<N>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmemTables<N> sm;
+  sm.carve(smem_raw, p);
+  sm.fill(p, p.window, true);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float2* buf = sm.bufs + warp * C::kBufF2;
+  const long long items = (frames + C::kQ - 1) / C::kQ;
+  for (long long item = static_cast<long long>(blockIdx.x) * kFeatWarps + warp; item < items;
+       item += static_cast<long long>(gridDim.x) * kFeatWarps) {
+    const long long t0 = item * C::kQ;
+#pragma unroll
+    for (int q = 0; q < C::kQ; ++q) {
+      const long long t = t0 + q;
+      for (int k = lane; k < C::kNz; k += 32) buf[q * C::kZS + k].x = (t < frames) ? __ldg(in + t * C::kF + k) : 0.f;
+    }
+    __syncwarp();
+    mel_project_smem<N>(p, sm.melw, sm.mel_lo, buf, lane, [&](int q, int, int m, float val) {
+      if (m < p.n_mel && t0 + q < frames) out[(t0 + q) * p.n_mel + m] = apply_scale(sc, val);
+    });
+    __syncwarp();
+  }
+}
+
+// mode 0: 10^(((in + p0) * (-p1) / (2 p0) + p1 + p2) / 20) ^ power ; mode 1: exp(in) ^ power ; mode 2: in ^ power (in >= 0)
+__global__ void spec_to_amplitude_kernel(const float* __restrict__ in, long long n, int mode, float p0, float p1, float p2,
+                                         float power, float* __restrict__ out) {
+  const float kLog2_10 = 3.3219280948873623f, kLog2_e = 1.4426950408889634f;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float v = __ldg(in + i);
+    float l2;   // log2 of the amplitude
+    if (mode == 0) {
+      const float db = (v + p0) * (-p1) / (2.f * p0) + p1 + p2;
+      l2 = db * 0.05f * kLog2_10;
+    } else if (mode == 1) {
+      l2 = v * kLog2_e;
+    } else {
+      l2 = log2f(v);
+    }
+    out[i] = exp2f(l2 * power);
+  }
+}
+
+__device__ __forceinline__ void row_of(const BatchDev& bd, int b, long long* base, long long* L) {
+  if (bd.sig_off) {
+    *base = __ldg(bd.sig_off + b);
+    *L = __ldg(bd.sig_len + b);
+  } else {
+    *base = b * bd.stride;
+    *L = bd.len;
+  }
+}
+
+// y[n] = x[n] - k x[n-1], zero initial state (transtacos/audio.py:64-66)
+__global__ void preemphasis_kernel(const float* __restrict__ x, const BatchDev bd, float k, float* __restrict__ y) {
+  long long base, L;
+  row_of(bd, blockIdx.y, &base, &L);
+  for (long long n = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; n < L;
+       n += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float prev = n > 0 ? __ldg(x + base + n - 1) : 0.f;
+    y[base + n] = fmaf(-k, prev, __ldg(x + base + n));
+  }
+}
+
+// y[n] = x[n] + k y[n-1] (transtacos/audio.py:69-70): one CTA per row, tiles of 256 x 8 samples.
+// Within a tile every thread runs the recurrence over its 8 samples from a zero state, the
+// per-thread carries (a = k^8, b = local tail) are combined with a warp-shuffle + smem scan of the
+// affine maps s -> a s + b, and the incoming state is folded back in.
+constexpr int kScanThreads = 256, kScanPer = 8;
+__global__ void __launch_bounds__(kScanThreads) inv_preemphasis_kernel(const float* x, const BatchDev bd, float k,
+                                                                       float* y) {   // x == y allowed (in place)
+  __shared__ float tile[kScanThreads * kScanPer];
+  __shared__ float warp_b[kScanThreads / 32];
+  long long base, L;
+  row_of(bd, blockIdx.x, &base, &L);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float kp[kScanPer + 1];   // k^1 .. k^8
+  kp[0] = 1.f;
+#pragma unroll
+  for (int i = 1; i <= kScanPer; ++i) kp[i] = kp[i - 1] * k;
+  const float a_thread = kp[kScanPer];
+  float a_pow_lane = 1.f;   // a_thread^lane
+  for (int i = 0; i < lane; ++i) a_pow_lane *= a_thread;
+  float a_warp = 1.f;       // a_thread^32
+  for (int i = 0; i < 32; ++i) a_warp *= a_thread;
+  float state = 0.f;        // y[tile_start - 1]
+  for (long long t0 = 0; t0 < L; t0 += kScanThreads * kScanPer) {
+    for (int i = tid; i < kScanThreads * kScanPer; i += kScanThreads)
+      tile[i] = (t0 + i < L) ? x[base + t0 + i] : 0.f;
+    __syncthreads();
+    float loc[kScanPer];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kScanPer; ++i) {
+      s = fmaf(k, s, tile[tid * kScanPer + i]);
+      loc[i] = s;
+    }
+    // inclusive scan over lanes of affine maps (a, b): combine(prev, cur) = (a_p a_c, a_c b_p + b_c); a is a power of a_thread
+    float b = s, a = a_thread;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const float bp = __shfl_up_sync(kFullMask, b, d);
+      const float ap = __shfl_up_sync(kFullMask, a, d);
+      if (lane >= d) {
+        b = fmaf(a, bp, b);
+        a *= ap;
+      }
+    }
+    if (lane == 31) warp_b[warp] = b;
+    __syncthreads();
+    // state entering this warp
+    float win_state = state;
+    for (int w = 0; w < warp; ++w) win_state = fmaf(a_warp, win_state, warp_b[w]);
+    // state entering this thread: exclusive prefix within the warp applied to win_state
+    float b_excl = __shfl_up_sync(kFullMask, b, 1);
+    if (lane == 0) b_excl = 0.f;
+    const float tin = fmaf(a_pow_lane, win_state, b_excl);
+#pragma unroll
+    for (int i = 0; i < kScanPer; ++i) tile[tid * kScanPer + i] = fmaf(kp[i + 1], tin, loc[i]);
+    // next tile's incoming state = value of the last sample of this tile
+    float next_state = state;
+    for (int w = 0; w < kScanThreads / 32; ++w) next_state = fmaf(a_warp, next_state, warp_b[w]);
+    state = next_state;
+    __syncthreads();
+    for (int i = tid; i < kScanThreads * kScanPer; i += kScanThreads)
+      if (t0 + i < L) y[base + t0 + i] = tile[i];
+    __syncthreads();
+  }
+}
+
+}  // namespace sb200

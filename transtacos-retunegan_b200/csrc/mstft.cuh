@@ -1,0 +1,341 @@
+// Multi-resolution STFT loss, forward and backward (retunegan/models/loss.py:22-62,
+// retunegan/audio.py:150-170; backward = the autograd graph of retunegan/train.py:192, closed form in
+// SURVEY.md 8a row L2).
+//
+// Forward, per resolution: one launch; a warp analyses the same Q frames of y and of y_g back to back,
+// keeps the real mel rows in registers, and accumulates |M - M_g| + |ln M - ln M_g| into a per-warp
+// partial (deterministic two-stage reduction, no atomics).  Optionally writes the [B,2,T',F]
+// (ln|D+1e-9|, angle(D)/PI) stacks for the STFT discriminator.
+// Backward, per resolution: recomputes the y_g analysis (cheaper than saving 8 B/bin), forms
+// gD = gS (D+1e-9)/S + (gP/PI) i D/|D|^2 with gS = basis^T gM + g_lnS/S on the Hermitian pairs in
+// registers, runs the adjoint of the one-sided rFFT through the inverse engine, windows, and stores
+// gradient frames; grad_ola_kernel then overlap-adds all resolutions as a gather and folds the
+// reflect padding back.
+#pragma once
+#include "feat.cuh"
+
+namespace sb200 {
+
+constexpr float kRefPI = 3.14159265358979f;   // retunegan/utils.py:12
+constexpr int kMstftWarps = 8;
+constexpr int kMaxRes = 4;
+
+struct MstftFwdArgs {
+  const float* y;
+  const float* yg;
+  BatchDev bd;          // uniform [B, T]
+  int Tf;               // frames per row
+  float* spec_r;        // [B, 2, Tf, F] or null
+  float* spec_g;        // [B, 2, Tf, F] or null
+  int phd_phase;
+  float* mel_r;         // [B*Tf, n_mel] saved for backward (never null)
+  float* partials;      // [gridDim.x * kMstftWarps]
+  int want_loss;
+};
+
+template <int N>
+__device__ __forceinline__ void mstft_analyse(const PlanDev& p, const SmemTables<N>& sm, float2* buf, float2 (&v)[32],
+                                              const float* x, long long L, int t0, int T, int lane, float* ch0,
+                                              float* ch0_alias, float* ch1, long long row0 /* (b*2*Tf + t0) * F */,
+                                              long long ch_stride /* Tf*F */) {
+  // analysis of Q frames; leaves S = |D + 1e-9| in buf[q*ZS + k].x; optionally writes ln S (ch0, ch0_alias) and angle/PI (ch1)
+  using C = FftCfg<N>;
+  load_frames<N, false>(v, x, L, t0, T, p.hop, 0.f, sm.win, lane);
+  fft_forward<N>(v, buf, sm.tw, lane);
+  const int rk = lane & 3, rm = (4 - rk) & 3;
+  static_for<0, C::kQ>([&](auto qc) {
+    constexpr int q = decltype(qc)::value;
+    if (t0 + q < T) {
+      float2* zq = buf + q * C::kZS;
+      const long long row = row0 + static_cast<long long>(q) * C::kF;
+      auto emit = [&](float2 X, int k, float S) {
+        if (ch0) ch0[row + k] = logf(S);
+        if (ch0_alias) ch0_alias[row + k] = logf(S);
+        if (ch1) ch1[row + ch_stride + k] = atan2f(X.y, X.x) / kRefPI;
+      };
+#pragma unroll 2
+      for (int i = 0; i < C::kPairIters; ++i) {
+        const int k = lane + 32 * i;
+        const int km = (C::kNz - k) & (C::kNz - 1);
+        float2 Ak, Am;
+        split_fwd(zq[k], zq[km], sm.ws[k], Ak, Am);
+        const float2 Xk = rot_fwd(Ak, rk), Xm = rot_fwd(Am, rm);
+        const float rek = Xk.x + 1e-9f, rem = Xm.x + 1e-9f;
+        const float sk = sqrtf(fmaf(rek, rek, Xk.y * Xk.y)), smg = sqrtf(fmaf(rem, rem, Xm.y * Xm.y));
+        zq[k].x = sk;
+        if (k != 0) zq[km].x = smg;
+        emit(Xk, k, sk);
+        emit(Xm, C::kNz - k, smg);
+      }
+      if (lane == 0) {
+        constexpr int k = C::kNz / 2;
+        float2 Ak, Am;
+        split_fwd(zq[k], zq[k], sm.ws[k], Ak, Am);
+        const float2 Xk = rot_fwd(Ak, k);
+        const float rek = Xk.x + 1e-9f;
+        const float sk = sqrtf(fmaf(rek, rek, Xk.y * Xk.y));
+        zq[k].x = sk;
+        emit(Xk, k, sk);
+      }
+    }
+  });
+  __syncwarp();
+}
+
+template <int N>
+__global__ void __launch_bounds__(kMstftWarps * 32, 2) mstft_fwd_kernel(const PlanDev p, const MstftFwdArgs a) {
+  using C = FftCfg<N>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmemTables<N> sm;
+  sm.carve(smem_raw, p);
+  sm.fill(p, p.window, true);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float2* buf = sm.bufs + warp * C::kBufF2;
+  float acc = 0.f;
+  const long long chs = static_cast<long long>(a.Tf) * C::kF;
+  for (long long item = static_cast<long long>(blockIdx.x) * kMstftWarps + warp; item < a.bd.total_items;
+       item += static_cast<long long>(gridDim.x) * kMstftWarps) {
+    const Item it = decode_item(a.bd, item, C::kQ);
+    const long long row0 = (static_cast<long long>(it.b) * 2 * a.Tf + it.t0) * C::kF;
+    float2 v[32];
+    float mr[kMaxMelRounds][C::kQ];
+    mstft_analyse<N>(p, sm, buf, v, a.y + it.sig_base, it.L, it.t0, it.T, lane, a.spec_r,
+                     a.phd_phase ? a.spec_g : nullptr, a.spec_r, row0, chs);
+    mel_project_smem<N>(p, sm.melw, sm.mel_lo, buf, lane, [&](int q, int rd, int m, float val) {
+      mr[rd][q] = val;
+      if (m < p.n_mel && it.t0 + q < it.T) a.mel_r[(it.frame_base + it.t0 + q) * p.n_mel + m] = val;
+    });
+    __syncwarp();
+    mstft_analyse<N>(p, sm, buf, v, a.yg + it.sig_base, it.L, it.t0, it.T, lane, a.phd_phase ? nullptr : a.spec_g,
+                     nullptr, a.spec_g, row0, chs);
+    mel_project_smem<N>(p, sm.melw, sm.mel_lo, buf, lane, [&](int q, int rd, int m, float val) {
+      if (a.want_loss && m < p.n_mel && it.t0 + q < it.T) {
+        const float r = mr[rd][q];
+        acc += fabsf(r - val) + fabsf(logf(r) - logf(val));
+      }
+    });
+    __syncwarp();
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(kFullMask, acc, d);
+  if (lane == 0) a.partials[blockIdx.x * kMstftWarps + warp] = acc;
+}
+
+struct MstftFinArgs {
+  int n_res;
+  const float* partials[kMaxRes];
+  int n_partials[kMaxRes];
+  float inv_count[kMaxRes];   // 1 / (B * n_mel * Tf)
+  float* loss;
+};
+// loss = 1/n_res * sum_res (sum of partials) / count   (F.l1_loss reduction='mean', loss.py:51-54)
+__global__ void mstft_finalize_kernel(const MstftFinArgs a) {
+  __shared__ float red[32];
+  float total = 0.f;
+  for (int r = 0; r < a.n_res; ++r) {
+    float s = 0.f;
+    for (int i = threadIdx.x; i < a.n_partials[r]; i += blockDim.x) s += a.partials[r][i];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(kFullMask, s, d);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) t += red[w];
+      total += t * a.inv_count[r];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *a.loss = total / a.n_res;
+}
+
+struct MstftBwdArgs {
+  const float* yg;
+  BatchDev bd;
+  int Tf;
+  const float* mel_r;      // saved [B*Tf, n_mel]
+  const float* g_loss;     // device scalar or null
+  float loss_scale;        // 1 / (n_res * B * n_mel * Tf)
+  const float* g_spec;     // [B, 2, Tf, F] upstream or null
+  int phd_phase;
+  float* gfb;              // [B*Tf, win] gradient frames
+};
+
+template <int N>
+__global__ void __launch_bounds__(kMstftWarps * 32, 2) mstft_bwd_kernel(const PlanDev p, const MstftBwdArgs a) {
+  using C = FftCfg<N>;
+  constexpr int kPairs = C::kQ * C::kPairIters;   // 16
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmemTables<N> sm;
+  sm.carve(smem_raw, p);
+  sm.fill(p, p.window, true);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float2* buf = sm.bufs + warp * C::kBufF2;
+  float* gmbuf = reinterpret_cast<float*>(buf);   // [Q][128] mel-row gradients, after the mel phase
+  const int rk = lane & 3, rm = (4 - rk) & 3;
+  const float gl = a.g_loss ? __ldg(a.g_loss) * a.loss_scale : 0.f;
+  const long long chs = static_cast<long long>(a.Tf) * C::kF;
+  for (long long item = static_cast<long long>(blockIdx.x) * kMstftWarps + warp; item < a.bd.total_items;
+       item += static_cast<long long>(gridDim.x) * kMstftWarps) {
+    const Item it = decode_item(a.bd, item, C::kQ);
+    float2 v[32];
+    load_frames<N, false>(v, a.yg + it.sig_base, it.L, it.t0, it.T, p.hop, 0.f, sm.win, lane);
+    fft_forward<N>(v, buf, sm.tw, lane);
+    float2 Xk[kPairs], Xm[kPairs], Xs[C::kQ];
+    static_for<0, C::kQ>([&](auto qc) {
+      constexpr int q = decltype(qc)::value;
+      float2* zq = buf + q * C::kZS;
+      static_for<0, C::kPairIters>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        const int k = lane + 32 * i;
+        const int km = (C::kNz - k) & (C::kNz - 1);
+        float2 Ak, Am;
+        split_fwd(zq[k], zq[km], sm.ws[k], Ak, Am);
+        const float2 xk = rot_fwd(Ak, rk), xm = rot_fwd(Am, rm);
+        Xk[q * C::kPairIters + i] = xk;
+        Xm[q * C::kPairIters + i] = xm;
+        const float rek = xk.x + 1e-9f, rem = xm.x + 1e-9f;
+        zq[k].x = sqrtf(fmaf(rek, rek, xk.y * xk.y));
+        if (k != 0) zq[km].x = sqrtf(fmaf(rem, rem, xm.y * xm.y));
+      });
+      {
+        constexpr int k = C::kNz / 2;
+        float2 Ak, Am;
+        split_fwd(zq[k], zq[k], sm.ws[k], Ak, Am);
+        Xs[q] = rot_fwd(Ak, k);
+        if (lane == 0) {
+          const float rek = Xs[q].x + 1e-9f;
+          zq[k].x = sqrtf(fmaf(rek, rek, Xs[q].y * Xs[q].y));
+        }
+      }
+    });
+    __syncwarp();
+    // mel of the generated signal -> gradient of the loss w.r.t. each mel row
+    float gm[kMaxMelRounds][C::kQ];
+#pragma unroll
+    for (int rd = 0; rd < kMaxMelRounds; ++rd)
+#pragma unroll
+      for (int q = 0; q < C::kQ; ++q) gm[rd][q] = 0.f;
+    mel_project_smem<N>(p, sm.melw, sm.mel_lo, buf, lane, [&](int q, int rd, int m, float mg) {
+      float g = 0.f;
+      if (gl != 0.f && m < p.n_mel && it.t0 + q < it.T) {
+        const float r = __ldg(a.mel_r + (it.frame_base + it.t0 + q) * p.n_mel + m);
+        const float sgn = (mg > r) ? 1.f : ((mg < r) ? -1.f : 0.f);
+        g = gl * (sgn + sgn / mg);
+      }
+      gm[rd][q] = g;
+    });
+    __syncwarp();   // all S reads done; reuse the buffer for the mel-row gradients
+#pragma unroll
+    for (int rd = 0; rd < kMaxMelRounds; ++rd)
+#pragma unroll
+      for (int q = 0; q < C::kQ; ++q) gmbuf[q * 128 + rd * 32 + lane] = gm[rd][q];
+    __syncwarp();
+    // gD on the Hermitian pairs (in registers), scaled for the adjoint: interior bins / 2, DC and Nyquist real
+    auto grad_bin = [&](float2 X, int q, int k, float half) -> float2 {
+      const long long t = it.t0 + q;
+      float2 G = make_float2(0.f, 0.f);
+      if (t < it.T) {
+        const float re = X.x + 1e-9f;
+        const float S = sqrtf(fmaf(re, re, X.y * X.y));
+        const int r0 = __ldg(p.col_r0 + k);
+        float gS = fmaf(__ldg(p.col_c0 + k), gmbuf[q * 128 + r0], __ldg(p.col_c1 + k) * gmbuf[q * 128 + r0 + 1]);
+        float gP = 0.f;
+        if (a.g_spec) {
+          const long long idx = (static_cast<long long>(it.b) * 2 * a.Tf + t) * C::kF + k;
+          if (!a.phd_phase) gS += __ldg(a.g_spec + idx) / S;
+          gP = __ldg(a.g_spec + idx + chs) / kRefPI;
+        }
+        const float d2 = fmaf(X.x, X.x, X.y * X.y);
+        const float gs = S > 0.f ? gS / S : 0.f, gp = d2 > 0.f ? gP / d2 : 0.f;   // abs / angle backward are 0 at 0
+        // gS (X + 1e-9)/S + gP i X / |X|^2
+        G = make_float2(half * fmaf(gs, re, -gp * X.y), half * fmaf(gs, X.y, gp * X.x));
+      }
+      return G;
+    };
+    static_for<0, C::kQ>([&](auto qc) {
+      constexpr int q = decltype(qc)::value;
+      static_for<0, C::kPairIters>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        constexpr int pi = q * C::kPairIters + i;
+        const int k = lane + 32 * i;
+        Xk[pi] = grad_bin(Xk[pi], q, k, k == 0 ? 1.f : 0.5f);
+        Xm[pi] = grad_bin(Xm[pi], q, C::kNz - k, k == 0 ? 1.f : 0.5f);
+      });
+      Xs[q] = grad_bin(Xs[q], q, C::kNz / 2, 0.5f);
+    });
+    __syncwarp();   // every lane has finished reading gmbuf before Z' overwrites it
+    static_for<0, C::kQ>([&](auto qc) {
+      constexpr int q = decltype(qc)::value;
+      float2* zq = buf + q * C::kZS;
+      static_for<0, C::kPairIters>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        constexpr int pi = q * C::kPairIters + i;
+        const int k = lane + 32 * i;
+        float2 Bk = rot_inv(Xk[pi], rk), Bm = rot_inv(Xm[pi], rm);
+        if (k == 0) { Bk.y = 0.f; Bm.y = 0.f; }
+        float2 Zk, Zr;
+        split_inv(Bk, Bm, sm.ws[k], Zk, Zr);
+        if (k != 0) zq[C::kNz - k] = Zr;
+        zq[k] = Zk;
+      });
+      if (lane == 0) {
+        constexpr int k = C::kNz / 2;
+        const float2 B = rot_inv(Xs[q], k);
+        float2 Zk, Zr;
+        split_inv(B, B, sm.ws[k], Zk, Zr);
+        zq[k] = Zk;
+      }
+    });
+    __syncwarp();
+    fft_inverse<N>(v, buf, sm.tw, lane);
+    static_for<0, C::kQ>([&](auto qc) {
+      constexpr int q = decltype(qc)::value;
+      if (it.t0 + q < it.T) {
+        float* dst = a.gfb + (it.frame_base + it.t0 + q) * C::kWin;
+        static_for<0, C::kR>([&](auto rc) {
+          constexpr int r = decltype(rc)::value;
+          const int m = 2 * lane + 64 * r;
+          const float2 w = *reinterpret_cast<const float2*>(sm.win + m);
+          const float2 z = v[q * C::kR + r];
+          *reinterpret_cast<float2*>(dst + m) = make_float2(z.x * w.x, z.y * w.y);
+        });
+      }
+    });
+  }
+}
+
+// g_yg[b, j] = sum_res ( gp[h + j] + [1 <= j <= h] gp[h - j] + [T-2-h < j <= T-2] gp[h + 2T - 2 - j] ),
+// gp[P] = sum of the gradient frames covering padded position P  (adjoint of reflect pad + framing)
+struct GradOlaArgs {
+  int n_res;
+  const float* gfb[kMaxRes];
+  int n_fft[kMaxRes], hop[kMaxRes], Tf[kMaxRes];
+  int B;
+  long long T;
+  float* g;
+};
+__global__ void grad_ola_kernel(const GradOlaArgs a) {
+  const int b = blockIdx.y;
+  for (long long j = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; j < a.T;
+       j += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float acc = 0.f;
+    for (int r = 0; r < a.n_res; ++r) {
+      const int N = a.n_fft[r], h = N / 2, win = N / 2, hop = a.hop[r], Tf = a.Tf[r];
+      const float* fb = a.gfb[r] + static_cast<long long>(b) * Tf * win;
+      // padded position P -> offset coordinate P - N/4; positions outside every window contribute 0
+      auto gp = [&](long long P) -> float {
+        const long long pp = P - N / 4;
+        return pp >= 0 ? ola_gather(fb, Tf, hop, win, pp) : 0.f;
+      };
+      acc += gp(h + j);
+      if (j >= 1 && j <= h) acc += gp(h - j);
+      if (j > a.T - 2 - h && j <= a.T - 2) acc += gp(h + 2 * a.T - 2 - j);
+    }
+    a.g[static_cast<long long>(b) * a.T + j] = acc;
+  }
+}
+
+}  // namespace sb200

@@ -1,0 +1,215 @@
+// Immutable per-configuration tables (window, twiddles, banded mel filterbank) -- the B200-side
+// replacement of the reference's cached mel_basis / window_fn_torch (retunegan/audio.py:20,25-26,
+// 153-159; transtacos/audio.py:151-162).  Built once on the host in double precision, rounded to
+// float32 the way the reference's libraries do, and uploaded to the current device.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/spectral_b200.h"
+
+namespace sb200 {
+
+constexpr int kMaxMelRounds = 4;   // n_mel <= 128
+
+// Device view of a plan, passed by value to kernels.
+struct PlanDev {
+  int n_fft, win, hop, n_mel, F;
+  const float* window;    // [win]            analysis window
+  const float* wout;      // [win]            window / n_fft                      (synthesis, un-normalised OLA)
+  const float* wnorm;     // [win]            window / (n_fft * wss_interior[m])  (synthesis, interior frames)
+  const float* wsq;       // [win]            window^2
+  const float2* tw;       // [(2R-1)*32]      w_Nz^{k1*lane}, row k1-1
+  const float2* ws;       // [Nz/2+1]         -0.5i * w_N^k
+  // banded mel, ELL per round of 32 rows: melw[round_off[r] + it*32 + lane], it < round_len[r]
+  const float* melw;
+  const int* mel_lo;      // [32*rounds]      first non-zero column of each row (0 for padding rows)
+  int mel_rounds;
+  int mel_round_off[kMaxMelRounds];
+  int mel_round_len[kMaxMelRounds];
+  int melw_count;         // floats in melw
+  // column view (<= 2 non-zeros per column, consecutive rows): basis[r0[k], k] = c0[k], basis[r0[k]+1, k] = c1[k]
+  const int* col_r0;      // [F]
+  const float* col_c0;    // [F]
+  const float* col_c1;    // [F]
+};
+
+}  // namespace sb200
+
+struct sb200_plan {
+  sb200_config cfg;
+  sb200::PlanDev dev;
+  int device;
+  std::vector<float> mel_dense;   // [n_mel * F] float32, == librosa.filters.mel
+  std::vector<float> window_f32;  // [win]
+  std::vector<void*> allocs;
+};
+
+namespace sb200 {
+
+inline double hz_to_mel(double f, bool htk) {
+  if (htk) return 2595.0 * std::log10(1.0 + f / 700.0);
+  const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = std::log(6.4) / 27.0;
+  return f >= min_log_hz ? min_log_mel + std::log(f / min_log_hz) / logstep : f / f_sp;
+}
+inline double mel_to_hz(double m, bool htk) {
+  if (htk) return 700.0 * (std::pow(10.0, m / 2595.0) - 1.0);
+  const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = std::log(6.4) / 27.0;
+  return m >= min_log_mel ? min_log_hz * std::exp(logstep * (m - min_log_mel)) : f_sp * m;
+}
+
+// librosa.filters.mel(sr, n_fft, n_mels, fmin, fmax, htk, norm='slaney', dtype=float32)  
+inline std::vector<float> mel_filterbank(int sr, int n_fft, int n_mels, double fmin, double fmax, bool htk) {
+  const int F = 1 + n_fft / 2;
+  std::vector<double> mel_f(n_mels + 2);
+  const double m0 = hz_to_mel(fmin, htk), m1 = hz_to_mel(fmax, htk);
+  for (int i = 0; i < n_mels + 2; ++i) {
+    // np.linspace(m0, m1, n): start + i*step with the last point pinned to m1
+    const double step = (m1 - m0) / (n_mels + 1);
+    mel_f[i] = mel_to_hz(i == n_mels + 1 ? m1 : m0 + i * step, htk);
+  }
+  std::vector<float> w(static_cast<size_t>(n_mels) * F, 0.f);
+  for (int i = 0; i < n_mels; ++i) {
+    const double fd0 = mel_f[i + 1] - mel_f[i], fd1 = mel_f[i + 2] - mel_f[i + 1];
+    const double enorm = 2.0 / (mel_f[i + 2] - mel_f[i]);
+    for (int k = 0; k < F; ++k) {
+      const double f = (k == F - 1) ? sr / 2.0 : k * ((sr / 2.0) / (F - 1));   // np.linspace(0, sr/2, F)
+      const double lower = -(mel_f[i] - f) / fd0, upper = (mel_f[i + 2] - f) / fd1;
+      const float tri = static_cast<float>(std::fmax(0.0, std::fmin(lower, upper)));   // stored f32 ...
+      w[static_cast<size_t>(i) * F + k] = static_cast<float>(static_cast<double>(tri) * enorm);   // ... then *= enorm
+    }
+  }
+  return w;
+}
+
+// scipy.signal.get_window(name, M, fftbins=True) in double
+inline std::vector<double> make_window(int kind, int M) {
+  std::vector<double> w(M);
+  const double pi = 3.14159265358979323846;
+  for (int n = 0; n < M; ++n) {
+    const double t = 2.0 * pi * n / M;
+    switch (kind) {
+      case SB200_WIN_HANN: w[n] = 0.5 - 0.5 * std::cos(t); break;
+      case SB200_WIN_HAMMING: w[n] = 0.54 - 0.46 * std::cos(t); break;
+      case SB200_WIN_BLACKMAN: w[n] = 0.42 - 0.5 * std::cos(t) + 0.08 * std::cos(2 * t); break;
+      default: w[n] = (n <= M / 2) ? 2.0 * n / M : 2.0 - 2.0 * n / M; break;   // bartlett(M+1)[:-1]
+    }
+  }
+  return w;
+}
+
+template <class T>
+inline cudaError_t upload(sb200_plan* p, const std::vector<T>& h, const T** out) {
+  void* d = nullptr;
+  cudaError_t e = cudaMalloc(&d, std::max<size_t>(h.size(), 1) * sizeof(T));
+  if (e != cudaSuccess) return e;
+  p->allocs.push_back(d);
+  e = cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+  *out = static_cast<const T*>(d);
+  return e;
+}
+
+// Returns "" on success, otherwise an error message (status in *st).
+inline std::string build_plan(const sb200_config& c, sb200_plan* p, int* st) {
+  *st = SB200_ERR_INVALID;
+  if (c.n_fft != 2048 && c.n_fft != 1024 && c.n_fft != 512) {
+    *st = SB200_ERR_UNSUPPORTED;
+    return "n_fft must be 512, 1024 or 2048";
+  }
+  if (c.win_length != c.n_fft / 2) {
+    *st = SB200_ERR_UNSUPPORTED;
+    return "win_length must equal n_fft/2 (all reference configurations: hparam.py n_fft/win = 2048/1024, 1024/512, 512/256)";
+  }
+  if (c.hop_length < 2 || c.hop_length > c.win_length || (c.hop_length & 1)) return "hop_length must be even and in [2, win_length]";
+  if (c.n_mel < 1 || c.n_mel > 32 * kMaxMelRounds) return "n_mel must be in [1, 128]";
+  if (!(c.fmax < c.sample_rate / 2)) return "fmax must be < sample_rate // 2 (transtacos/audio.py:160)";
+  if (!(c.fmin >= 0 && c.fmin < c.fmax)) return "need 0 <= fmin < fmax";
+  if (c.window < 0 || c.window > 3) return "unknown window";
+  const double pi = 3.14159265358979323846;
+  const int N = c.n_fft, Nz = N / 2, win = c.win_length, hop = c.hop_length, F = N / 2 + 1, R2 = N / 64;
+  p->cfg = c;
+  cudaGetDevice(&p->device);
+  PlanDev& d = p->dev;
+  d.n_fft = N; d.win = win; d.hop = hop; d.n_mel = c.n_mel; d.F = F;
+
+  const std::vector<double> w = make_window(c.window, win);
+  std::vector<float> wf(win), wout(win), wnorm(win), wsq(win);
+  // interior window-sum-square at offset m (periodic in hop): sum over all shifts of w^2
+  std::vector<double> wss(win, 0.0);
+  for (int m = 0; m < win; ++m)
+    for (int j = m % hop; j < win; j += hop) wss[m] += w[j] * w[j];
+  for (int m = 0; m < win; ++m) {
+    wf[m] = static_cast<float>(w[m]);
+    wout[m] = static_cast<float>(w[m] / N);
+    wsq[m] = static_cast<float>(w[m] * w[m]);
+    wnorm[m] = static_cast<float>(wss[m] > 1.1754943508222875e-38 ? w[m] / (N * wss[m]) : w[m] / N);
+  }
+  p->window_f32 = wf;
+  std::vector<float2> tw(static_cast<size_t>(R2 - 1) * 32), ws(Nz / 2 + 2);
+  for (int k1 = 1; k1 < R2; ++k1)
+    for (int l = 0; l < 32; ++l) {
+      const double th = 2.0 * pi * ((k1 * l) % Nz) / Nz;
+      tw[(k1 - 1) * 32 + l] = make_float2(static_cast<float>(std::cos(th)), static_cast<float>(-std::sin(th)));
+    }
+  for (int k = 0; k <= Nz / 2; ++k) {
+    const double th = 2.0 * pi * k / N;   // -0.5i (cos - i sin) = -0.5 sin - 0.5i cos
+    ws[k] = make_float2(static_cast<float>(-0.5 * std::sin(th)), static_cast<float>(-0.5 * std::cos(th)));
+  }
+  ws[Nz / 2 + 1] = make_float2(0.f, 0.f);
+
+  p->mel_dense = mel_filterbank(c.sample_rate, N, c.n_mel, c.fmin, c.fmax, c.mel_htk != 0);
+  const std::vector<float>& mb = p->mel_dense;
+  const int rounds = (c.n_mel + 31) / 32;
+  d.mel_rounds = rounds;
+  std::vector<int> lo(32 * rounds, 0), len(32 * rounds, 0);
+  for (int m = 0; m < c.n_mel; ++m) {
+    int first = -1, last = -1;
+    for (int k = 0; k < F; ++k)
+      if (mb[static_cast<size_t>(m) * F + k] != 0.f) { if (first < 0) first = k; last = k; }
+    if (first >= 0) { lo[m] = first; len[m] = last - first + 1; }
+    if (last >= F - 1) return "mel filter reaches the Nyquist bin (requires fmax < sample_rate/2)";
+  }
+  std::vector<float> melw;
+  for (int r = 0; r < kMaxMelRounds; ++r) { d.mel_round_off[r] = 0; d.mel_round_len[r] = 0; }
+  for (int r = 0; r < rounds; ++r) {
+    int mx = 0;
+    for (int l = 0; l < 32; ++l) mx = std::max(mx, len[r * 32 + l]);
+    d.mel_round_off[r] = static_cast<int>(melw.size());
+    d.mel_round_len[r] = mx;
+    for (int it = 0; it < mx; ++it)
+      for (int l = 0; l < 32; ++l) {
+        const int m = r * 32 + l;
+        melw.push_back((m < c.n_mel && it < len[m]) ? mb[static_cast<size_t>(m) * F + lo[m] + it] : 0.f);
+      }
+  }
+  d.melw_count = static_cast<int>(melw.size());
+  std::vector<int> r0(F, 0);
+  std::vector<float> c0(F, 0.f), c1(F, 0.f);
+  for (int k = 0; k < F; ++k) {
+    int first = -1, cnt = 0;
+    for (int m = 0; m < c.n_mel; ++m)
+      if (mb[static_cast<size_t>(m) * F + k] != 0.f) { if (first < 0) first = m; ++cnt; }
+    if (cnt > 2) return "mel filterbank has more than two non-zeros in a column";
+    if (first >= 0) {
+      r0[k] = std::min(first, c.n_mel - 2 < 0 ? 0 : c.n_mel - 2);
+      c0[k] = mb[static_cast<size_t>(r0[k]) * F + k];
+      c1[k] = (r0[k] + 1 < c.n_mel) ? mb[static_cast<size_t>(r0[k] + 1) * F + k] : 0.f;
+    }
+  }
+  *st = SB200_ERR_CUDA;
+  cudaError_t e;
+#define SB200_UP(vec, field) \
+  if ((e = upload(p, vec, &d.field)) != cudaSuccess) return std::string("cuda upload: ") + cudaGetErrorString(e);
+  SB200_UP(wf, window) SB200_UP(wout, wout) SB200_UP(wnorm, wnorm) SB200_UP(wsq, wsq) SB200_UP(tw, tw) SB200_UP(ws, ws)
+  SB200_UP(melw, melw) SB200_UP(lo, mel_lo) SB200_UP(r0, col_r0) SB200_UP(c0, col_c0) SB200_UP(c1, col_c1)
+#undef SB200_UP
+  *st = SB200_OK;
+  return "";
+}
+
+}  // namespace sb200

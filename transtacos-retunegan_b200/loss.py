@@ -1,0 +1,133 @@
+"""Drop-in for ``multi_stft_loss`` (retunegan/models/loss.py:22-62) as a torch.autograd.Function over the
+fused forward / backward kernels.
+
+    multi_stft_loss(y, y_g, ret_loss=False, ret_specs=False)
+        -> loss | (stft_r, stft_g) | (loss, (stft_r, stft_g))
+
+``y`` (real audio) is treated as a constant, exactly how the reference uses it (retunegan/train.py:139,165:
+only ``y_g_hat`` carries gradients).  The spec stacks are ``[B, 2, F, T']`` views of frame-major buffers and
+carry gradients back to ``y_g`` (they feed the STFT discriminator, retunegan/train.py:172).
+Under DDP every rank holds its own segments; ``ddp_reduce=True`` averages the *reported* loss over ranks with
+one NCCL all-reduce of a scalar (the gradient all-reduce is DDP's own, on the generator parameters).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib, core
+from .config import RETUNEGAN, SpectralConfig
+
+hp: SpectralConfig = RETUNEGAN
+
+
+def set_hparams(cfg) -> None:
+    global hp
+    hp = cfg if isinstance(cfg, SpectralConfig) else SpectralConfig.from_hparam(cfg)
+
+
+def _ptr_array(tensors):
+    arr = (C.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = 0 if t is None else t.data_ptr()
+    return arr
+
+
+class _MultiStftFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, y_g, cfg: SpectralConfig, want_loss: bool, want_specs: bool):
+        lib = _lib.load()
+        dev = core.require_cuda()
+        yc = y.detach().to(device=dev, dtype=torch.float32).contiguous()
+        gc = y_g.detach().to(device=dev, dtype=torch.float32).contiguous()
+        B, T = gc.shape
+        plans = [core.get_plan(cfg, *p) for p in cfg.multi_stft_params]
+        n_res = len(plans)
+        handles = (C.c_void_p * n_res)(*[p.handle for p in plans])
+        saved_bytes = lib.sb200_mstft_saved_bytes(handles, n_res, B, T)
+        ws_bytes = lib.sb200_mstft_workspace_bytes(handles, n_res, B, T)
+        if saved_bytes < 0 or ws_bytes < 0:
+            _lib.check(-1)
+        saved = torch.empty(int(saved_bytes), device=dev, dtype=torch.uint8)
+        ws = core._workspace(int(ws_bytes), dev, "mstft")
+        loss = torch.empty((), device=dev, dtype=torch.float32) if want_loss else None
+        specs_r = specs_g = None
+        if want_specs:
+            specs_r = [torch.empty((B, 2, 1 + T // p.hop_length, p.F), device=dev, dtype=torch.float32) for p in plans]
+            specs_g = [torch.empty_like(s) for s in specs_r]
+        phd_phase = int(cfg.phd_input == "phase")
+        _lib.check(lib.sb200_mstft_forward(handles, n_res, core.ptr(yc), core.ptr(gc), B, T, phd_phase, core.ptr(loss),
+                                           _ptr_array(specs_r) if want_specs else None,
+                                           _ptr_array(specs_g) if want_specs else None,
+                                           core.ptr(saved), core.ptr(ws), core.stream_ptr()), "mstft_forward")
+        ctx.cfg, ctx.plans, ctx.handles = cfg, plans, handles
+        ctx.shape = (B, T)
+        ctx.want_loss, ctx.want_specs, ctx.phd_phase = want_loss, want_specs, phd_phase
+        ctx.in_shape, ctx.in_dtype = y_g.shape, y_g.dtype
+        ctx.save_for_backward(gc, saved)
+        outs = []
+        if want_loss:
+            outs.append(loss)
+        if want_specs:
+            outs += specs_r + specs_g
+            ctx.mark_non_differentiable(*specs_r)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        lib = _lib.load()
+        gc, saved = ctx.saved_tensors
+        B, T = ctx.shape
+        n_res = len(ctx.plans)
+        dev = gc.device
+        i = 0
+        g_loss = None
+        if ctx.want_loss:
+            g_loss = grads[0]
+            i = 1
+            if g_loss is not None:
+                g_loss = g_loss.to(device=dev, dtype=torch.float32).contiguous()
+        g_specs = None
+        if ctx.want_specs:
+            gs = grads[i + n_res: i + 2 * n_res]
+            if any(g is not None for g in gs):
+                g_specs = [None if g is None else g.to(torch.float32).contiguous() for g in gs]
+        g_yg = torch.empty((B, T), device=dev, dtype=torch.float32)
+        ws_bytes = lib.sb200_mstft_workspace_bytes(ctx.handles, n_res, B, T)
+        ws = core._workspace(int(ws_bytes), dev, "mstft")
+        _lib.check(lib.sb200_mstft_backward(ctx.handles, n_res, core.ptr(gc), B, T, ctx.phd_phase, core.ptr(g_loss),
+                                            _ptr_array(g_specs) if g_specs is not None else None, core.ptr(saved),
+                                            core.ptr(g_yg), core.ptr(ws), core.stream_ptr()), "mstft_backward")
+        return None, g_yg.to(ctx.in_dtype).reshape(ctx.in_shape), None, None, None
+
+
+def multi_stft_loss(y, y_g, ret_loss=False, ret_specs=False, ddp_reduce=False):
+    """retunegan/models/loss.py:22-62 (same arguments and return structure)."""
+    if not (ret_loss or ret_specs):
+        raise RuntimeError("multi_stft_loss: neither ret_loss nor ret_specs")   # bare `raise` at loss.py:62
+    if hp.phd_input not in ("stft", "phase"):
+        raise RuntimeError(f"unknown phd_input {hp.phd_input!r}")               # bare `raise` at loss.py:48
+    if y.dim() == 3:                                                            # [B, 1, T] => [B, T]
+        y, y_g = y.squeeze(1), y_g.squeeze(1)
+    if y.shape != y_g.shape or y.dim() != 2:
+        raise ValueError(f"expected matching [B, T] / [B, 1, T] inputs, got {tuple(y.shape)} and {tuple(y_g.shape)}")
+    outs = _MultiStftFn.apply(y, y_g, hp, bool(ret_loss), bool(ret_specs))
+    n_res = len(hp.multi_stft_params)
+    i = 0
+    loss = None
+    if ret_loss:
+        loss = outs[0]
+        i = 1
+        if ddp_reduce and torch.distributed.is_available() and torch.distributed.is_initialized():
+            red = loss.detach().clone()
+            torch.distributed.all_reduce(red, op=torch.distributed.ReduceOp.SUM)
+            loss = loss + (red / torch.distributed.get_world_size() - loss.detach())   # value = global mean, grad = local
+    if ret_specs:
+        stft_r = [s.transpose(2, 3) for s in outs[i:i + n_res]]
+        stft_g = [s.transpose(2, 3) for s in outs[i + n_res:i + 2 * n_res]]
+    if ret_loss and ret_specs:
+        return loss, (stft_r, stft_g)
+    elif ret_loss:
+        return loss
+    return (stft_r, stft_g)

@@ -1,0 +1,136 @@
+"""Drop-in for the spectral functions of ``retunegan/audio.py`` (same names, arguments, return arity).
+
+    get_mag(y, clamp_low=True) -> ln|STFT| [F,T] f32              retunegan/audio.py:116-120
+    get_mel(y, clamp_low=True) -> ln(mel @ |STFT|) [M,T] f32      retunegan/audio.py:123-128
+    mag_to_mel(x)              -> mel_basis @ x                   retunegan/audio.py:20-21
+    inv_mag(mag, wavlen=None)  -> Griffin-Lim wav (4 it, m=0.7)   retunegan/audio.py:131-147
+    get_stft_torch(y, n_fft, win_length, hop_length) -> S, M, P   retunegan/audio.py:150-170
+
+numpy in -> numpy out, torch in -> CUDA float32 tensors out.  Spectrograms are ``[F, T]`` views of
+frame-major memory.  Lists / ``[B, L]`` batches are additions over the reference.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import core
+from .config import RETUNEGAN, SpectralConfig
+from .transtacos_audio import _is_np, _split_fm, _to_frame_major, griffin_lim_amplitude
+
+hp: SpectralConfig = RETUNEGAN
+eps = 1e-5
+_phase_cache = {}
+
+
+def set_hparams(cfg) -> None:
+    global hp
+    hp = cfg if isinstance(cfg, SpectralConfig) else SpectralConfig.from_hparam(cfg)
+    _phase_cache.clear()
+
+
+def __getattr__(name):
+    if name == "mel_basis":   # retunegan/audio.py:20 -- built lazily here (needs the device library)
+        return core.get_plan(hp).mel_basis()
+    raise AttributeError(name)
+
+
+def ln_scale(clamp_low: bool) -> core.Scale:
+    """np.log(S.clip(min=eps)) / np.log(S) as a*log2(max(floor, x)) + b."""
+    return core.log_scale(math.log(2.0), 0.0, eps if clamp_low else 0.0)
+
+
+def _features(y, want_mag, want_mel, clamp_low):
+    as_np = _is_np(y)
+    plan = core.get_plan(hp)
+    batch = core.SignalBatch(plan, y)
+    sc = ln_scale(clamp_low)
+    mag, mel, _ = core.stft_features(plan, batch, 0.0, sc, sc, want_mag, want_mel)
+    single = not isinstance(y, (list, tuple)) and getattr(y, "ndim", 1) == 1
+    S = _split_fm(mag, batch.frames, plan.F, as_np, np.float32, single) if want_mag else None
+    M = _split_fm(mel, batch.frames, plan.n_mel, as_np, np.float32, single) if want_mel else None
+    return S, M
+
+
+def get_mag(y, clamp_low=True):
+    return _features(y, True, False, clamp_low)[0]
+
+
+def get_mel(y, clamp_low=True):
+    return _features(y, False, True, clamp_low)[1]
+
+
+def get_mag_mel(y, clamp_low=True):
+    """Addition: both features from one launch (the reference computes the STFT twice)."""
+    return _features(y, True, True, clamp_low)
+
+
+def mag_to_mel(x):
+    """np.dot(mel_basis, x) on whatever it is given, [F,T] -> [M,T] (retunegan/audio.py:21)."""
+    plan = core.get_plan(hp)
+    if x.shape[0] != plan.F:
+        raise ValueError(f"shapes ({plan.n_mel},{plan.F}) and {tuple(x.shape)} not aligned")   # np.dot's complaint
+    out = core.mel_project(plan, _to_frame_major(x))
+    return out.cpu().numpy().T if isinstance(x, np.ndarray) else out.t()
+
+
+def _seeded_phase(F: int, T: int) -> torch.Tensor:
+    """librosa.griffinlim(random_state=int) draws RandomState(seed).rand(F, T) afresh on every call, so every
+    utterance of a given length starts from the same phase: cache it on the device."""
+    key = (hp.randseed, F, T, torch.cuda.current_device())
+    ph = _phase_cache.get(key)
+    if ph is None:
+        ph = _to_frame_major(np.random.RandomState(hp.randseed).rand(F, T))
+        _phase_cache[key] = ph
+    return ph
+
+
+def _griffinlim(S, wavlen=None, init_phase=None):
+    """retunegan/audio.py:131-136 on an amplitude spectrogram S [F,T]."""
+    S_fm = core.spec_to_amplitude(_to_frame_major(S), 2, power=hp.gl_power) if hp.gl_power else _to_frame_major(S)
+    T = S.shape[1]
+    ph = _seeded_phase(S.shape[0], T) if init_phase is None else init_phase
+    y = griffin_lim_amplitude(S_fm, T, ph, hp.gl_iters, hp.gl_momentum, 1, wavlen, 0.0, hp)
+    return y.cpu().numpy().astype(np.float32) if isinstance(S, np.ndarray) else y
+
+
+def inv_mag(mag, wavlen=None, init_phase=None):
+    """retunegan/audio.py:139-147: exp, prepend a zero DC row if F == n_freq-1, S**gl_power, fast Griffin-Lim."""
+    F, T = mag.shape
+    x = _to_frame_major(mag)
+    S = core.spec_to_amplitude(x, 1, power=hp.gl_power if hp.gl_power else 1.0)
+    if F == hp.n_freq - 1:
+        S = torch.cat([torch.zeros(T, 1, device=S.device), S], dim=1).contiguous()
+    elif F != hp.n_freq:
+        raise ValueError(f"expected {hp.n_freq} or {hp.n_freq - 1} frequency rows, got {F}")
+    ph = _seeded_phase(hp.n_freq, T) if init_phase is None else init_phase
+    y = griffin_lim_amplitude(S, T, ph, hp.gl_iters, hp.gl_momentum, 1, wavlen, 0.0, hp)
+    if wavlen:
+        assert y.numel() == wavlen
+    return y.cpu().numpy().astype(np.float32) if isinstance(mag, np.ndarray) else y
+
+
+def get_stft_torch(y, n_fft, win_length, hop_length):
+    """S = |D + 1e-9|, M = mel_basis @ S, P = angle(D) for y [B, T] (retunegan/audio.py:150-170).
+
+    Outputs are [B, F, T'] / [B, n_mel, T'] views of frame-major buffers.  This standalone entry is not
+    differentiable; gradients flow through ``multi_stft_loss`` (the only differentiable use in the reference).
+    """
+    if not isinstance(y, torch.Tensor):
+        raise TypeError("get_stft_torch expects a torch.Tensor [B, T]")
+    if y.dim() == 1:
+        y = y.unsqueeze(0)
+    if y.shape[-1] <= n_fft // 2:
+        raise RuntimeError(f"Argument #4: Padding size should be less than the corresponding input dimension, "
+                           f"but got: padding ({n_fft // 2}, {n_fft // 2}) at dimension 2 of input")   # torch.stft
+    plan = core.get_plan(hp, n_fft, win_length, hop_length)
+    batch = core.SignalBatch(plan, y)
+    _, _, D = core.stft_features(plan, batch, 0.0, None, None, False, False, True)
+    B, Tf = batch.B, int(batch.frames[0])
+    S = torch.abs(D + 1e-9)
+    M = core.mel_project(plan, S.contiguous())
+    P = torch.angle(D)
+    return (S.view(B, Tf, plan.F).transpose(1, 2), M.view(B, Tf, plan.n_mel).transpose(1, 2),
+            P.view(B, Tf, plan.F).transpose(1, 2))

@@ -1,0 +1,178 @@
+"""Drop-in for the spectral functions of ``transtacos/audio.py`` (same names, arguments, return arity).
+
+    get_specs(y) -> (mag_norm [F,T], mel_norm [M,T])          transtacos/audio.py:73-77
+    inv_spec(spec) -> wav                                      transtacos/audio.py:93-97
+    preemphasis / inv_preemphasis / spec_to_natural_scale / fix_zero_DC / align_wav
+
+numpy in -> numpy out with the reference's dtypes (float64 features, float32 wav); torch in -> float32
+CUDA tensors out.  Every spectrogram is returned as an ``[F, T]`` view of frame-major memory (strides
+(1, F)), the layout ``librosa.stft`` itself allocates (order='F').  Additions over the reference:
+batched input (``[B, L]`` tensor/array or a list of ragged utterances -> list of per-utterance results),
+``init_phase=`` / ``n_iter=`` on ``inv_spec``.  Configuration lives in the module attribute ``hp``
+(a ``SpectralConfig``; the reference reads a global ``hparam`` module) -- use ``set_hparams``.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import core
+from .config import TRANSTACOS, SpectralConfig
+
+hp: SpectralConfig = TRANSTACOS
+eps = 1e-5
+
+
+def set_hparams(cfg) -> None:
+    """Install a SpectralConfig or a reference-style ``hparam`` module."""
+    global hp
+    hp = cfg if isinstance(cfg, SpectralConfig) else SpectralConfig.from_hparam(cfg, gl_momentum=0.0)
+
+
+def _is_np(x) -> bool:
+    return isinstance(x, np.ndarray) or (isinstance(x, (list, tuple)) and len(x) > 0 and isinstance(x[0], np.ndarray))
+
+
+def db_norm_scale(cfg: SpectralConfig) -> core.Scale:
+    """_normalize(_amp_to_db(x) - ref_level_db) as a*log2(max(1e-5, x)) + b (transtacos/audio.py:177-193)."""
+    a = 2 * cfg.max_abs_value * 20 * math.log10(2.0) / -cfg.min_level_db
+    b = 2 * cfg.max_abs_value * ((-cfg.ref_level_db - cfg.min_level_db) / -cfg.min_level_db) - cfg.max_abs_value
+    return core.log_scale(a, b, 1e-5)
+
+
+def _split_fm(t: torch.Tensor, frames, width: int, as_numpy: bool, np_dtype, single: bool):
+    """[total_frames, width] frame-major -> per-utterance [width, T] views (numpy: Fortran-ordered)."""
+    if as_numpy:
+        host = t.cpu().numpy()
+        if np_dtype is not None and host.dtype != np_dtype:
+            host = host.astype(np_dtype)
+    outs, o = [], 0
+    for T in frames:
+        T = int(T)
+        outs.append((host[o:o + T].T if as_numpy else t[o:o + T].t()))
+        o += T
+    return outs[0] if single else outs
+
+
+def align_wav(wav, r=None):
+    """transtacos/audio.py:52-56 -- pad to a multiple of hop_length."""
+    r = hp.hop_length if r is None else r
+    d = len(wav) % r
+    if d != 0:
+        wav = np.pad(wav, (0, (r - d))) if isinstance(wav, np.ndarray) else torch.nn.functional.pad(wav, (0, r - d))
+    return wav
+
+
+def preemphasis(x):
+    """x[n] - k*x[n-1], zero initial state (transtacos/audio.py:64-66; scipy promotes to float64)."""
+    t = core.to_device_f32(x)
+    out = core.preemphasis(t.reshape(1, -1) if t.dim() == 1 else t, hp.preemphasis).reshape(t.shape)
+    return out.cpu().numpy().astype(np.float64) if isinstance(x, np.ndarray) else out
+
+
+def inv_preemphasis(x):
+    """y[n] = x[n] + k*y[n-1] (transtacos/audio.py:69-70)."""
+    t = core.to_device_f32(x)
+    out = core.inv_preemphasis(t.reshape(1, -1) if t.dim() == 1 else t, hp.preemphasis).reshape(t.shape)
+    return out.cpu().numpy().astype(np.float64) if isinstance(x, np.ndarray) else out
+
+
+def get_specs(y, out_dtype=None):
+    """(normalised dB magnitude [F,T], normalised dB mel [M,T]) -- transtacos/audio.py:73-77."""
+    as_np = _is_np(y)
+    plan = core.get_plan(hp)
+    batch = core.SignalBatch(plan, y)
+    sc = db_norm_scale(hp)
+    mag, mel, _ = core.stft_features(plan, batch, preemph=hp.preemphasis, mag_scale=sc, mel_scale=sc)
+    single = not isinstance(y, (list, tuple)) and getattr(y, "ndim", 1) == 1
+    dt = (np.float64 if out_dtype is None else out_dtype) if as_np else None
+    S = _split_fm(mag, batch.frames, plan.F, as_np, dt, single)
+    M = _split_fm(mel, batch.frames, plan.n_mel, as_np, dt, single)
+    return S, M
+
+
+def _amp_to_db(x):
+    return 20 * np.log10(np.maximum(1e-5, x)) if isinstance(x, np.ndarray) else 20 * torch.log10(x.clamp_min(1e-5))
+
+
+def _db_to_amp(x):
+    return np.power(10.0, x * 0.05) if isinstance(x, np.ndarray) else torch.pow(10.0, x * 0.05)
+
+
+def _normalize(S):
+    return 2 * hp.max_abs_value * ((S - hp.min_level_db) / -hp.min_level_db) - hp.max_abs_value
+
+
+def _denormalize(S):
+    return ((S + hp.max_abs_value) * -hp.min_level_db) / (2 * hp.max_abs_value) + hp.min_level_db
+
+
+def spec_to_natural_scale(spec):
+    """transtacos/audio.py:80-82 (host-side element-wise helper, kept for API parity)."""
+    return _db_to_amp(_denormalize(spec) + hp.ref_level_db)
+
+
+def fix_zero_DC(S):
+    """transtacos/audio.py:85-90 -- prepend a DC row S.min()*1e-2 when F == n_freq - 1."""
+    F, T = S.shape
+    if F == hp.n_freq - 1:
+        if isinstance(S, np.ndarray):
+            S = np.concatenate([np.ones([1, T]) * S.min() * 1e-2, S], axis=0)
+        else:
+            S = torch.cat([torch.ones(1, T, device=S.device, dtype=S.dtype) * S.min() * 1e-2, S], dim=0)
+    return S
+
+
+def _to_frame_major(spec) -> torch.Tensor:
+    """[F, T] (numpy any order / torch any strides) -> contiguous float32 CUDA [T, F]."""
+    if isinstance(spec, np.ndarray):
+        return core.to_device_f32(np.ascontiguousarray(spec.T, dtype=np.float32))
+    return spec.detach().to(device=core.require_cuda(), dtype=torch.float32).t().contiguous()
+
+
+def draw_phase(F: int, T: int, seed=None) -> np.ndarray:
+    """The reference's initial-phase draw: ``np.random.rand(F, T)`` from the global RNG
+    (transtacos/audio.py:134) or a fresh ``RandomState(seed)`` (librosa.griffinlim random_state=int)."""
+    rng = np.random if seed is None else np.random.RandomState(seed)
+    return rng.rand(F, T)
+
+
+def griffin_lim_amplitude(S_fm: torch.Tensor, T: int, init_phase, n_iter: int, momentum: float, form: int,
+                          length, inv_preemph: float, cfg: SpectralConfig, seed=None) -> torch.Tensor:
+    """Shared driver: S_fm [T, F] amplitudes already raised to gl_power -> wav (float32 CUDA)."""
+    plan = core.get_plan(cfg)
+    if init_phase is None:
+        init_phase = draw_phase(plan.F, T, seed)
+    if isinstance(init_phase, str) and init_phase == "device":
+        ph = torch.rand((T, plan.F), device=S_fm.device, dtype=torch.float32)
+    else:
+        ph = _to_frame_major(init_phase)
+    fb = core.FramesBatch(plan, [T], None if not length else [int(length)], S_fm.device)
+    return core.griffinlim(plan, S_fm, ph, fb, n_iter, momentum, form, inv_preemph)
+
+
+def _griffin_lim(S, init_phase=None, n_iter=None):
+    """transtacos/audio.py:130-140 -- 'angle' form, no momentum; returns the raw Griffin-Lim signal."""
+    S_fm = _to_frame_major(np.abs(S) if isinstance(S, np.ndarray) else S.abs())
+    y = griffin_lim_amplitude(S_fm, S.shape[1], init_phase, hp.gl_iters if n_iter is None else n_iter, 0.0, 0, None,
+                              0.0, hp)
+    return y.cpu().numpy().astype(np.float64) if isinstance(S, np.ndarray) else y
+
+
+def inv_spec(spec, init_phase=None, n_iter=None):
+    """transtacos/audio.py:93-97 -- denormalise, fix DC, S**gl_power, Griffin-Lim (30 it), de-emphasis."""
+    F, T = spec.shape
+    x = _to_frame_major(spec)                                     # [T, F or F-1]
+    if F == hp.n_freq:
+        S = core.spec_to_amplitude(x, 0, hp.max_abs_value, hp.min_level_db, hp.ref_level_db, hp.gl_power)
+    elif F == hp.n_freq - 1:                                      # fix_zero_DC acts on the natural scale, before the power
+        S = core.spec_to_amplitude(x, 0, hp.max_abs_value, hp.min_level_db, hp.ref_level_db, 1.0)
+        S = torch.cat([(S.min() * 1e-2).expand(T, 1), S], dim=1).contiguous()
+        S = core.spec_to_amplitude(S, 2, power=hp.gl_power)
+    else:
+        raise ValueError(f"expected {hp.n_freq} or {hp.n_freq - 1} frequency rows, got {F}")
+    wav = griffin_lim_amplitude(S, T, init_phase, hp.gl_iters if n_iter is None else n_iter, 0.0, 0, None,
+                                hp.preemphasis, hp)
+    return wav.cpu().numpy().astype(np.float32) if isinstance(spec, np.ndarray) else wav
