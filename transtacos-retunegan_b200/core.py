@@ -273,3 +273,75 @@ def griffinlim(plan: Plan, S_fm: torch.Tensor, phase_fm: torch.Tensor, fb: Frame
         b = Batch(fb.B, 0, 0, fb.tables[0].data_ptr(), fb.tables[1].data_ptr(), None, None, 0, 0)
         check(lib.sb200_inv_preemphasis(ptr(y), C.byref(b), float(inv_preemph), ptr(y), stream_ptr()))
     return y
+
+
+class HostFeaturePipeline:
+    """Host-resident batches: overlap H2D copies, the fused STFT+mel launch and D2H copies chunk by chunk.
+
+    For a uniform ``[B, L]`` batch living in (ideally pinned) host memory.  Three CUDA streams and a ring of
+    ``depth`` device slots; every chunk is one ``sb200_stft_features`` launch.  This is what the numpy-facing
+    ``get_specs`` / ``get_mag`` use for 2-D host input, and what bench.py times as the end-to-end number.
+    """
+
+    def __init__(self, plan: Plan, L: int, chunk: int = 8, depth: int = 3):
+        self.plan, self.L, self.chunk, self.depth = plan, int(L), int(chunk), int(depth)
+        dev = require_cuda()
+        self.T = 1 + self.L // plan.hop_length
+        self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
+        self.x = [torch.empty((chunk, self.L), device=dev, dtype=torch.float32) for _ in range(depth)]
+        self.mag = [torch.empty((chunk * self.T, plan.F), device=dev, dtype=torch.float32) for _ in range(depth)]
+        self.mel = [torch.empty((chunk * self.T, plan.n_mel), device=dev, dtype=torch.float32) for _ in range(depth)]
+        self.ev_in = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_run = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_out = [torch.cuda.Event() for _ in range(depth)]
+        self.used = [False] * depth
+
+    def run(self, y_host: torch.Tensor, mag_host: Optional[torch.Tensor], mel_host: Optional[torch.Tensor],
+            preemph: float, mag_scale: Scale, mel_scale: Scale) -> None:
+        """y_host [B, L] float32 CPU; mag_host [B*T, F] / mel_host [B*T, n_mel] float32 CPU (None = not wanted).
+        Returns after all copies have completed."""
+        lib = _lib.load()
+        B = y_host.shape[0]
+        plan, T = self.plan, self.T
+        cur = torch.cuda.current_stream()
+        self.s_in.wait_stream(cur)
+        for c, b0 in enumerate(range(0, B, self.chunk)):
+            n = min(self.chunk, B - b0)
+            s = c % self.depth
+            with torch.cuda.stream(self.s_in):
+                if self.used[s]:
+                    self.s_in.wait_event(self.ev_run[s])          # slot's previous launch has consumed x[s]
+                self.x[s][:n].copy_(y_host[b0:b0 + n], non_blocking=True)
+                self.ev_in[s].record(self.s_in)
+            with torch.cuda.stream(self.s_run):
+                self.s_run.wait_event(self.ev_in[s])
+                if self.used[s]:
+                    self.s_run.wait_event(self.ev_out[s])         # slot's previous outputs have left the device
+                bc = Batch(n, self.L, self.L, None, None, None, None, 0, 0)
+                check(lib.sb200_stft_features(plan.handle, ptr(self.x[s]), C.byref(bc), float(preemph), mag_scale,
+                                              mel_scale, ptr(self.mag[s]) if mag_host is not None else None,
+                                              ptr(self.mel[s]) if mel_host is not None else None, None,
+                                              C.c_void_p(self.s_run.cuda_stream)), "stft_features")
+                self.ev_run[s].record(self.s_run)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(self.ev_run[s])
+                if mag_host is not None:
+                    mag_host[b0 * T:(b0 + n) * T].copy_(self.mag[s][:n * T], non_blocking=True)
+                if mel_host is not None:
+                    mel_host[b0 * T:(b0 + n) * T].copy_(self.mel[s][:n * T], non_blocking=True)
+                self.ev_out[s].record(self.s_out)
+            self.used[s] = True
+        self.s_out.synchronize()
+        cur.wait_stream(self.s_out)
+
+
+_pipelines = {}
+
+
+def host_feature_pipeline(plan: Plan, L: int, chunk: int = 8) -> HostFeaturePipeline:
+    key = (plan.key, plan.device_index, int(L), int(chunk))
+    p = _pipelines.get(key)
+    if p is None:
+        p = HostFeaturePipeline(plan, L, chunk)
+        _pipelines[key] = p
+    return p

@@ -18,7 +18,7 @@ import torch
 
 from . import core
 from .config import RETUNEGAN, SpectralConfig
-from .transtacos_audio import _is_np, _split_fm, _to_frame_major, griffin_lim_amplitude
+from .transtacos_audio import _is_np, _split_fm, _to_frame_major, griffin_lim_amplitude, phase_to_frame_major
 
 hp: SpectralConfig = RETUNEGAN
 eps = 1e-5
@@ -91,7 +91,7 @@ def _griffinlim(S, wavlen=None, init_phase=None):
     """retunegan/audio.py:131-136 on an amplitude spectrogram S [F,T]."""
     S_fm = core.spec_to_amplitude(_to_frame_major(S), 2, power=hp.gl_power) if hp.gl_power else _to_frame_major(S)
     T = S.shape[1]
-    ph = _seeded_phase(S.shape[0], T) if init_phase is None else init_phase
+    ph = _seeded_phase(S.shape[0], T) if init_phase is None else phase_to_frame_major(init_phase, S.shape[0], T, S_fm.device)
     y = griffin_lim_amplitude(S_fm, T, ph, hp.gl_iters, hp.gl_momentum, 1, wavlen, 0.0, hp)
     return y.cpu().numpy().astype(np.float32) if isinstance(S, np.ndarray) else y
 
@@ -105,7 +105,7 @@ def inv_mag(mag, wavlen=None, init_phase=None):
         S = torch.cat([torch.zeros(T, 1, device=S.device), S], dim=1).contiguous()
     elif F != hp.n_freq:
         raise ValueError(f"expected {hp.n_freq} or {hp.n_freq - 1} frequency rows, got {F}")
-    ph = _seeded_phase(hp.n_freq, T) if init_phase is None else init_phase
+    ph = _seeded_phase(hp.n_freq, T) if init_phase is None else phase_to_frame_major(init_phase, hp.n_freq, T, S.device)
     y = griffin_lim_amplitude(S, T, ph, hp.gl_iters, hp.gl_momentum, 1, wavlen, 0.0, hp)
     if wavlen:
         assert y.numel() == wavlen

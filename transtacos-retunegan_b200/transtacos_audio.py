@@ -79,17 +79,68 @@ def inv_preemphasis(x):
     return out.cpu().numpy().astype(np.float64) if isinstance(x, np.ndarray) else out
 
 
-def get_specs(y, out_dtype=None):
-    """(normalised dB magnitude [F,T], normalised dB mel [M,T]) -- transtacos/audio.py:73-77."""
+def _host_batch(y):
+    """A uniform [B, L] batch living in host memory (numpy or CPU tensor) -> CPU float32 tensor, else None."""
+    if isinstance(y, np.ndarray) and y.ndim == 2 and y.shape[0] > 1:
+        return torch.from_numpy(np.ascontiguousarray(y, dtype=np.float32))
+    if isinstance(y, torch.Tensor) and not y.is_cuda and y.dim() == 2 and y.shape[0] > 1:
+        return y.detach().to(torch.float32).contiguous()
+    return None
+
+
+def features_host(cfg: SpectralConfig, y_host: torch.Tensor, preemph, mag_scale, mel_scale, want_mag=True,
+                  want_mel=True, out=None, chunk=8):
+    """Host-resident [B, L] batch -> host features through the chunked copy/compute pipeline.
+    ``out=(mag [B*T, F], mel [B*T, n_mel])`` lets the caller supply (pinned) destinations; returns CPU tensors."""
+    plan = core.get_plan(cfg)
+    B, L = y_host.shape
+    if L < plan.n_fft // 4 + 1:
+        raise ValueError("signal shorter than n_fft/4 + 1 samples: reflect padding undefined")
+    T = 1 + L // plan.hop_length
+    mag = mel = None
+    if out is not None:
+        mag, mel = out
+    else:
+        if want_mag:
+            mag = torch.empty((B * T, plan.F), dtype=torch.float32)
+        if want_mel:
+            mel = torch.empty((B * T, plan.n_mel), dtype=torch.float32)
+    core.host_feature_pipeline(plan, L, chunk).run(y_host, mag, mel, preemph, mag_scale, mel_scale)
+    return mag, mel, T
+
+
+def get_specs(y, out_dtype=None, out=None):
+    """(normalised dB magnitude [F,T], normalised dB mel [M,T]) -- transtacos/audio.py:73-77.
+
+    Host input (numpy / CPU tensor) -> host output; ``out_dtype`` defaults to float32, the precision the kernels
+    compute in (the reference returns float64 only because scipy's lfilter promotes; pass np.float64 to get
+    that dtype).  CUDA tensor in -> CUDA float32 views out.  ``[B, L]`` host batches stream through pinned-copy /
+    launch / copy-back overlap; ``out=(mag [B*T, F], mel [B*T, M])`` supplies (pinned) CPU destination tensors.
+    """
+    sc = db_norm_scale(hp)
+    yh = _host_batch(y)
+    if yh is not None:
+        if isinstance(y, np.ndarray) and not np.isfinite(y).all():
+            raise ValueError("Audio buffer is not finite everywhere")
+        mag, mel, T = features_host(hp, yh, hp.preemphasis, sc, sc, out=out)
+        B = yh.shape[0]
+        if isinstance(y, np.ndarray):
+            dt = np.float32 if out_dtype is None else out_dtype
+            S = mag.numpy().astype(dt, copy=False).reshape(B, T, -1).transpose(0, 2, 1)
+            M = mel.numpy().astype(dt, copy=False).reshape(B, T, -1).transpose(0, 2, 1)
+            return S, M
+        return mag.view(B, T, -1).transpose(1, 2), mel.view(B, T, -1).transpose(1, 2)
     as_np = _is_np(y)
     plan = core.get_plan(hp)
     batch = core.SignalBatch(plan, y)
-    sc = db_norm_scale(hp)
     mag, mel, _ = core.stft_features(plan, batch, preemph=hp.preemphasis, mag_scale=sc, mel_scale=sc)
     single = not isinstance(y, (list, tuple)) and getattr(y, "ndim", 1) == 1
-    dt = (np.float64 if out_dtype is None else out_dtype) if as_np else None
+    dt = (np.float32 if out_dtype is None else out_dtype) if as_np else None
     S = _split_fm(mag, batch.frames, plan.F, as_np, dt, single)
     M = _split_fm(mel, batch.frames, plan.n_mel, as_np, dt, single)
+    if not single and not isinstance(y, (list, tuple)):      # uniform [B, L] CUDA batch -> [B, F, T] views
+        S = torch.stack(S) if not as_np else np.stack(S)
+        M = torch.stack(M) if not as_np else np.stack(M)
     return S, M
 
 
@@ -139,25 +190,33 @@ def draw_phase(F: int, T: int, seed=None) -> np.ndarray:
     return rng.rand(F, T)
 
 
-def griffin_lim_amplitude(S_fm: torch.Tensor, T: int, init_phase, n_iter: int, momentum: float, form: int,
-                          length, inv_preemph: float, cfg: SpectralConfig, seed=None) -> torch.Tensor:
-    """Shared driver: S_fm [T, F] amplitudes already raised to gl_power -> wav (float32 CUDA)."""
-    plan = core.get_plan(cfg)
+def phase_to_frame_major(init_phase, F: int, T: int, device, seed=None) -> torch.Tensor:
+    """User-facing ``init_phase`` ([F, T] values in [0,1) like the reference's rand draw, None, or 'device')
+    -> float32 CUDA [T, F]."""
     if init_phase is None:
-        init_phase = draw_phase(plan.F, T, seed)
-    if isinstance(init_phase, str) and init_phase == "device":
-        ph = torch.rand((T, plan.F), device=S_fm.device, dtype=torch.float32)
-    else:
-        ph = _to_frame_major(init_phase)
+        init_phase = draw_phase(F, T, seed)
+    if isinstance(init_phase, str):
+        if init_phase != "device":
+            raise ValueError("init_phase must be an [F, T] array, None or 'device'")
+        return torch.rand((T, F), device=device, dtype=torch.float32)   # throughput mode: on-device counter RNG
+    if tuple(init_phase.shape) != (F, T):
+        raise ValueError(f"init_phase must have shape {(F, T)}, got {tuple(init_phase.shape)}")
+    return _to_frame_major(init_phase)
+
+
+def griffin_lim_amplitude(S_fm: torch.Tensor, T: int, phase_fm: torch.Tensor, n_iter: int, momentum: float, form: int,
+                          length, inv_preemph: float, cfg: SpectralConfig) -> torch.Tensor:
+    """Shared driver: S_fm [T, F] amplitudes already raised to gl_power, phase_fm [T, F] -> wav (float32 CUDA)."""
+    plan = core.get_plan(cfg)
     fb = core.FramesBatch(plan, [T], None if not length else [int(length)], S_fm.device)
-    return core.griffinlim(plan, S_fm, ph, fb, n_iter, momentum, form, inv_preemph)
+    return core.griffinlim(plan, S_fm, phase_fm, fb, n_iter, momentum, form, inv_preemph)
 
 
 def _griffin_lim(S, init_phase=None, n_iter=None):
     """transtacos/audio.py:130-140 -- 'angle' form, no momentum; returns the raw Griffin-Lim signal."""
     S_fm = _to_frame_major(np.abs(S) if isinstance(S, np.ndarray) else S.abs())
-    y = griffin_lim_amplitude(S_fm, S.shape[1], init_phase, hp.gl_iters if n_iter is None else n_iter, 0.0, 0, None,
-                              0.0, hp)
+    ph = phase_to_frame_major(init_phase, S.shape[0], S.shape[1], S_fm.device)
+    y = griffin_lim_amplitude(S_fm, S.shape[1], ph, hp.gl_iters if n_iter is None else n_iter, 0.0, 0, None, 0.0, hp)
     return y.cpu().numpy().astype(np.float64) if isinstance(S, np.ndarray) else y
 
 
@@ -173,6 +232,6 @@ def inv_spec(spec, init_phase=None, n_iter=None):
         S = core.spec_to_amplitude(S, 2, power=hp.gl_power)
     else:
         raise ValueError(f"expected {hp.n_freq} or {hp.n_freq - 1} frequency rows, got {F}")
-    wav = griffin_lim_amplitude(S, T, init_phase, hp.gl_iters if n_iter is None else n_iter, 0.0, 0, None,
-                                hp.preemphasis, hp)
+    ph = phase_to_frame_major(init_phase, hp.n_freq, T, S.device)
+    wav = griffin_lim_amplitude(S, T, ph, hp.gl_iters if n_iter is None else n_iter, 0.0, 0, None, hp.preemphasis, hp)
     return wav.cpu().numpy().astype(np.float32) if isinstance(spec, np.ndarray) else wav
