@@ -87,7 +87,7 @@ int64_t sb200_launch_count(void);
  * Created on the current CUDA device. */
 int sb200_plan_create(const sb200_config* cfg, sb200_plan** out);
 int sb200_plan_destroy(sb200_plan* plan);
-int sb200_plan_frames_per_pass(const sb200_plan* plan);             /* 2048 / n_fft */
+int sb200_plan_frames_per_pass(const sb200_plan* plan);             /* frames per work item: 4096 / n_fft */
 /* Dense float32 filterbank [n_mel, F] == librosa.filters.mel(sr, n_fft, n_mel, fmin, fmax) (host buffer). */
 int sb200_plan_mel_basis_host(const sb200_plan* plan, float* out_host);
 /* float32 window [win_length] (host buffer). */

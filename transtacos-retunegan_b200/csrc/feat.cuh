@@ -228,7 +228,8 @@ __global__ void __launch_bounds__(kFeatWarps * 32, 2) stft_feature_kernel(const 
   const long long warps_total = static_cast<long long>(gridDim.x) * kFeatWarps;
   for (long long item = static_cast<long long>(blockIdx.x) * kFeatWarps + warp; item < a.bd.total_items;
        item += warps_total) {
-    const Item it = decode_item(a.bd, item, C::kQ);
+    Item it = decode_item(a.bd, item, 2 * C::kQ);   // an item is 2Q frames (packed-engine granularity): two passes
+    for (int half = 0; half < 2 && it.t0 < it.T; ++half, it.t0 += C::kQ) {
     float2 v[32];
     load_frames<N, PRE>(v, a.x + it.sig_base, it.L, it.t0, it.T, p.hop, a.pre, sm.win, lane);
     fft_forward<N>(v, buf, sm.tw, lane);
@@ -275,6 +276,7 @@ __global__ void __launch_bounds__(kFeatWarps * 32, 2) stft_feature_kernel(const 
       });
     }
     __syncwarp();
+    }
   }
 }
 

@@ -1,0 +1,257 @@
+// Fused STFT-magnitude + mel feature kernel on the packed FFT engine (fft2.cuh):
+//   [pre-emphasis ->] reflect pad -> frame gather -> window -> real FFT -> |.|^2 -> banded mel -> dB-normalise / ln / raw
+//   transtacos/audio.py:73-77 get_specs;  retunegan/audio.py:116-128 get_mag / get_mel.
+// One warp owns one item = 4096/n_fft consecutive frames of one utterance, processed as frame PAIRS packed
+// in the halves of 64-bit registers (2 frames for n_fft 2048).  A CTA is 8 warps sharing the plan tables in
+// shared memory, each warp with a private 16.5 KB exchange buffer; the grid is persistent (1 CTA per SM).
+// Log-scaled magnitudes are taken from |A|^2 directly (a/2 log2 max(floor^2, p) + b): no sqrt on that path.
+#pragma once
+#include "feat.cuh"
+#include "fft2.cuh"
+
+namespace sb200 {
+
+constexpr int kFeat2Warps = 8;
+
+template <int N>
+struct Smem2 {
+  using C = Fft2Cfg<N>;
+  uint4* xbufs;   // [warps][32*33] exchange buffers (first: 16-byte aligned)
+  float* win;     // [win] 0.5 * analysis window
+  float2* tw;     // [kTwCount]
+  float2* sp2;    // [17*32]
+  float* melw;    // [melw_count]
+  int* mel_lo;    // [32*rounds]
+  __host__ __device__ static size_t bytes(int melw_count, int mel_rounds, int warps) {
+    return static_cast<size_t>(warps) * C::kXBytes + sizeof(float) * C::kWin + sizeof(float2) * (C::kTwCount + 17 * 32) +
+           sizeof(float) * melw_count + sizeof(int) * 32 * mel_rounds;
+  }
+  __device__ __forceinline__ void carve(unsigned char* raw, const PlanDev& p, int warps) {
+    xbufs = reinterpret_cast<uint4*>(raw);
+    win = reinterpret_cast<float*>(raw + static_cast<size_t>(warps) * C::kXBytes);
+    tw = reinterpret_cast<float2*>(win + C::kWin);
+    sp2 = tw + C::kTwCount;
+    melw = reinterpret_cast<float*>(sp2 + 17 * 32);
+    mel_lo = reinterpret_cast<int*>(melw + p.melw_count);
+  }
+  __device__ __forceinline__ void fill(const PlanDev& p, bool with_mel) {
+    for (int i = threadIdx.x; i < C::kWin; i += blockDim.x) win[i] = 0.5f * p.window[i];
+    for (int i = threadIdx.x; i < C::kTwCount; i += blockDim.x) tw[i] = p.tw[i];
+    for (int i = threadIdx.x; i < 17 * 32; i += blockDim.x) sp2[i] = p.sp2[i];
+    if (with_mel) {
+      for (int i = threadIdx.x; i < p.melw_count; i += blockDim.x) melw[i] = p.melw[i];
+      for (int i = threadIdx.x; i < 32 * p.mel_rounds; i += blockDim.x) mel_lo[i] = p.mel_lo[i];
+    }
+  }
+};
+
+// One frame's windowed sample pairs z[lane + 32 r] = (re[r], im[r]), r < R: reflect padding (np.pad mode='reflect') and
+// the optional pre-emphasis FIR are applied on the fly.  s_win holds 0.5 * window (the 1/2 of the Hermitian split).
+template <int N, bool PRE>
+__device__ __forceinline__ void load_frame2(float (&re)[Fft2Cfg<N>::kR], float (&im)[Fft2Cfg<N>::kR],
+                                            const float* __restrict__ x, long long L, int t, int T, int hop, float pre,
+                                            const float* __restrict__ s_win, int lane) {
+  using C = Fft2Cfg<N>;
+  const long long p0 = static_cast<long long>(t) * hop - N / 4;
+  if (t < T && p0 >= 1 && p0 + C::kWin <= L) {
+    const float* xp = x + p0 + 2 * lane;
+    static_for<0, C::kR>([&](auto rc) {
+      constexpr int r = decltype(rc)::value;
+      const float lo = __ldg(xp + 64 * r), hi = __ldg(xp + 64 * r + 1);
+      float a0 = lo, a1 = hi;
+      if constexpr (PRE) {
+        a0 = fmaf(-pre, __ldg(xp + 64 * r - 1), lo);
+        a1 = fmaf(-pre, lo, hi);
+      }
+      const float2 w = *reinterpret_cast<const float2*>(s_win + 2 * lane + 64 * r);
+      re[r] = a0 * w.x;
+      im[r] = a1 * w.y;
+    });
+  } else if (t < T) {
+    auto sample = [&](long long i) -> float {
+      if (i < 0) i = -i;
+      if (i >= L) i = 2 * (L - 1) - i;
+      float s = __ldg(x + i);
+      if constexpr (PRE) s = fmaf(-pre, i > 0 ? __ldg(x + i - 1) : 0.f, s);
+      return s;
+    };
+    static_for<0, C::kR>([&](auto rc) {
+      constexpr int r = decltype(rc)::value;
+      const int m = 2 * lane + 64 * r;
+      const float2 w = *reinterpret_cast<const float2*>(s_win + m);
+      re[r] = sample(p0 + m) * w.x;
+      im[r] = sample(p0 + m + 1) * w.y;
+    });
+  } else {
+    static_for<0, C::kR>([&](auto rc) {
+      constexpr int r = decltype(rc)::value;
+      re[r] = 0.f;
+      im[r] = 0.f;
+    });
+  }
+}
+
+// Gather the frames of one item into pass-A registers (see fft2_forward).  Frame t = t0 + 2p + h sits in half h
+// of pair p.  HS > 0 (requires hop == 64*HS, n_fft 2048): the two frames of a pair overlap by R - HS lane slots, so
+// interior pairs load R + HS slots once instead of 2R.
+template <int N, bool PRE, int HS>
+__device__ __forceinline__ void load_item2(PC (&v)[32], const float* __restrict__ x, long long L, int t0, int T, int hop,
+                                           float pre, const float* __restrict__ s_win, int lane) {
+  using C = Fft2Cfg<N>;
+  static_for<0, C::kP>([&](auto pc_) {
+    constexpr int p = decltype(pc_)::value;
+    float re[2][C::kR], im[2][C::kR];
+    const int t = t0 + 2 * p;
+    bool shared = false;
+    if constexpr (HS > 0) {
+      const long long p0 = static_cast<long long>(t) * hop - N / 4;
+      shared = (t + 1 < T) && p0 >= 1 && p0 + hop + C::kWin <= L;
+      if (shared) {
+        const float* xp = x + p0 + 2 * lane;
+        float de[C::kR + HS], dO[C::kR + HS];
+        static_for<0, C::kR + HS>([&](auto rc) {
+          constexpr int r = decltype(rc)::value;
+          const float lo = __ldg(xp + 64 * r), hi = __ldg(xp + 64 * r + 1);
+          de[r] = lo;
+          dO[r] = hi;
+          if constexpr (PRE) {
+            de[r] = fmaf(-pre, __ldg(xp + 64 * r - 1), lo);
+            dO[r] = fmaf(-pre, lo, hi);
+          }
+        });
+        static_for<0, C::kR>([&](auto rc) {
+          constexpr int r = decltype(rc)::value;
+          const float2 w = *reinterpret_cast<const float2*>(s_win + 2 * lane + 64 * r);
+          re[0][r] = de[r] * w.x;
+          im[0][r] = dO[r] * w.y;
+          re[1][r] = de[r + HS] * w.x;
+          im[1][r] = dO[r + HS] * w.y;
+        });
+      }
+    }
+    if (!shared) {
+      load_frame2<N, PRE>(re[0], im[0], x, L, t, T, hop, pre, s_win, lane);
+      load_frame2<N, PRE>(re[1], im[1], x, L, t + 1, T, hop, pre, s_win, lane);
+    }
+    static_for<0, C::kR>([&](auto rc) {
+      constexpr int r = decltype(rc)::value;
+      constexpr int idx = p * C::kR2 + brev(r, C::kLogR2);
+      v[idx].re = pk(re[0][r], re[1][r]);
+      v[idx].im = pk(im[0][r], im[1][r]);
+      v[idx + 1] = v[idx];
+    });
+  });
+}
+
+__device__ __forceinline__ pf sqrt2(pf p) { return pk(fast_sqrt(plo(p)), fast_sqrt(phi(p))); }
+
+template <int N, bool PRE, bool LOGMAG, int HS>
+__global__ void __launch_bounds__(kFeat2Warps * 32, 1) stft_feature2_kernel(const PlanDev p, const FeatArgs a) {
+  using C = Fft2Cfg<N>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem2<N> sm;
+  sm.carve(smem_raw, p, kFeat2Warps);
+  sm.fill(p, a.mel != nullptr);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint4* xbuf = sm.xbufs + warp * (32 * C::kXStride);
+  pf* sbuf = reinterpret_cast<pf*>(xbuf);   // [P][Nz] magnitudes of both frames of a pair (aliases the exchange buffer)
+  const int k1 = lane & (C::kR2 - 1), pl = lane / C::kR2;   // pass-B role of this lane: column k1 of pair pl
+  const bool col0 = (k1 == 0);
+  const int partner = (lane & ~(C::kR2 - 1)) | ((C::kR2 - k1) & (C::kR2 - 1));
+  const bool want_mag = a.mag != nullptr, want_mel = a.mel != nullptr;
+  // squared-magnitude form of the log scale: a log2 max(floor, sqrt p) + b = a/2 log2 max(floor^2, p) + b
+  const float mag_a = 0.5f * a.mag_scale.a, mag_b = a.mag_scale.b, mag_fl = a.mag_scale.floor * a.mag_scale.floor;
+  pf* const sa = sbuf + pl * C::kNz + k1;              // bins k1 + R2 s
+  pf* const sb = sbuf + pl * C::kNz + C::kNz - k1;     // bins Nz - k1 - R2 s
+  const float2* const sp = sm.sp2 + lane;
+  const long long warps_total = static_cast<long long>(gridDim.x) * kFeat2Warps;
+  for (long long item = static_cast<long long>(blockIdx.x) * kFeat2Warps + warp; item < a.bd.total_items;
+       item += warps_total) {
+    const Item it = decode_item(a.bd, item, C::kFrames);
+    PC v[32];
+    load_item2<N, PRE, HS>(v, a.x + it.sig_base, it.L, it.t0, it.T, p.hop, a.pre, sm.win, lane);
+    fft2_forward<N>(v, xbuf, sm.tw, lane);
+    // lane (pl, k1) now holds Z[k1 + R2*k2] of frames fA = t0 + 2 pl, fB = fA + 1
+    const int fA = it.t0 + 2 * pl;
+    const bool stA = want_mag && fA < it.T, stB = want_mag && fA + 1 < it.T;
+    float* const pa = a.mag + (it.frame_base + fA) * C::kF + k1;             // bins k1 + R2 s       (frame B: + F)
+    float* const pb = a.mag + (it.frame_base + fA) * C::kF + C::kNz - k1;    // bins Nz - k1 - R2 s
+    auto scaled = [&](pf pw) -> pf {   // |A|^2 of both frames -> output values
+      if constexpr (LOGMAG) {
+        return fma2s(pk(fast_lg2(fmaxf(mag_fl, plo(pw))), fast_lg2(fmaxf(mag_fl, phi(pw)))), mag_a, pk(mag_b, mag_b));
+      } else {
+        return sqrt2(pw);
+      }
+    };
+    static_for<0, 16>([&](auto sc) {
+      constexpr int s = decltype(sc)::value;
+      const PC send = pc_sel(col0, v[(32 - s) & 31], v[31 - s]);
+      const PC Zr = pc_shfl(send, partner);
+      PC ak, am;
+      split2<(s >= 8)>(v[s], Zr, sp[s * 32], ak, am);
+      const pf pa2 = norm2(ak), pm2 = norm2(am);
+      const pf oa = scaled(pa2), om = scaled(pm2);
+      if (stA) {
+        pa[C::kR2 * s] = plo(oa);
+        pb[-C::kR2 * s] = plo(om);
+      }
+      if (stB) {
+        pa[C::kF + C::kR2 * s] = phi(oa);
+        pb[C::kF - C::kR2 * s] = phi(om);
+      }
+      if (want_mel) {   // magnitudes for the mel filterbank (bin Nz is never part of a filter)
+        sa[C::kR2 * s] = LOGMAG ? sqrt2(pa2) : oa;
+        if (s > 0 || !col0) sb[-C::kR2 * s] = LOGMAG ? sqrt2(pm2) : om;
+      }
+    });
+    {
+      // self pair of column 0: bin Nz/2
+      PC ak, am;
+      split2<true>(v[16], v[16], sp[16 * 32], ak, am);
+      const pf pa2 = norm2(ak);
+      const pf oa = scaled(pa2);
+      if (stA && col0) pa[C::kR2 * 16] = plo(oa);
+      if (stB && col0) pa[C::kF + C::kR2 * 16] = phi(oa);
+      if (want_mel && col0) sa[C::kR2 * 16] = LOGMAG ? sqrt2(pa2) : oa;
+    }
+    __syncwarp();
+    if (want_mel) {
+#pragma unroll
+      for (int rd = 0; rd < kMaxMelRounds; ++rd) {
+        if (rd < p.mel_rounds) {
+          const int m = rd * 32 + lane;
+          const int lo = sm.mel_lo[m];
+          const float* wr = sm.melw + p.mel_round_off[rd] + lane;
+          const int n = p.mel_round_len[rd];
+          pf acc[C::kP];
+#pragma unroll
+          for (int q = 0; q < C::kP; ++q) acc[q] = 0ull;
+          for (int i = 0; i < n; ++i) {
+            const float w = wr[i * 32];
+            const int idx = min(lo + i, C::kNz - 1);
+#pragma unroll
+            for (int q = 0; q < C::kP; ++q) acc[q] = fma2s(sbuf[q * C::kNz + idx], w, acc[q]);
+          }
+          if (m < p.n_mel) {
+#pragma unroll
+            for (int q = 0; q < C::kP; ++q) {
+              const int f = it.t0 + 2 * q;
+              float* dst = a.mel + (it.frame_base + f) * p.n_mel + m;
+              if (f < it.T) dst[0] = apply_scale(a.mel_scale, plo(acc[q]));
+              if (f + 1 < it.T) dst[p.n_mel] = apply_scale(a.mel_scale, phi(acc[q]));
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <int N>
+inline size_t feat2_smem_bytes(const PlanDev& p) {
+  return Smem2<N>::bytes(p.melw_count, p.mel_rounds, kFeat2Warps);
+}
+
+}  // namespace sb200

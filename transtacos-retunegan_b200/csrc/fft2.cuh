@@ -1,0 +1,247 @@
+// Packed warp-level FFT engine (sm_100a): every lane register holds the SAME quantity of TWO frames in
+// the two halves of a 64-bit register pair, and all arithmetic is FFMA2 / FADD2 / FMUL2 (fma.rn.f32x2 ...).
+//
+// Measured on B200 (tools/ubench): a packed instruction occupies the FMA pipe for 2 cycles but only ONE
+// issue slot, and it takes 32-bit immediates / scalar registers broadcast to both halves for free.  The
+// scalar engine (fftcore.cuh) was issue-bound; the packed one leaves half of the issue slots to LDS / STS /
+// MUFU / integer work, so the kernel becomes FMA-pipe bound.
+//
+// Transform (same mathematics as fftcore.cuh): a frame is win = N/2 window taps a[m] centred in N points,
+//   z[n] = a[2n] + i a[2n+1]   (n < Nz/2, Nz = N/2; upper half of the Nz-point input is zero)
+//   Z = DFT_Nz(z) = pass A (in-lane radix-2R DIT, first stage pruned) -> twiddle -> 32x32 transpose through
+//       shared memory (one 16-byte packed complex per element) -> pass B (in-lane radix-32 DIT)
+//   split: A[k] = Zk + conj Zr + g_k (Zk - conj Zr), A[Nz-k] = conj(Zk + conj Zr - g_k (Zk - conj Zr)),
+//          Zr = Z[Nz-k], g_k = -i w_N^k, with the 1/2 folded into the window table;  X[k] = (-i)^k A[k].
+// Butterflies are in Linzer-Feig form: w b = c (b.re + t b.im, b.im - t b.re), t = tan, and the scale c is
+// absorbed into the following a +- c t' FMAs: 6 FMAs per non-trivial radix-2 butterfly.
+//
+// One warp "item" is 32 lanes x 32 packed complex registers = P = 1024/N... pairs of frames:
+//   n_fft 2048: 1 pair (2 frames), 1024: 2 pairs (4 frames), 512: 4 pairs (8 frames).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "fftcore.cuh"
+
+namespace sb200 {
+
+typedef unsigned long long pf;   // packed float pair: lo = first frame of the pair, hi = second
+
+__device__ __forceinline__ pf pk(float lo, float hi) {
+  pf r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float plo(pf a) {
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a));
+  return lo;
+}
+__device__ __forceinline__ float phi(pf a) {
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a));
+  return hi;
+}
+__device__ __forceinline__ pf add2(pf a, pf b) {
+  pf d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ pf sub2(pf a, pf b) {
+  pf d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ pf mul2(pf a, pf b) {
+  pf d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ pf fma2(pf a, pf b, pf c) {
+  pf d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+// scalar (immediate or register) broadcast to both halves: ptxas folds the mov.b64 into the operand
+__device__ __forceinline__ pf mul2s(pf a, float s) { return mul2(a, pk(s, s)); }
+__device__ __forceinline__ pf fma2s(pf a, float s, pf c) { return fma2(a, pk(s, s), c); }
+
+struct PC {   // packed complex: (re, im) of two frames
+  pf re, im;
+};
+
+__device__ __forceinline__ PC pc_shfl(const PC& a, int src) {
+  PC r;
+  r.re = __shfl_sync(kFullMask, a.re, src);
+  r.im = __shfl_sync(kFullMask, a.im, src);
+  return r;
+}
+__device__ __forceinline__ PC pc_sel(bool c, const PC& a, const PC& b) {
+  PC r;
+  r.re = c ? a.re : b.re;
+  r.im = c ? a.im : b.im;
+  return r;
+}
+
+// cos / sin of 2 pi i / 32 in double (compile-time), i in [0, 16]
+__host__ __device__ constexpr double dcos32_q(int i) {   // i in [0, 8]
+  return i == 0 ? 1.0
+       : i == 1 ? 0.98078528040323044913
+       : i == 2 ? 0.92387953251128675613
+       : i == 3 ? 0.83146961230254523708
+       : i == 4 ? 0.70710678118654752440
+       : i == 5 ? 0.55557023301960222474
+       : i == 6 ? 0.38268343236508977173
+       : i == 7 ? 0.19509032201612826785
+                : 0.0;
+}
+__host__ __device__ constexpr double dcos32(int i) { return i <= 8 ? dcos32_q(i) : -dcos32_q(16 - i); }
+__host__ __device__ constexpr double dsin32(int i) { return i <= 8 ? dcos32_q(8 - i) : dcos32_q(i - 8); }
+
+// Radix-2 DIT butterfly with twiddle w_32^I (forward: e^{-2 pi i I/32}; INV: conjugate), I in [0, 16):
+//   a' = a + w b,  b' = a - w b
+template <int I, bool INV>
+__device__ __forceinline__ void bfly(PC& a, PC& b) {
+  static_assert(I >= 0 && I < 16, "twiddle index");
+  if constexpr (I == 0) {
+    const PC t = b;
+    b.re = sub2(a.re, t.re); b.im = sub2(a.im, t.im);
+    a.re = add2(a.re, t.re); a.im = add2(a.im, t.im);
+  } else if constexpr (I == 8) {
+    // forward: w b = -i b = (b.im, -b.re); inverse: +i b = (-b.im, b.re)
+    const PC t = b;
+    if constexpr (!INV) {
+      b.re = sub2(a.re, t.im); b.im = add2(a.im, t.re);
+      a.re = add2(a.re, t.im); a.im = sub2(a.im, t.re);
+    } else {
+      b.re = add2(a.re, t.im); b.im = sub2(a.im, t.re);
+      a.re = sub2(a.re, t.im); a.im = add2(a.im, t.re);
+    }
+  } else {
+    constexpr double c = dcos32(I), s = INV ? -dsin32(I) : dsin32(I);   // w = c - i s
+    // w b = (c b.re + s b.im, c b.im - s b.re)
+    if constexpr ((c < 0 ? -c : c) >= (s < 0 ? -s : s)) {
+      constexpr float t = static_cast<float>(s / c), cf = static_cast<float>(c);
+      const pf tr = fma2s(b.im, t, b.re);     // (w b).re / c
+      const pf ti = fma2s(b.re, -t, b.im);    // (w b).im / c
+      b.re = fma2s(tr, -cf, a.re); b.im = fma2s(ti, -cf, a.im);
+      a.re = fma2s(tr, cf, a.re);  a.im = fma2s(ti, cf, a.im);
+    } else {
+      constexpr float k = static_cast<float>(c / s), sf = static_cast<float>(s);
+      const pf tr = fma2s(b.re, k, b.im);     // (w b).re / s
+      const pf tn = fma2s(b.im, -k, b.re);    // -(w b).im / s
+      b.re = fma2s(tr, -sf, a.re); b.im = fma2s(tn, sf, a.im);
+      a.re = fma2s(tr, sf, a.re);  a.im = fma2s(tn, -sf, a.im);
+    }
+  }
+}
+
+// In-register radix-2 DIT DFT of LEN points v[BASE .. BASE+LEN).  Input in bit-reversed order
+// (v[BASE + brev(n)] = x[n]), output in natural order.  Stages with block size < MIN_M are skipped:
+// MIN_M = 4 with v[BASE+2i+1] == v[BASE+2i] is the transform of an input whose upper half is zero.
+template <int LEN, int BASE, bool INV, int MIN_M>
+__device__ __forceinline__ void dit(PC (&v)[32]) {
+  if constexpr (LEN > 1) {
+    constexpr int H = LEN / 2;
+    dit<H, BASE, INV, MIN_M>(v);
+    dit<H, BASE + H, INV, MIN_M>(v);
+    if constexpr (LEN >= MIN_M) {
+      static_for<0, H>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        bfly<j * (32 / LEN), INV>(v[BASE + j], v[BASE + j + H]);
+      });
+    }
+  }
+}
+
+template <int N>
+struct Fft2Cfg {
+  static_assert(N == 2048 || N == 1024 || N == 512, "supported n_fft: 512, 1024, 2048 (win = n_fft/2)");
+  static constexpr int kN = N;
+  static constexpr int kNz = N / 2;          // complex FFT length
+  static constexpr int kWin = N / 2;         // window support
+  static constexpr int kR = N / 128;         // non-zero pass-A inputs per lane per frame
+  static constexpr int kR2 = 2 * kR;         // pass-A radix (32 / 16 / 8)
+  static constexpr int kLogR2 = ilog2(kR2);
+  static constexpr int kP = 2048 / N;        // frame PAIRS per item (1 / 2 / 4)
+  static constexpr int kFrames = 2 * kP;     // frames per item
+  static constexpr int kF = N / 2 + 1;       // one-sided bins
+  static constexpr int kTwCount = (kR2 - 1) * 32;   // float2 w_Nz^{k1*lane}, row k1-1
+  static constexpr int kSplitSlots = 17;     // pair slots per lane: k2 = 0..15 and the self pair k2 = 16 of column 0
+  static constexpr int kXStride = 33;        // transpose row stride in 16-byte elements (conflict-free both ways)
+  static constexpr int kXBytes = 32 * kXStride * 16;   // per-warp exchange buffer
+};
+
+// ---- pass A + twiddle + transpose + pass B: v (pass-A inputs, see below) -> v[k2] = Z_p[k1 + R2 k2] --------
+// On entry v[p*R2 + brev(r)] = v[p*R2 + brev(r) + 1] = z_p[lane + 32 r], r < R (brev over log2(R2) bits).
+// On exit lane j = p*R2 + k1 holds Z_p[k1 + R2*k2] in v[k2], k2 = 0..31.  xbuf: this warp's exchange buffer.
+// tw: smem table tw[(k1-1)*32 + lane] = w_Nz^{k1*lane}.
+template <int N>
+__device__ __forceinline__ void fft2_forward(PC (&v)[32], uint4* __restrict__ xbuf, const float2* __restrict__ tw,
+                                             int lane) {
+  using C = Fft2Cfg<N>;
+  static_for<0, C::kP>([&](auto pc_) {
+    constexpr int p = decltype(pc_)::value;
+    dit<C::kR2, p * C::kR2, false, 4>(v);
+  });
+  // twiddle (shared by all pairs) + transposed store: element (row = lane, col = p*R2 + k1)
+  uint4* wrow = xbuf + lane * C::kXStride;
+  static_for<0, C::kR2>([&](auto kc) {
+    constexpr int k1 = decltype(kc)::value;
+    if constexpr (k1 == 0) {
+      static_for<0, C::kP>([&](auto pc_) {
+        constexpr int p = decltype(pc_)::value;
+        const PC& y = v[p * C::kR2];
+        wrow[p * C::kR2] = make_uint4(static_cast<unsigned>(y.re), static_cast<unsigned>(y.re >> 32),
+                                      static_cast<unsigned>(y.im), static_cast<unsigned>(y.im >> 32));
+      });
+    } else {
+      const float2 w = tw[(k1 - 1) * 32 + lane];
+      static_for<0, C::kP>([&](auto pc_) {
+        constexpr int p = decltype(pc_)::value;
+        const PC& y = v[p * C::kR2 + k1];
+        const pf re = fma2s(y.im, -w.y, mul2s(y.re, w.x));
+        const pf im = fma2s(y.im, w.x, mul2s(y.re, w.y));
+        wrow[p * C::kR2 + k1] = make_uint4(static_cast<unsigned>(re), static_cast<unsigned>(re >> 32),
+                                           static_cast<unsigned>(im), static_cast<unsigned>(im >> 32));
+      });
+    }
+  });
+  __syncwarp();
+  // transposed read: lane j takes column j of every row n1, placed bit-reversed for the DIT
+  const uint4* rcol = xbuf + lane;
+  static_for<0, 32>([&](auto nc) {
+    constexpr int n1 = decltype(nc)::value;
+    const uint4 e = rcol[n1 * C::kXStride];
+    PC& d = v[brev(n1, 5)];
+    d.re = (static_cast<pf>(e.y) << 32) | e.x;
+    d.im = (static_cast<pf>(e.w) << 32) | e.z;
+  });
+  dit<32, 0, false, 2>(v);
+  __syncwarp();   // exchange buffer free again
+}
+
+// ---- Hermitian split on packed data -------------------------------------------------------------------------
+// Zk, Zr = Z[k], Z[Nz-k];  (t, c) = L-F twiddle of g_k = -i w_N^k = (-s, -c') with phi = 2 pi k / N:
+//   SINFORM == false (phi <= pi/4): tw = (tan phi, cos phi);  true (phi >= pi/4): tw = (cot phi, sin phi).
+// Returns A[k] in ak and conj(A[Nz-k]) in am (imaginary part of am has the sign of the conjugate).
+template <bool SINFORM>
+__device__ __forceinline__ void split2(const PC& Zk, const PC& Zr, float2 tw, PC& ak, PC& am) {
+  const pf fer = add2(Zk.re, Zr.re), fei = sub2(Zk.im, Zr.im);   // Zk + conj Zr
+  const pf fr = sub2(Zk.re, Zr.re), fi = add2(Zk.im, Zr.im);     // Zk - conj Zr
+  // t = g fo = (c fi - s fr, -s fi - c fr)
+  if constexpr (!SINFORM) {
+    const pf tr = fma2s(fr, -tw.x, fi);    // t.re / c
+    const pf tn = fma2s(fi, tw.x, fr);     // -t.im / c
+    ak.re = fma2s(tr, tw.y, fer);  ak.im = fma2s(tn, -tw.y, fei);
+    am.re = fma2s(tr, -tw.y, fer); am.im = fma2s(tn, tw.y, fei);
+  } else {
+    const pf nr = fma2s(fi, -tw.x, fr);    // -t.re / s = fr - cot fi
+    const pf tn = fma2s(fr, tw.x, fi);     // -t.im / s = fi + cot fr
+    ak.re = fma2s(nr, -tw.y, fer); ak.im = fma2s(tn, -tw.y, fei);
+    am.re = fma2s(nr, tw.y, fer);  am.im = fma2s(tn, tw.y, fei);
+  }
+}
+
+__device__ __forceinline__ pf norm2(const PC& a) { return fma2(a.re, a.re, mul2(a.im, a.im)); }
+
+}  // namespace sb200

@@ -161,8 +161,9 @@ __global__ void __launch_bounds__(kGlWarps * 32, 2) istft_frames_kernel(const Pl
   for (long long item = static_cast<long long>(blockIdx.x) * kGlWarps + warp; item < a.g.bd.total_items;
        item += static_cast<long long>(gridDim.x) * kGlWarps) {
     int b, t0;
-    gl_decode(a.g, item, C::kQ, &b, &t0);
+    gl_decode(a.g, item, 2 * C::kQ, &b, &t0);   // an item is 2Q frames: two passes
     const GlRow row = gl_row(a.g, b, N, p.hop);
+    for (int half = 0; half < 2 && t0 < row.T; ++half, t0 += C::kQ) {
     auto fetch = [&](long long idx) -> float2 {
       if (a.spec) return __ldg(a.spec + idx);
       float s, c;
@@ -199,6 +200,7 @@ __global__ void __launch_bounds__(kGlWarps * 32, 2) istft_frames_kernel(const Pl
     __syncwarp();
     float2 v[32];
     synth_store<N>(p, v, buf, sm.tw, sm.wnorm, a.fb_out + row.frame_base * C::kWin, t0, row, lane);
+    }
   }
 }
 
@@ -215,9 +217,10 @@ __global__ void __launch_bounds__(kGlWarps * 32, 2) gl_iter_kernel(const PlanDev
   for (long long item = static_cast<long long>(blockIdx.x) * kGlWarps + warp; item < a.g.bd.total_items;
        item += static_cast<long long>(gridDim.x) * kGlWarps) {
     int b, t0;
-    gl_decode(a.g, item, C::kQ, &b, &t0);
+    gl_decode(a.g, item, 2 * C::kQ, &b, &t0);
     const GlRow row = gl_row(a.g, b, N, p.hop);
     const float* fb = a.fb_in + row.frame_base * C::kWin;
+    for (int half = 0; half < 2 && t0 < row.T; ++half, t0 += C::kQ) {
     float2 v[32];
     // 1. gather the current signal under each analysis frame (reflect padded, np.pad mode='reflect')
     static_for<0, C::kQ>([&](auto qc) {
@@ -299,6 +302,7 @@ __global__ void __launch_bounds__(kGlWarps * 32, 2) gl_iter_kernel(const PlanDev
     __syncwarp();
     // 4. synthesis into the other buffer
     synth_store<N>(p, v, buf, sm.tw, sm.wnorm, a.fb_out + row.frame_base * C::kWin, t0, row, lane);
+    }
   }
 }
 

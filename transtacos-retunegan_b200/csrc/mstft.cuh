@@ -96,7 +96,8 @@ __global__ void __launch_bounds__(kMstftWarps * 32, 2) mstft_fwd_kernel(const Pl
   const long long chs = static_cast<long long>(a.Tf) * C::kF;
   for (long long item = static_cast<long long>(blockIdx.x) * kMstftWarps + warp; item < a.bd.total_items;
        item += static_cast<long long>(gridDim.x) * kMstftWarps) {
-    const Item it = decode_item(a.bd, item, C::kQ);
+    Item it = decode_item(a.bd, item, 2 * C::kQ);   // an item is 2Q frames: two passes
+    for (int half = 0; half < 2 && it.t0 < it.T; ++half, it.t0 += C::kQ) {
     const long long row0 = (static_cast<long long>(it.b) * 2 * a.Tf + it.t0) * C::kF;
     float2 v[32];
     float mr[kMaxMelRounds][C::kQ];
@@ -116,6 +117,7 @@ __global__ void __launch_bounds__(kMstftWarps * 32, 2) mstft_fwd_kernel(const Pl
       }
     });
     __syncwarp();
+    }
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(kFullMask, acc, d);
@@ -179,7 +181,8 @@ __global__ void __launch_bounds__(kMstftWarps * 32, 2) mstft_bwd_kernel(const Pl
   const long long chs = static_cast<long long>(a.Tf) * C::kF;
   for (long long item = static_cast<long long>(blockIdx.x) * kMstftWarps + warp; item < a.bd.total_items;
        item += static_cast<long long>(gridDim.x) * kMstftWarps) {
-    const Item it = decode_item(a.bd, item, C::kQ);
+    Item it = decode_item(a.bd, item, 2 * C::kQ);
+    for (int half = 0; half < 2 && it.t0 < it.T; ++half, it.t0 += C::kQ) {
     float2 v[32];
     load_frames<N, false>(v, a.yg + it.sig_base, it.L, it.t0, it.T, p.hop, 0.f, sm.win, lane);
     fft_forward<N>(v, buf, sm.tw, lane);
@@ -304,6 +307,8 @@ __global__ void __launch_bounds__(kMstftWarps * 32, 2) mstft_bwd_kernel(const Pl
         });
       }
     });
+    __syncwarp();
+    }
   }
 }
 

@@ -26,6 +26,8 @@ struct PlanDev {
   const float* wsq;       // [win]            window^2
   const float2* tw;       // [(2R-1)*32]      w_Nz^{k1*lane}, row k1-1
   const float2* ws;       // [Nz/2+1]         -0.5i * w_N^k
+  const float2* sp2;      // [17*32]          packed-engine split twiddles, slot s, lane l: k = l%R2 + R2*s, phi = 2 pi k/N:
+                          //                  s < 8: (tan phi, cos phi); s >= 8: (cot phi, sin phi)   (fft2.cuh split2)
   // banded mel, ELL per round of 32 rows: melw[round_off[r] + it*32 + lane], it < round_len[r]
   const float* melw;
   const int* mel_lo;      // [32*rounds]      first non-zero column of each row (0 for padding rows)
@@ -33,6 +35,7 @@ struct PlanDev {
   int mel_round_off[kMaxMelRounds];
   int mel_round_len[kMaxMelRounds];
   int melw_count;         // floats in melw
+  int mel_kmin, mel_kmax; // first / last bin with a non-zero filter weight
   // column view (<= 2 non-zeros per column, consecutive rows): basis[r0[k], k] = c0[k], basis[r0[k]+1, k] = c1[k]
   const int* col_r0;      // [F]
   const float* col_c0;    // [F]
@@ -161,6 +164,14 @@ inline std::string build_plan(const sb200_config& c, sb200_plan* p, int* st) {
     ws[k] = make_float2(static_cast<float>(-0.5 * std::sin(th)), static_cast<float>(-0.5 * std::cos(th)));
   }
   ws[Nz / 2 + 1] = make_float2(0.f, 0.f);
+  std::vector<float2> sp2(17 * 32);
+  for (int s = 0; s < 17; ++s)
+    for (int l = 0; l < 32; ++l) {
+      const int k = (l % R2) + R2 * s;
+      const double ph = 2.0 * pi * k / N;
+      sp2[s * 32 + l] = s < 8 ? make_float2(static_cast<float>(std::tan(ph)), static_cast<float>(std::cos(ph)))
+                              : make_float2(static_cast<float>(std::cos(ph) / std::sin(ph)), static_cast<float>(std::sin(ph)));
+    }
 
   p->mel_dense = mel_filterbank(c.sample_rate, N, c.n_mel, c.fmin, c.fmax, c.mel_htk != 0);
   const std::vector<float>& mb = p->mel_dense;
@@ -188,6 +199,13 @@ inline std::string build_plan(const sb200_config& c, sb200_plan* p, int* st) {
       }
   }
   d.melw_count = static_cast<int>(melw.size());
+  d.mel_kmin = F;
+  d.mel_kmax = -1;
+  for (int m = 0; m < c.n_mel; ++m)
+    if (len[m] > 0) {
+      d.mel_kmin = std::min(d.mel_kmin, lo[m]);
+      d.mel_kmax = std::max(d.mel_kmax, lo[m] + len[m] - 1);
+    }
   std::vector<int> r0(F, 0);
   std::vector<float> c0(F, 0.f), c1(F, 0.f);
   for (int k = 0; k < F; ++k) {
@@ -205,7 +223,7 @@ inline std::string build_plan(const sb200_config& c, sb200_plan* p, int* st) {
   cudaError_t e;
 #define SB200_UP(vec, field) \
   if ((e = upload(p, vec, &d.field)) != cudaSuccess) return std::string("cuda upload: ") + cudaGetErrorString(e);
-  SB200_UP(wf, window) SB200_UP(wout, wout) SB200_UP(wnorm, wnorm) SB200_UP(wsq, wsq) SB200_UP(tw, tw) SB200_UP(ws, ws)
+  SB200_UP(wf, window) SB200_UP(wout, wout) SB200_UP(wnorm, wnorm) SB200_UP(wsq, wsq) SB200_UP(tw, tw) SB200_UP(ws, ws) SB200_UP(sp2, sp2)
   SB200_UP(melw, melw) SB200_UP(lo, mel_lo) SB200_UP(r0, col_r0) SB200_UP(c0, col_c0) SB200_UP(c1, col_c1)
 #undef SB200_UP
   *st = SB200_OK;

@@ -6,6 +6,7 @@
 #include <string>
 
 #include "feat.cuh"
+#include "feat2.cuh"
 #include "gl.cuh"
 #include "mstft.cuh"
 #include "misc.cuh"
@@ -45,7 +46,7 @@ ScaleDev to_dev(const sb200_scale& s) { return ScaleDev{s.log, s.a, s.b, s.floor
 // Signal-described batch (STFT direction): frames = 1 + len/hop.
 int make_batch_signal(const sb200_plan* plan, const sb200_batch* b, BatchDev* out, long long* total_frames) {
   if (!b || b->B < 1) return fail(SB200_ERR_INVALID, "batch: B must be >= 1");
-  const int Q = 2048 / plan->cfg.n_fft, hop = plan->cfg.hop_length;
+  const int Q = 4096 / plan->cfg.n_fft, hop = plan->cfg.hop_length;   // frames per item
   BatchDev d{};
   d.B = b->B;
   if (b->item_off == nullptr) {
@@ -70,8 +71,9 @@ int make_batch_signal(const sb200_plan* plan, const sb200_batch* b, BatchDev* ou
   return SB200_OK;
 }
 
+// Scalar engine: only used when the complex STFT itself is requested (get_stft_torch).
 template <int N>
-int launch_features(const sb200_plan* plan, const FeatArgs& a, cudaStream_t st) {
+int launch_features_spec(const sb200_plan* plan, const FeatArgs& a, cudaStream_t st) {
   const size_t smem = feat_smem_bytes<N>(plan->dev);
   const long long ctas_needed = (a.bd.total_items + kFeatWarps - 1) / kFeatWarps;
   const int grid = static_cast<int>(std::min<long long>(ctas_needed, 2LL * sm_count()));
@@ -83,6 +85,35 @@ int launch_features(const sb200_plan* plan, const FeatArgs& a, cudaStream_t st) 
     stft_feature_kernel<N, false><<<grid, kFeatWarps * 32, smem, st>>>(plan->dev, a);
   }
   return check_launch("stft_feature_kernel");
+}
+
+template <int N, bool PRE, bool LOGMAG, int HS>
+void launch_features2_t(const sb200_plan* plan, const FeatArgs& a, int grid, size_t smem, cudaStream_t st) {
+  cudaFuncSetAttribute(stft_feature2_kernel<N, PRE, LOGMAG, HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  stft_feature2_kernel<N, PRE, LOGMAG, HS><<<grid, kFeat2Warps * 32, smem, st>>>(plan->dev, a);
+}
+
+// Packed engine: magnitude / mel features (the hot path).
+template <int N>
+int launch_features2(const sb200_plan* plan, const FeatArgs& a, cudaStream_t st) {
+  const size_t smem = feat2_smem_bytes<N>(plan->dev);
+  const long long ctas_needed = (a.bd.total_items + kFeat2Warps - 1) / kFeat2Warps;
+  const int grid = static_cast<int>(std::min<long long>(ctas_needed, sm_count()));
+  const bool pre = a.pre != 0.f, lg = a.mag_scale.log != 0;
+  if constexpr (N == 2048) {
+    if (plan->cfg.hop_length == 256) {   // the reference hop (hparam.py): frames of a pair share 3/4 of their samples
+      if (pre && lg) launch_features2_t<N, true, true, 4>(plan, a, grid, smem, st);
+      else if (pre) launch_features2_t<N, true, false, 4>(plan, a, grid, smem, st);
+      else if (lg) launch_features2_t<N, false, true, 4>(plan, a, grid, smem, st);
+      else launch_features2_t<N, false, false, 4>(plan, a, grid, smem, st);
+      return check_launch("stft_feature2_kernel");
+    }
+  }
+  if (pre && lg) launch_features2_t<N, true, true, 0>(plan, a, grid, smem, st);
+  else if (pre) launch_features2_t<N, true, false, 0>(plan, a, grid, smem, st);
+  else if (lg) launch_features2_t<N, false, true, 0>(plan, a, grid, smem, st);
+  else launch_features2_t<N, false, false, 0>(plan, a, grid, smem, st);
+  return check_launch("stft_feature2_kernel");
 }
 
 }  // namespace
@@ -126,7 +157,7 @@ int sb200_plan_destroy(sb200_plan* plan) {
   return SB200_OK;
 }
 
-int sb200_plan_frames_per_pass(const sb200_plan* plan) { return plan ? 2048 / plan->cfg.n_fft : 0; }
+int sb200_plan_frames_per_pass(const sb200_plan* plan) { return plan ? 4096 / plan->cfg.n_fft : 0; }
 
 int sb200_plan_mel_basis_host(const sb200_plan* plan, float* out_host) {
   if (!plan || !out_host) return fail(SB200_ERR_INVALID, "mel_basis_host: null argument");
@@ -156,7 +187,11 @@ int sb200_stft_features(const sb200_plan* plan, const float* x, const sb200_batc
   a.mel = mel;
   a.spec = reinterpret_cast<float2*>(spec);
   int rc = 0;
-  SB200_DISPATCH_N(plan, rc = launch_features<kN>(plan, a, static_cast<cudaStream_t>(stream)));
+  if (spec) {
+    SB200_DISPATCH_N(plan, rc = launch_features_spec<kN>(plan, a, static_cast<cudaStream_t>(stream)));
+  } else {
+    SB200_DISPATCH_N(plan, rc = launch_features2<kN>(plan, a, static_cast<cudaStream_t>(stream)));
+  }
   return rc;
 }
 
