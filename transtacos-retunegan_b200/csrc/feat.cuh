@@ -161,7 +161,7 @@ __device__ __forceinline__ void load_frames(float2 (&v)[32], const float* __rest
 }
 
 // Banded mel projection of the raw magnitudes held in buf[q*ZS + k].x; calls emit(q, rd, m, value) with
-// m = 32*rd + lane (q and rd come from fully unrolled loops, so register arrays indexed by them stay in registers).
+// m = the mel row of slot (rd, lane), >= n_mel for an empty slot (q and rd come from fully unrolled loops, so register arrays indexed by them stay in registers).
 template <int N, class Emit>
 __device__ __forceinline__ void mel_project_smem(const PlanDev& p, const float* __restrict__ s_melw,
                                                  const int* __restrict__ s_lo, const float2* __restrict__ buf, int lane,
@@ -170,8 +170,8 @@ __device__ __forceinline__ void mel_project_smem(const PlanDev& p, const float* 
 #pragma unroll
   for (int rd = 0; rd < kMaxMelRounds; ++rd) {
     if (rd < p.mel_rounds) {
-      const int m = rd * 32 + lane;
-      const int lo = s_lo[m];
+      const int slot = s_lo[rd * 32 + lane];
+      const int m = slot >> 16, lo = slot & 0xffff;   // mel row of this lane in this round (>= n_mel: none)
       const float* wr = s_melw + p.mel_round_off[rd] + lane;
       const int n = p.mel_round_len[rd];
       float acc[C::kQ];

@@ -11,12 +11,16 @@
 
 namespace sb200 {
 
+#ifdef kFeat2WarpsOverride
+constexpr int kFeat2Warps = kFeat2WarpsOverride;
+#else
 constexpr int kFeat2Warps = 8;
+#endif
 
 template <int N>
 struct Smem2 {
   using C = Fft2Cfg<N>;
-  uint4* xbufs;   // [warps][32*33] exchange buffers (first: 16-byte aligned)
+  uint4* xbufs;   // [warps][kXElems] exchange buffers (first: 16-byte aligned)
   float* win;     // [win] 0.5 * analysis window
   float2* tw;     // [kTwCount]
   float2* sp2;    // [17*32]
@@ -46,11 +50,11 @@ struct Smem2 {
 };
 
 // One frame's windowed sample pairs z[lane + 32 r] = (re[r], im[r]), r < R: reflect padding (np.pad mode='reflect') and
-// the optional pre-emphasis FIR are applied on the fly.  s_win holds 0.5 * window (the 1/2 of the Hermitian split).
+// the optional pre-emphasis FIR are applied on the fly.  stage: >= win floats of this warp's shared memory (edge frames).  s_win holds 0.5 * window (the 1/2 of the Hermitian split).
 template <int N, bool PRE>
 __device__ __forceinline__ void load_frame2(float (&re)[Fft2Cfg<N>::kR], float (&im)[Fft2Cfg<N>::kR],
                                             const float* __restrict__ x, long long L, int t, int T, int hop, float pre,
-                                            const float* __restrict__ s_win, int lane) {
+                                            const float* __restrict__ s_win, float* stage, int lane) {
   using C = Fft2Cfg<N>;
   const long long p0 = static_cast<long long>(t) * hop - N / 4;
   if (t < T && p0 >= 1 && p0 + C::kWin <= L) {
@@ -68,20 +72,26 @@ __device__ __forceinline__ void load_frame2(float (&re)[Fft2Cfg<N>::kR], float (
       im[r] = a1 * w.y;
     });
   } else if (t < T) {
-    auto sample = [&](long long i) -> float {
+    // edge frame: a rolled loop stages the reflected (pre-emphasised) samples in shared memory (keeps the code small)
+#pragma unroll 1
+    for (int m = lane; m < C::kWin; m += 32) {
+      long long i = p0 + m;
       if (i < 0) i = -i;
       if (i >= L) i = 2 * (L - 1) - i;
       float s = __ldg(x + i);
       if constexpr (PRE) s = fmaf(-pre, i > 0 ? __ldg(x + i - 1) : 0.f, s);
-      return s;
-    };
+      stage[m] = s;
+    }
+    __syncwarp();
     static_for<0, C::kR>([&](auto rc) {
       constexpr int r = decltype(rc)::value;
       const int m = 2 * lane + 64 * r;
       const float2 w = *reinterpret_cast<const float2*>(s_win + m);
-      re[r] = sample(p0 + m) * w.x;
-      im[r] = sample(p0 + m + 1) * w.y;
+      const float2 sv = *reinterpret_cast<const float2*>(stage + m);
+      re[r] = sv.x * w.x;
+      im[r] = sv.y * w.y;
     });
+    __syncwarp();
   } else {
     static_for<0, C::kR>([&](auto rc) {
       constexpr int r = decltype(rc)::value;
@@ -91,47 +101,65 @@ __device__ __forceinline__ void load_frame2(float (&re)[Fft2Cfg<N>::kR], float (
   }
 }
 
-// Gather the frames of one item into pass-A registers (see fft2_forward).  Frame t = t0 + 2p + h sits in half h
-// of pair p.  HS > 0 (requires hop == 64*HS, n_fft 2048): the two frames of a pair overlap by R - HS lane slots, so
-// interior pairs load R + HS slots once instead of 2R.
+// Raw samples of one frame pair, loaded ahead of use (software prefetch across the mel phase of the previous item).
+// HS > 0 (requires hop == 64*HS, n_fft 2048): the two frames of a pair overlap by R - HS lane slots, so an interior
+// pair needs R + HS slots of (previous, even, odd) samples once instead of 2R.
 template <int N, bool PRE, int HS>
-__device__ __forceinline__ void load_item2(PC (&v)[32], const float* __restrict__ x, long long L, int t0, int T, int hop,
-                                           float pre, const float* __restrict__ s_win, int lane) {
+struct Fetch2 {
+  using C = Fft2Cfg<N>;
+  static constexpr int kSlots = HS > 0 ? C::kR + HS : 1;
+  Item it;
+  bool shared;
+  float lo[kSlots], hi[kSlots], pv[PRE ? kSlots : 1];
+  __device__ __forceinline__ void issue(const BatchDev& bd, long long item, const float* __restrict__ x, int hop, int lane) {
+    it = decode_item(bd, item, C::kFrames);
+    shared = false;
+    if constexpr (HS > 0) {
+      const long long p0 = static_cast<long long>(it.t0) * hop - N / 4;
+      shared = (it.t0 + 1 < it.T) && p0 >= 1 && p0 + hop + C::kWin <= it.L;
+      if (shared) {
+        const float* xp = x + it.sig_base + p0 + 2 * lane;
+        static_for<0, kSlots>([&](auto rc) {
+          constexpr int r = decltype(rc)::value;
+          lo[r] = __ldg(xp + 64 * r);
+          hi[r] = __ldg(xp + 64 * r + 1);
+          if constexpr (PRE) pv[r] = __ldg(xp + 64 * r - 1);
+        });
+      }
+    }
+  }
+};
+
+// Build the pass-A registers of one item (see fft2_forward).  Frame t = t0 + 2p + h sits in half h of pair p.
+template <int N, bool PRE, int HS>
+__device__ __forceinline__ void load_item2(PC (&v)[32], const Fetch2<N, PRE, HS>& f, const float* __restrict__ x, int hop,
+                                           float pre, const float* __restrict__ s_win, float* stage, int lane) {
   using C = Fft2Cfg<N>;
   static_for<0, C::kP>([&](auto pc_) {
     constexpr int p = decltype(pc_)::value;
     float re[2][C::kR], im[2][C::kR];
-    const int t = t0 + 2 * p;
-    bool shared = false;
-    if constexpr (HS > 0) {
-      const long long p0 = static_cast<long long>(t) * hop - N / 4;
-      shared = (t + 1 < T) && p0 >= 1 && p0 + hop + C::kWin <= L;
-      if (shared) {
-        const float* xp = x + p0 + 2 * lane;
-        float de[C::kR + HS], dO[C::kR + HS];
-        static_for<0, C::kR + HS>([&](auto rc) {
-          constexpr int r = decltype(rc)::value;
-          const float lo = __ldg(xp + 64 * r), hi = __ldg(xp + 64 * r + 1);
-          de[r] = lo;
-          dO[r] = hi;
-          if constexpr (PRE) {
-            de[r] = fmaf(-pre, __ldg(xp + 64 * r - 1), lo);
-            dO[r] = fmaf(-pre, lo, hi);
-          }
-        });
+    if (HS > 0 && f.shared) {
+      if constexpr (HS > 0) {
         static_for<0, C::kR>([&](auto rc) {
           constexpr int r = decltype(rc)::value;
           const float2 w = *reinterpret_cast<const float2*>(s_win + 2 * lane + 64 * r);
-          re[0][r] = de[r] * w.x;
-          im[0][r] = dO[r] * w.y;
-          re[1][r] = de[r + HS] * w.x;
-          im[1][r] = dO[r + HS] * w.y;
+          if constexpr (PRE) {
+            re[0][r] = fmaf(-pre, f.pv[r], f.lo[r]) * w.x;
+            im[0][r] = fmaf(-pre, f.lo[r], f.hi[r]) * w.y;
+            re[1][r] = fmaf(-pre, f.pv[r + HS], f.lo[r + HS]) * w.x;
+            im[1][r] = fmaf(-pre, f.lo[r + HS], f.hi[r + HS]) * w.y;
+          } else {
+            re[0][r] = f.lo[r] * w.x;
+            im[0][r] = f.hi[r] * w.y;
+            re[1][r] = f.lo[r + HS] * w.x;
+            im[1][r] = f.hi[r + HS] * w.y;
+          }
         });
       }
-    }
-    if (!shared) {
-      load_frame2<N, PRE>(re[0], im[0], x, L, t, T, hop, pre, s_win, lane);
-      load_frame2<N, PRE>(re[1], im[1], x, L, t + 1, T, hop, pre, s_win, lane);
+    } else {
+      const int t = f.it.t0 + 2 * p;
+      load_frame2<N, PRE>(re[0], im[0], x + f.it.sig_base, f.it.L, t, f.it.T, hop, pre, s_win, stage, lane);
+      load_frame2<N, PRE>(re[1], im[1], x + f.it.sig_base, f.it.L, t + 1, f.it.T, hop, pre, s_win, stage, lane);
     }
     static_for<0, C::kR>([&](auto rc) {
       constexpr int r = decltype(rc)::value;
@@ -154,7 +182,7 @@ __global__ void __launch_bounds__(kFeat2Warps * 32, 1) stft_feature2_kernel(cons
   sm.fill(p, a.mel != nullptr);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint4* xbuf = sm.xbufs + warp * (32 * C::kXStride);
+  uint4* xbuf = sm.xbufs + warp * C::kXElems;
   pf* sbuf = reinterpret_cast<pf*>(xbuf);   // [P][Nz] magnitudes of both frames of a pair (aliases the exchange buffer)
   const int k1 = lane & (C::kR2 - 1), pl = lane / C::kR2;   // pass-B role of this lane: column k1 of pair pl
   const bool col0 = (k1 == 0);
@@ -165,12 +193,23 @@ __global__ void __launch_bounds__(kFeat2Warps * 32, 1) stft_feature2_kernel(cons
   pf* const sa = sbuf + pl * C::kNz + k1;              // bins k1 + R2 s
   pf* const sb = sbuf + pl * C::kNz + C::kNz - k1;     // bins Nz - k1 - R2 s
   const float2* const sp = sm.sp2 + lane;
+  // slots whose bins the mel filterbank reads: bit s of need_a for bins [R2 s, R2 (s+1)), of need_b for (Nz - R2 (s+1), Nz - R2 s]
+  unsigned need_a = 0, need_b = 0;
+  if (want_mel) {
+    for (int s = 0; s < 16; ++s) {
+      if (C::kR2 * s <= p.mel_kmax && C::kR2 * (s + 1) > p.mel_kmin) need_a |= 1u << s;
+      if (C::kNz - C::kR2 * (s + 1) < p.mel_kmax && C::kNz - C::kR2 * s >= p.mel_kmin) need_b |= 1u << s;
+    }
+  }
   const long long warps_total = static_cast<long long>(gridDim.x) * kFeat2Warps;
-  for (long long item = static_cast<long long>(blockIdx.x) * kFeat2Warps + warp; item < a.bd.total_items;
-       item += warps_total) {
-    const Item it = decode_item(a.bd, item, C::kFrames);
+  long long item = static_cast<long long>(blockIdx.x) * kFeat2Warps + warp;
+  Fetch2<N, PRE, HS> nx;
+  bool have = item < a.bd.total_items;
+  if (have) nx.issue(a.bd, item, a.x, p.hop, lane);
+  while (have) {
+    const Item it = nx.it;
     PC v[32];
-    load_item2<N, PRE, HS>(v, a.x + it.sig_base, it.L, it.t0, it.T, p.hop, a.pre, sm.win, lane);
+    load_item2<N, PRE, HS>(v, nx, a.x, p.hop, a.pre, sm.win, reinterpret_cast<float*>(xbuf), lane);
     fft2_forward<N>(v, xbuf, sm.tw, lane);
     // lane (pl, k1) now holds Z[k1 + R2*k2] of frames fA = t0 + 2 pl, fB = fA + 1
     const int fA = it.t0 + 2 * pl;
@@ -184,12 +223,27 @@ __global__ void __launch_bounds__(kFeat2Warps * 32, 1) stft_feature2_kernel(cons
         return sqrt2(pw);
       }
     };
+    {
+      // self pair of column 0 (bin Nz/2) first: the exchange below overwrites v[16]
+      PC ak, am;
+      split2<true>(v[16], v[16], sp[16 * 32], ak, am);
+      const pf pa2 = norm2(ak);
+      const pf oa = scaled(pa2);
+      if (stA && col0) pa[C::kR2 * 16] = plo(oa);
+      if (stB && col0) pa[C::kF + C::kR2 * 16] = phi(oa);
+      if (want_mel && col0) sa[C::kR2 * 16] = LOGMAG ? sqrt2(pa2) : oa;
+    }
+    // exchange with the partner lane, all slots back to back and in place: slot s receives Z[Nz - k] into v[31 - s]
+    // (descending s: column-0 lanes send v[32 - s], which slot s - 1 overwrites afterwards)
+    static_for<0, 16>([&](auto sc) {
+      constexpr int s = 15 - decltype(sc)::value;
+      const PC send = pc_sel(col0, v[(32 - s) & 31], v[31 - s]);
+      v[31 - s] = pc_shfl(send, partner);
+    });
     static_for<0, 16>([&](auto sc) {
       constexpr int s = decltype(sc)::value;
-      const PC send = pc_sel(col0, v[(32 - s) & 31], v[31 - s]);
-      const PC Zr = pc_shfl(send, partner);
       PC ak, am;
-      split2<(s >= 8)>(v[s], Zr, sp[s * 32], ak, am);
+      split2<(s >= 8)>(v[s], v[31 - s], sp[s * 32], ak, am);
       const pf pa2 = norm2(ak), pm2 = norm2(am);
       const pf oa = scaled(pa2), om = scaled(pm2);
       if (stA) {
@@ -200,39 +254,47 @@ __global__ void __launch_bounds__(kFeat2Warps * 32, 1) stft_feature2_kernel(cons
         pa[C::kF + C::kR2 * s] = phi(oa);
         pb[C::kF - C::kR2 * s] = phi(om);
       }
-      if (want_mel) {   // magnitudes for the mel filterbank (bin Nz is never part of a filter)
-        sa[C::kR2 * s] = LOGMAG ? sqrt2(pa2) : oa;
-        if (s > 0 || !col0) sb[-C::kR2 * s] = LOGMAG ? sqrt2(pm2) : om;
-      }
+      // magnitudes for the mel filterbank (bin Nz is never part of a filter)
+      if (need_a & (1u << s)) sa[C::kR2 * s] = LOGMAG ? sqrt2(pa2) : oa;
+      if ((need_b & (1u << s)) && (s > 0 || !col0)) sb[-C::kR2 * s] = LOGMAG ? sqrt2(pm2) : om;
     });
-    {
-      // self pair of column 0: bin Nz/2
-      PC ak, am;
-      split2<true>(v[16], v[16], sp[16 * 32], ak, am);
-      const pf pa2 = norm2(ak);
-      const pf oa = scaled(pa2);
-      if (stA && col0) pa[C::kR2 * 16] = plo(oa);
-      if (stB && col0) pa[C::kF + C::kR2 * 16] = phi(oa);
-      if (want_mel && col0) sa[C::kR2 * 16] = LOGMAG ? sqrt2(pa2) : oa;
-    }
+    // next item's samples are requested now and land during the mel phase
+    item += warps_total;
+    have = item < a.bd.total_items;
+    if (have) nx.issue(a.bd, item, a.x, p.hop, lane);
     __syncwarp();
     if (want_mel) {
 #pragma unroll
       for (int rd = 0; rd < kMaxMelRounds; ++rd) {
         if (rd < p.mel_rounds) {
-          const int m = rd * 32 + lane;
-          const int lo = sm.mel_lo[m];
+          const int slot = sm.mel_lo[rd * 32 + lane];
+          const int m = slot >> 16, lo = slot & 0xffff;
           const float* wr = sm.melw + p.mel_round_off[rd] + lane;
-          const int n = p.mel_round_len[rd];
-          pf acc[C::kP];
+          const pf* sr = sbuf + lo;   // reads may run past the row end (zero weights) into finite stale data
+          const int n = p.mel_round_len[rd];   // multiple of 8
+          pf acc[C::kP], acc2[C::kP];
 #pragma unroll
-          for (int q = 0; q < C::kP; ++q) acc[q] = 0ull;
-          for (int i = 0; i < n; ++i) {
-            const float w = wr[i * 32];
-            const int idx = min(lo + i, C::kNz - 1);
+          for (int q = 0; q < C::kP; ++q) acc[q] = acc2[q] = 0ull;
+#pragma unroll 1
+          for (int i0 = 0; i0 < n; i0 += 8) {
+            float w[8];
+            pf sv[C::kP][8];
 #pragma unroll
-            for (int q = 0; q < C::kP; ++q) acc[q] = fma2s(sbuf[q * C::kNz + idx], w, acc[q]);
+            for (int j = 0; j < 8; ++j) w[j] = wr[(i0 + j) * 32];
+#pragma unroll
+            for (int q = 0; q < C::kP; ++q)
+#pragma unroll
+              for (int j = 0; j < 8; ++j) sv[q][j] = sr[q * C::kNz + i0 + j];
+#pragma unroll
+            for (int q = 0; q < C::kP; ++q)
+#pragma unroll
+              for (int j = 0; j < 8; j += 2) {
+                acc[q] = fma2s(sv[q][j], w[j], acc[q]);
+                acc2[q] = fma2s(sv[q][j + 1], w[j + 1], acc2[q]);
+              }
           }
+#pragma unroll
+          for (int q = 0; q < C::kP; ++q) acc[q] = add2(acc[q], acc2[q]);
           if (m < p.n_mel) {
 #pragma unroll
             for (int q = 0; q < C::kP; ++q) {

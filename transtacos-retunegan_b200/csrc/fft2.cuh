@@ -82,6 +82,19 @@ __device__ __forceinline__ PC pc_sel(bool c, const PC& a, const PC& b) {
   return r;
 }
 
+// 16-byte shared-memory access of one packed complex (re pair, im pair); OFF = compile-time byte offset
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+template <int OFF>
+__device__ __forceinline__ void sts_pc(unsigned addr, pf re, pf im) {
+  asm volatile("st.shared.v2.b64 [%0+%3], {%1, %2};" ::"r"(addr), "l"(re), "l"(im), "n"(OFF) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ PC lds_pc(unsigned addr) {
+  PC r;
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2+%3];" : "=l"(r.re), "=l"(r.im) : "r"(addr), "n"(OFF) : "memory");
+  return r;
+}
+
 // cos / sin of 2 pi i / 32 in double (compile-time), i in [0, 16]
 __host__ __device__ constexpr double dcos32_q(int i) {   // i in [0, 8]
   return i == 0 ? 1.0
@@ -167,8 +180,11 @@ struct Fft2Cfg {
   static constexpr int kF = N / 2 + 1;       // one-sided bins
   static constexpr int kTwCount = (kR2 - 1) * 32;   // float2 w_Nz^{k1*lane}, row k1-1
   static constexpr int kSplitSlots = 17;     // pair slots per lane: k2 = 0..15 and the self pair k2 = 16 of column 0
-  static constexpr int kXStride = 33;        // transpose row stride in 16-byte elements (conflict-free both ways)
-  static constexpr int kXBytes = 32 * kXStride * 16;   // per-warp exchange buffer
+  // transpose buffer: element (row, col) of 16 bytes at 33*row + col: the 8 rows of a quarter-warp start in 8
+  // different 16-byte bank groups, so both the row-wise stores and the column-wise loads are conflict free
+  __host__ __device__ static constexpr int xoff(int row) { return row * 33; }
+  static constexpr int kXElems = 32 * 33;
+  static constexpr int kXBytes = kXElems * 16;   // per-warp exchange buffer
 };
 
 // ---- pass A + twiddle + transpose + pass B: v (pass-A inputs, see below) -> v[k2] = Z_p[k1 + R2 k2] --------
@@ -184,15 +200,13 @@ __device__ __forceinline__ void fft2_forward(PC (&v)[32], uint4* __restrict__ xb
     dit<C::kR2, p * C::kR2, false, 4>(v);
   });
   // twiddle (shared by all pairs) + transposed store: element (row = lane, col = p*R2 + k1)
-  uint4* wrow = xbuf + lane * C::kXStride;
+  const unsigned wrow = smem_u32(xbuf + C::xoff(lane));
   static_for<0, C::kR2>([&](auto kc) {
     constexpr int k1 = decltype(kc)::value;
     if constexpr (k1 == 0) {
       static_for<0, C::kP>([&](auto pc_) {
         constexpr int p = decltype(pc_)::value;
-        const PC& y = v[p * C::kR2];
-        wrow[p * C::kR2] = make_uint4(static_cast<unsigned>(y.re), static_cast<unsigned>(y.re >> 32),
-                                      static_cast<unsigned>(y.im), static_cast<unsigned>(y.im >> 32));
+        sts_pc<16 * (p * C::kR2)>(wrow, v[p * C::kR2].re, v[p * C::kR2].im);
       });
     } else {
       const float2 w = tw[(k1 - 1) * 32 + lane];
@@ -201,20 +215,16 @@ __device__ __forceinline__ void fft2_forward(PC (&v)[32], uint4* __restrict__ xb
         const PC& y = v[p * C::kR2 + k1];
         const pf re = fma2s(y.im, -w.y, mul2s(y.re, w.x));
         const pf im = fma2s(y.im, w.x, mul2s(y.re, w.y));
-        wrow[p * C::kR2 + k1] = make_uint4(static_cast<unsigned>(re), static_cast<unsigned>(re >> 32),
-                                           static_cast<unsigned>(im), static_cast<unsigned>(im >> 32));
+        sts_pc<16 * (p * C::kR2 + k1)>(wrow, re, im);
       });
     }
   });
   __syncwarp();
   // transposed read: lane j takes column j of every row n1, placed bit-reversed for the DIT
-  const uint4* rcol = xbuf + lane;
+  const unsigned rcol = smem_u32(xbuf + lane);
   static_for<0, 32>([&](auto nc) {
     constexpr int n1 = decltype(nc)::value;
-    const uint4 e = rcol[n1 * C::kXStride];
-    PC& d = v[brev(n1, 5)];
-    d.re = (static_cast<pf>(e.y) << 32) | e.x;
-    d.im = (static_cast<pf>(e.w) << 32) | e.z;
+    v[brev(n1, 5)] = lds_pc<16 * C::xoff(n1)>(rcol);
   });
   dit<32, 0, false, 2>(v);
   __syncwarp();   // exchange buffer free again

@@ -234,7 +234,10 @@ __global__ void __launch_bounds__(kMstftWarps * 32, 2) mstft_bwd_kernel(const Pl
 #pragma unroll
     for (int rd = 0; rd < kMaxMelRounds; ++rd)
 #pragma unroll
-      for (int q = 0; q < C::kQ; ++q) gmbuf[q * 128 + rd * 32 + lane] = gm[rd][q];
+      for (int q = 0; q < C::kQ; ++q) {
+        const int row = (rd < p.mel_rounds) ? (sm.mel_lo[rd * 32 + lane] >> 16) : 0x7fff;
+        if (row < 128) gmbuf[q * 128 + row] = gm[rd][q];
+      }
     __syncwarp();
     // gD on the Hermitian pairs (in registers), scaled for the adjoint: interior bins / 2, DC and Nyquist real
     auto grad_bin = [&](float2 X, int q, int k, float half) -> float2 {

@@ -5,7 +5,9 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
+#include <functional>
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -30,7 +32,7 @@ struct PlanDev {
                           //                  s < 8: (tan phi, cos phi); s >= 8: (cot phi, sin phi)   (fft2.cuh split2)
   // banded mel, ELL per round of 32 rows: melw[round_off[r] + it*32 + lane], it < round_len[r]
   const float* melw;
-  const int* mel_lo;      // [32*rounds]      first non-zero column of each row (0 for padding rows)
+  const int* mel_lo;      // [32*rounds]      slot (round, lane): first bin read | mel row << 16 (row 0x7fff: empty slot)
   int mel_rounds;
   int mel_round_off[kMaxMelRounds];
   int mel_round_len[kMaxMelRounds];
@@ -177,7 +179,7 @@ inline std::string build_plan(const sb200_config& c, sb200_plan* p, int* st) {
   const std::vector<float>& mb = p->mel_dense;
   const int rounds = (c.n_mel + 31) / 32;
   d.mel_rounds = rounds;
-  std::vector<int> lo(32 * rounds, 0), len(32 * rounds, 0);
+  std::vector<int> lo(c.n_mel, 0), len(c.n_mel, 0);
   for (int m = 0; m < c.n_mel; ++m) {
     int first = -1, last = -1;
     for (int k = 0; k < F; ++k)
@@ -185,19 +187,73 @@ inline std::string build_plan(const sb200_config& c, sb200_plan* p, int* st) {
     if (first >= 0) { lo[m] = first; len[m] = last - first + 1; }
     if (last >= F - 1) return "mel filter reaches the Nyquist bin (requires fmax < sample_rate/2)";
   }
+  // Rows are dealt to (round, lane) slots longest first, so a round's 32 lanes have similar lengths; inside a round the
+  // lanes of each half-warp get distinct start residues mod 16 (the 64-bit magnitude loads of a half-warp then hit 16
+  // different bank pairs) by starting a row up to (round length - row length) bins early with zero weights: bipartite
+  // matching rows -> (half, residue) slots.
+  std::vector<int> order(c.n_mel);
+  for (int m = 0; m < c.n_mel; ++m) order[m] = m;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return len[a] > len[b]; });
+  std::vector<int> slot_row(32 * rounds, -1), slot_lo(32 * rounds, 0);
   std::vector<float> melw;
   for (int r = 0; r < kMaxMelRounds; ++r) { d.mel_round_off[r] = 0; d.mel_round_len[r] = 0; }
   for (int r = 0; r < rounds; ++r) {
+    const int nrows = std::min(32, c.n_mel - 32 * r);
+    const int* rows = order.data() + 32 * r;
     int mx = 0;
-    for (int l = 0; l < 32; ++l) mx = std::max(mx, len[r * 32 + l]);
-    d.mel_round_off[r] = static_cast<int>(melw.size());
-    d.mel_round_len[r] = mx;
-    for (int it = 0; it < mx; ++it)
-      for (int l = 0; l < 32; ++l) {
-        const int m = r * 32 + l;
-        melw.push_back((m < c.n_mel && it < len[m]) ? mb[static_cast<size_t>(m) * F + lo[m] + it] : 0.f);
+    for (int i = 0; i < nrows; ++i) mx = std::max(mx, len[rows[i]]);
+    std::vector<int> owner(32, -1), shift(nrows, -1);   // slot = half * 16 + residue
+    std::function<bool(int, std::vector<char>&)> place = [&](int i, std::vector<char>& seen) -> bool {
+      const int m = rows[i];
+      for (int dsh = 0; dsh <= std::min(mx - len[m], lo[m]); ++dsh)
+        for (int h = 0; h < 2; ++h) {
+          const int sl = h * 16 + ((lo[m] - dsh) & 15);
+          if (seen[sl]) continue;
+          seen[sl] = 1;
+          if (owner[sl] < 0 || place(owner[sl], seen)) {
+            owner[sl] = i;
+            shift[i] = dsh;
+            return true;
+          }
+        }
+      return false;
+    };
+    std::vector<int> lane_of(nrows, -1);
+    for (int i = 0; i < nrows; ++i) {
+      std::vector<char> seen(32, 0);
+      place(i, seen);
+    }
+    std::vector<char> lane_used(32, 0);
+    std::vector<int> half_fill(2, 0);
+    for (int sl = 0; sl < 32; ++sl)
+      if (owner[sl] >= 0) {
+        const int h = sl / 16, lane = h * 16 + half_fill[h]++;
+        lane_of[owner[sl]] = lane;
+        lane_used[lane] = 1;
       }
+    for (int i = 0; i < nrows; ++i)
+      if (lane_of[i] < 0) {   // unmatched (bank conflicts accepted): any free lane, no shift
+        int lane = 0;
+        while (lane_used[lane]) ++lane;
+        lane_used[lane] = 1;
+        lane_of[i] = lane;
+        shift[i] = 0;
+      }
+    d.mel_round_off[r] = static_cast<int>(melw.size());
+    const int mx8 = (mx + 7) / 8 * 8;   // kernels walk a round in fully unrolled chunks of 8 taps (zero weights pad)
+    d.mel_round_len[r] = mx8;
+    melw.resize(melw.size() + static_cast<size_t>(mx8) * 32, 0.f);
+    for (int i = 0; i < nrows; ++i) {
+      const int m = rows[i], lane = lane_of[i], start = lo[m] - shift[i];
+      slot_row[32 * r + lane] = m;
+      slot_lo[32 * r + lane] = start;
+      for (int it = 0; it < len[m]; ++it)
+        melw[d.mel_round_off[r] + static_cast<size_t>(it + shift[i]) * 32 + lane] = mb[static_cast<size_t>(m) * F + lo[m] + it];
+    }
   }
+  // packed slot table: low 16 bits = first bin read, high bits = mel row (0x7fff: empty slot)
+  std::vector<int> slots(32 * rounds);
+  for (int i = 0; i < 32 * rounds; ++i) slots[i] = slot_lo[i] | ((slot_row[i] < 0 ? 0x7fff : slot_row[i]) << 16);
   d.melw_count = static_cast<int>(melw.size());
   d.mel_kmin = F;
   d.mel_kmax = -1;
@@ -224,7 +280,7 @@ inline std::string build_plan(const sb200_config& c, sb200_plan* p, int* st) {
 #define SB200_UP(vec, field) \
   if ((e = upload(p, vec, &d.field)) != cudaSuccess) return std::string("cuda upload: ") + cudaGetErrorString(e);
   SB200_UP(wf, window) SB200_UP(wout, wout) SB200_UP(wnorm, wnorm) SB200_UP(wsq, wsq) SB200_UP(tw, tw) SB200_UP(ws, ws) SB200_UP(sp2, sp2)
-  SB200_UP(melw, melw) SB200_UP(lo, mel_lo) SB200_UP(r0, col_r0) SB200_UP(c0, col_c0) SB200_UP(c1, col_c1)
+  SB200_UP(melw, melw) SB200_UP(slots, mel_lo) SB200_UP(r0, col_r0) SB200_UP(c0, col_c0) SB200_UP(c1, col_c1)
 #undef SB200_UP
   *st = SB200_OK;
   return "";
