@@ -226,10 +226,12 @@ __global__ void __launch_bounds__(kFeatWarps * 32, 2) stft_feature_kernel(const 
   float2* buf = sm.bufs + warp * C::kBufF2;
   const int rk = lane & 3, rm = (4 - rk) & 3;   // (-i)^k rotation index for bins k = lane + 32 i and Nz - k
   const long long warps_total = static_cast<long long>(gridDim.x) * kFeatWarps;
-  for (long long item = static_cast<long long>(blockIdx.x) * kFeatWarps + warp; item < a.bd.total_items;
-       item += warps_total) {
-    Item it = decode_item(a.bd, item, 2 * C::kQ);   // an item is 2Q frames (packed-engine granularity): two passes
-    for (int half = 0; half < 2 && it.t0 < it.T; ++half, it.t0 += C::kQ) {
+  // an item is 2Q frames (packed-engine granularity); this engine takes it as two independent Q-frame passes
+  for (long long sub = static_cast<long long>(blockIdx.x) * kFeatWarps + warp; sub < 2 * a.bd.total_items;
+       sub += warps_total) {
+    Item it = decode_item(a.bd, sub >> 1, 2 * C::kQ);
+    it.t0 += static_cast<int>(sub & 1) * C::kQ;
+    if (it.t0 < it.T) {
     float2 v[32];
     load_frames<N, PRE>(v, a.x + it.sig_base, it.L, it.t0, it.T, p.hop, a.pre, sm.win, lane);
     fft_forward<N>(v, buf, sm.tw, lane);

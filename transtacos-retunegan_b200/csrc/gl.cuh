@@ -158,12 +158,14 @@ __global__ void __launch_bounds__(kGlWarps * 32, 2) istft_frames_kernel(const Pl
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float2* buf = sm.bufs + warp * C::kBufF2;
   const int rk = lane & 3, rm = (4 - rk) & 3;
-  for (long long item = static_cast<long long>(blockIdx.x) * kGlWarps + warp; item < a.g.bd.total_items;
-       item += static_cast<long long>(gridDim.x) * kGlWarps) {
+  // an item is 2Q frames (packed-engine granularity); this engine takes it as two independent Q-frame passes
+  for (long long sub = static_cast<long long>(blockIdx.x) * kGlWarps + warp; sub < 2 * a.g.bd.total_items;
+       sub += static_cast<long long>(gridDim.x) * kGlWarps) {
     int b, t0;
-    gl_decode(a.g, item, 2 * C::kQ, &b, &t0);   // an item is 2Q frames: two passes
+    gl_decode(a.g, sub >> 1, 2 * C::kQ, &b, &t0);
+    t0 += static_cast<int>(sub & 1) * C::kQ;
     const GlRow row = gl_row(a.g, b, N, p.hop);
-    for (int half = 0; half < 2 && t0 < row.T; ++half, t0 += C::kQ) {
+    if (t0 < row.T) {
     auto fetch = [&](long long idx) -> float2 {
       if (a.spec) return __ldg(a.spec + idx);
       float s, c;
@@ -214,13 +216,14 @@ __global__ void __launch_bounds__(kGlWarps * 32, 2) gl_iter_kernel(const PlanDev
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float2* buf = sm.bufs + warp * C::kBufF2;
   const int rk = lane & 3, rm = (4 - rk) & 3;
-  for (long long item = static_cast<long long>(blockIdx.x) * kGlWarps + warp; item < a.g.bd.total_items;
-       item += static_cast<long long>(gridDim.x) * kGlWarps) {
+  for (long long sub = static_cast<long long>(blockIdx.x) * kGlWarps + warp; sub < 2 * a.g.bd.total_items;
+       sub += static_cast<long long>(gridDim.x) * kGlWarps) {
     int b, t0;
-    gl_decode(a.g, item, 2 * C::kQ, &b, &t0);
+    gl_decode(a.g, sub >> 1, 2 * C::kQ, &b, &t0);
+    t0 += static_cast<int>(sub & 1) * C::kQ;
     const GlRow row = gl_row(a.g, b, N, p.hop);
     const float* fb = a.fb_in + row.frame_base * C::kWin;
-    for (int half = 0; half < 2 && t0 < row.T; ++half, t0 += C::kQ) {
+    if (t0 < row.T) {
     float2 v[32];
     // 1. gather the current signal under each analysis frame (reflect padded, np.pad mode='reflect')
     static_for<0, C::kQ>([&](auto qc) {

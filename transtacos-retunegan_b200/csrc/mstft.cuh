@@ -94,10 +94,12 @@ __global__ void __launch_bounds__(kMstftWarps * 32, 2) mstft_fwd_kernel(const Pl
   float2* buf = sm.bufs + warp * C::kBufF2;
   float acc = 0.f;
   const long long chs = static_cast<long long>(a.Tf) * C::kF;
-  for (long long item = static_cast<long long>(blockIdx.x) * kMstftWarps + warp; item < a.bd.total_items;
-       item += static_cast<long long>(gridDim.x) * kMstftWarps) {
-    Item it = decode_item(a.bd, item, 2 * C::kQ);   // an item is 2Q frames: two passes
-    for (int half = 0; half < 2 && it.t0 < it.T; ++half, it.t0 += C::kQ) {
+  // an item is 2Q frames (packed-engine granularity); this engine takes it as two independent Q-frame passes
+  for (long long sub = static_cast<long long>(blockIdx.x) * kMstftWarps + warp; sub < 2 * a.bd.total_items;
+       sub += static_cast<long long>(gridDim.x) * kMstftWarps) {
+    Item it = decode_item(a.bd, sub >> 1, 2 * C::kQ);
+    it.t0 += static_cast<int>(sub & 1) * C::kQ;
+    if (it.t0 < it.T) {
     const long long row0 = (static_cast<long long>(it.b) * 2 * a.Tf + it.t0) * C::kF;
     float2 v[32];
     float mr[kMaxMelRounds][C::kQ];
@@ -179,10 +181,11 @@ __global__ void __launch_bounds__(kMstftWarps * 32, 2) mstft_bwd_kernel(const Pl
   const int rk = lane & 3, rm = (4 - rk) & 3;
   const float gl = a.g_loss ? __ldg(a.g_loss) * a.loss_scale : 0.f;
   const long long chs = static_cast<long long>(a.Tf) * C::kF;
-  for (long long item = static_cast<long long>(blockIdx.x) * kMstftWarps + warp; item < a.bd.total_items;
-       item += static_cast<long long>(gridDim.x) * kMstftWarps) {
-    Item it = decode_item(a.bd, item, 2 * C::kQ);
-    for (int half = 0; half < 2 && it.t0 < it.T; ++half, it.t0 += C::kQ) {
+  for (long long sub = static_cast<long long>(blockIdx.x) * kMstftWarps + warp; sub < 2 * a.bd.total_items;
+       sub += static_cast<long long>(gridDim.x) * kMstftWarps) {
+    Item it = decode_item(a.bd, sub >> 1, 2 * C::kQ);
+    it.t0 += static_cast<int>(sub & 1) * C::kQ;
+    if (it.t0 < it.T) {
     float2 v[32];
     load_frames<N, false>(v, a.yg + it.sig_base, it.L, it.t0, it.T, p.hop, 0.f, sm.win, lane);
     fft_forward<N>(v, buf, sm.tw, lane);

@@ -75,7 +75,7 @@ int make_batch_signal(const sb200_plan* plan, const sb200_batch* b, BatchDev* ou
 template <int N>
 int launch_features_spec(const sb200_plan* plan, const FeatArgs& a, cudaStream_t st) {
   const size_t smem = feat_smem_bytes<N>(plan->dev);
-  const long long ctas_needed = (a.bd.total_items + kFeatWarps - 1) / kFeatWarps;
+  const long long ctas_needed = (2 * a.bd.total_items + kFeatWarps - 1) / kFeatWarps;
   const int grid = static_cast<int>(std::min<long long>(ctas_needed, 2LL * sm_count()));
   if (a.pre != 0.f) {
     cudaFuncSetAttribute(stft_feature_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
