@@ -191,7 +191,7 @@ def make_stft_mel(sb, torch, B=64, rot=6):
     w.step, w.e2e = step, e2e
     w.units = B * L5 / SR
     w.alg_bytes = B * (4 * L5 + 4 * T5 * (F + N_MEL))          # 4L + 4T(F+M) per utterance
-    w.dominant = "stft_feature_kernel<2048,true>"
+    w.dominant = "stft_feature2_kernel<2048,true,true,4>"
     w.h2d = B * L5 * 4
     w.d2h = B * T5 * (F + N_MEL) * 4
     w.note = (f"{rot} rotating input/output sets ({rot * (w.alg_bytes) / 1e6:.0f} MB) > 126 MB L2 between reuses; "
@@ -224,7 +224,7 @@ def make_griffinlim(sb, torch, B=1, form="rtg", rot=4):
     w.units = B * L5 / SR
     per_iter = B * (4 * F * T5 + 8 * L5 + (16 * F * T5 if frm == 1 else 0))   # SURVEY.md 8d streaming model
     w.alg_bytes = per_iter
-    w.dominant = f"gl_iter_kernel<2048,{frm}>"
+    w.dominant = f"gl2_kernel<2048,{2 + frm}>"
     w.launches_dominant_per_step = n_iter
     w.h2d, w.d2h = F * T5 * 4, L5 * 4
     w.note = f"{'fast form, momentum 0.7' if frm else 'angle form'}; {n_iter} iterations + initial/final ISTFT; state L2/HBM resident"

@@ -131,7 +131,8 @@ int sb200_inv_preemphasis(const float* x, const sb200_batch* batch, float k, flo
  * (librosa.istft length=None) else `length` (uniform) / sig_len[b] (ragged).  Output row b starts at
  * b*stride (uniform) or sig_off[b] (ragged).
  *
- * sb200_griffinlim_workspace_bytes: bytes of `workspace` needed for a batch of total_frames frames.
+ * sb200_griffinlim_workspace_bytes: bytes of `workspace` needed for a batch of n_rows utterances with total_frames frames
+ *   in all (four signal buffers of total_frames*hop + n_rows*win floats; form 1 adds the previous spectrum).
  * sb200_istft: y = librosa.istft(spec) (transtacos/audio.py:147-148), spec complex [frames, F].
  * sb200_griffinlim:
  *   form 0 (transtacos/audio.py:130-140 _griffin_lim): angles = exp(i angle(STFT(y))), no momentum;
@@ -140,7 +141,7 @@ int sb200_inv_preemphasis(const float* x, const sb200_batch* batch, float k, flo
  *   (the np.random.rand draw of the reference; initial angles = exp(2 pi i u)).  n_iter iterations, then
  *   the final ISTFT.  inv_preemph != 0 additionally applies inv_preemphasis to the result
  *   (transtacos/audio.py:96).  y: float32 output. */
-int64_t sb200_griffinlim_workspace_bytes(const sb200_plan* plan, int64_t total_frames, int32_t form);
+int64_t sb200_griffinlim_workspace_bytes(const sb200_plan* plan, int64_t total_frames, int32_t n_rows, int32_t form);
 int sb200_istft(const sb200_plan* plan, const float* spec, const sb200_batch* frames_batch, int64_t length,
                 float* y, void* workspace, sb200_stream stream);
 int sb200_griffinlim(const sb200_plan* plan, const float* S, const float* init_phase,

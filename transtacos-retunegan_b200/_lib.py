@@ -46,7 +46,7 @@ SIGNATURES = {
     "sb200_spec_to_amplitude": (C.c_int, [_P, _I64, _I32, _F, _F, _F, _F, _P, _P]),
     "sb200_preemphasis": (C.c_int, [_P, C.POINTER(Batch), _F, _P, _P]),
     "sb200_inv_preemphasis": (C.c_int, [_P, C.POINTER(Batch), _F, _P, _P]),
-    "sb200_griffinlim_workspace_bytes": (_I64, [_P, _I64, _I32]),
+    "sb200_griffinlim_workspace_bytes": (_I64, [_P, _I64, _I32, _I32]),
     "sb200_istft": (C.c_int, [_P, _P, C.POINTER(Batch), _I64, _P, _P, _P]),
     "sb200_griffinlim": (C.c_int, [_P, _P, _P, C.POINTER(Batch), _I64, _I32, _F, _I32, _F, _P, _P, _P]),
     "sb200_mstft_saved_bytes": (_I64, [C.POINTER(_P), _I32, _I32, _I64]),

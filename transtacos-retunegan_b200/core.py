@@ -253,7 +253,7 @@ def istft(plan: Plan, spec_fm: torch.Tensor, fb: FramesBatch) -> torch.Tensor:
     lib = _lib.load()
     sp = torch.view_as_real(spec_fm.contiguous())
     y = torch.empty(fb.total_out, device=spec_fm.device, dtype=torch.float32)
-    ws = _workspace(lib.sb200_griffinlim_workspace_bytes(plan.handle, fb.total_frames, 0), spec_fm.device, "gl")
+    ws = _workspace(lib.sb200_griffinlim_workspace_bytes(plan.handle, fb.total_frames, fb.B, 0), spec_fm.device, "gl")
     check(lib.sb200_istft(plan.handle, ptr(sp), C.byref(fb.c), fb.length_arg, ptr(y), ptr(ws), stream_ptr()), "istft")
     return y
 
@@ -264,7 +264,7 @@ def griffinlim(plan: Plan, S_fm: torch.Tensor, phase_fm: torch.Tensor, fb: Frame
     lib = _lib.load()
     assert S_fm.is_contiguous() and phase_fm.is_contiguous() and S_fm.shape == phase_fm.shape == (fb.total_frames, plan.F)
     y = torch.empty(fb.total_out, device=S_fm.device, dtype=torch.float32)
-    ws = _workspace(lib.sb200_griffinlim_workspace_bytes(plan.handle, fb.total_frames, form), S_fm.device, "gl")
+    ws = _workspace(lib.sb200_griffinlim_workspace_bytes(plan.handle, fb.total_frames, fb.B, form), S_fm.device, "gl")
     pre_in_call = inv_preemph if fb.uniform else 0.0
     check(lib.sb200_griffinlim(plan.handle, ptr(S_fm), ptr(phase_fm), C.byref(fb.c), fb.length_arg, int(n_iter),
                                float(momentum), int(form), float(pre_in_call), ptr(y), ptr(ws), stream_ptr()),

@@ -254,4 +254,113 @@ __device__ __forceinline__ void split2(const PC& Zk, const PC& Zr, float2 tw, PC
 
 __device__ __forceinline__ pf norm2(const PC& a) { return fma2(a.re, a.re, mul2(a.im, a.im)); }
 
+// ======================================= inverse direction ==========================================================
+// Half butterfly a' = a + w b (the b' = a - w b output is pruned), same twiddle convention as bfly<I, INV>.
+template <int I, bool INV>
+__device__ __forceinline__ void bfly_half(PC& a, const PC& b) {
+  static_assert(I >= 0 && I < 16, "twiddle index");
+  if constexpr (I == 0) {
+    a.re = add2(a.re, b.re); a.im = add2(a.im, b.im);
+  } else if constexpr (I == 8) {
+    if constexpr (!INV) { a.re = add2(a.re, b.im); a.im = sub2(a.im, b.re); }
+    else { a.re = sub2(a.re, b.im); a.im = add2(a.im, b.re); }
+  } else {
+    constexpr double c = dcos32(I), s = INV ? -dsin32(I) : dsin32(I);   // w = c - i s
+    if constexpr ((c < 0 ? -c : c) >= (s < 0 ? -s : s)) {
+      constexpr float t = static_cast<float>(s / c), cf = static_cast<float>(c);
+      const pf tr = fma2s(b.im, t, b.re);
+      const pf ti = fma2s(b.re, -t, b.im);
+      a.re = fma2s(tr, cf, a.re); a.im = fma2s(ti, cf, a.im);
+    } else {
+      constexpr float k = static_cast<float>(c / s), sf = static_cast<float>(s);
+      const pf tr = fma2s(b.re, k, b.im);
+      const pf tn = fma2s(b.im, -k, b.re);
+      a.re = fma2s(tr, sf, a.re); a.im = fma2s(tn, -sf, a.im);
+    }
+  }
+}
+
+// Radix-2 DIT DFT of LEN points whose upper half of OUTPUTS is not needed: v[BASE + j], j < LEN/2, on exit.
+template <int LEN, int BASE, bool INV>
+__device__ __forceinline__ void dit_pruned_out(PC (&v)[32]) {
+  constexpr int H = LEN / 2;
+  dit<H, BASE, INV, 2>(v);
+  dit<H, BASE + H, INV, 2>(v);
+  static_for<0, H>([&](auto jc) {
+    constexpr int j = decltype(jc)::value;
+    bfly_half<j * (32 / LEN), INV>(v[BASE + j], v[BASE + j + H]);
+  });
+}
+
+// ---- inverse of fft2_forward: v[k2] = Z'_p[k1 + R2 k2] in lane j = p*R2 + k1  ->  v[p*R2 + r] = sum_k Z'_p[k] e^{+2 pi i k n / Nz},
+// n = lane + 32 r, r < R (outputs n >= Nz/2, outside the window support, are pruned).  No 1/Nz scaling.
+template <int N>
+__device__ __forceinline__ void fft2_inverse(PC (&v)[32], uint4* __restrict__ xbuf, const float2* __restrict__ tw, int lane) {
+  using C = Fft2Cfg<N>;
+  {
+    PC u[32];
+    static_for<0, 32>([&](auto kc) {
+      constexpr int k2 = decltype(kc)::value;
+      u[brev(k2, 5)] = v[k2];
+    });
+    dit<32, 0, true, 2>(u);   // u[n1] = sum_k2 Z'[k1 + R2 k2] e^{+2 pi i n1 k2 / 32}
+    // transposed store: element (row = n1, col = lane)
+    const unsigned wcol = smem_u32(xbuf + lane);
+    static_for<0, 32>([&](auto nc) {
+      constexpr int n1 = decltype(nc)::value;
+      sts_pc<16 * C::xoff(n1)>(wcol, u[n1].re, u[n1].im);
+    });
+  }
+  __syncwarp();
+  // row read: lane n1 takes (p, k1) for all columns, conjugate twiddle, placed bit-reversed for the DIT over k1
+  const unsigned rrow = smem_u32(xbuf + C::xoff(lane));
+  static_for<0, C::kR2>([&](auto kc) {
+    constexpr int k1 = decltype(kc)::value;
+    if constexpr (k1 == 0) {
+      static_for<0, C::kP>([&](auto pc_) {
+        constexpr int p = decltype(pc_)::value;
+        v[p * C::kR2] = lds_pc<16 * (p * C::kR2)>(rrow);
+      });
+    } else {
+      const float2 w = tw[(k1 - 1) * 32 + lane];
+      static_for<0, C::kP>([&](auto pc_) {
+        constexpr int p = decltype(pc_)::value;
+        const PC y = lds_pc<16 * (p * C::kR2 + k1)>(rrow);
+        PC& o = v[p * C::kR2 + brev(k1, C::kLogR2)];
+        o.re = fma2s(y.im, w.y, mul2s(y.re, w.x));     // y * conj(w)
+        o.im = fma2s(y.re, -w.y, mul2s(y.im, w.x));
+      });
+    }
+  });
+  __syncwarp();   // exchange buffer free again
+  static_for<0, C::kP>([&](auto pc_) {
+    constexpr int p = decltype(pc_)::value;
+    dit_pruned_out<C::kR2, p * C::kR2, true>(v);
+  });
+}
+
+// ---- inverse Hermitian split on packed data ----------------------------------------------------------------------
+// P = A'[k], Q = conj(A'[Nz-k]) (the form split2 returns); tw as in split2.  Returns Zk = 2 Z'[k] and Zr = 2 Z'[Nz-k]
+// with Z' the spectrum of z'[n] = a'[2n] + i a'[2n+1], a' = N * irfft(A') restricted to the window support:
+//   Zk = Fe + conj(g) G,  Zr = conj(Fe - conj(g) G),  Fe = P + Q, G = P - Q, g = -i w_N^k.
+// The factor 2 and the 1/Nz of the inverse FFT are folded into the synthesis window table (1/N overall).
+template <bool SINFORM>
+__device__ __forceinline__ void split2_inv(const PC& P, const PC& Q, float2 tw, PC& Zk, PC& Zr) {
+  const pf fer = add2(P.re, Q.re), fei = add2(P.im, Q.im);
+  const pf gr = sub2(P.re, Q.re), gi = sub2(P.im, Q.im);
+  if constexpr (!SINFORM) {   // conj(g) G = c [(-t gr - gi) + i (gr - t gi)]
+    const pf nr = fma2s(gr, tw.x, gi);
+    const pf ui = fma2s(gi, -tw.x, gr);
+    const pf cu = mul2s(ui, tw.y);
+    Zk.re = fma2s(nr, -tw.y, fer); Zk.im = add2(cu, fei);
+    Zr.re = fma2s(nr, tw.y, fer);  Zr.im = sub2(cu, fei);
+  } else {                    // conj(g) G = s [(-gr - k gi) + i (k gr - gi)]
+    const pf nr = fma2s(gi, tw.x, gr);
+    const pf nui = fma2s(gr, -tw.x, gi);
+    const pf cu = mul2s(nui, -tw.y);
+    Zk.re = fma2s(nr, -tw.y, fer); Zk.im = add2(cu, fei);
+    Zr.re = fma2s(nr, tw.y, fer);  Zr.im = sub2(cu, fei);
+  }
+}
+
 }  // namespace sb200

@@ -26,6 +26,9 @@ struct PlanDev {
   const float* wout;      // [win]            window / n_fft                      (synthesis, un-normalised OLA)
   const float* wnorm;     // [win]            window / (n_fft * wss_interior[m])  (synthesis, interior frames)
   const float* wsq;       // [win]            window^2
+  const float* wedge;     // [2][nov][win]    synthesis window / (n_fft * wss) for the first nov frames ([0][t]) and the last
+                          //                  nov frames ([1][t'], t' = n_frames-1-t) of an utterance with >= 2 nov + 1 frames
+  int nov;                // (win - 1) / hop: frames overlapping a given frame on each side
   const float2* tw;       // [(2R-1)*32]      w_Nz^{k1*lane}, row k1-1
   const float2* ws;       // [Nz/2+1]         -0.5i * w_N^k
   const float2* sp2;      // [17*32]          packed-engine split twiddles, slot s, lane l: k = l%R2 + R2*s, phi = 2 pi k/N:
@@ -155,6 +158,22 @@ inline std::string build_plan(const sb200_config& c, sb200_plan* p, int* st) {
     wnorm[m] = static_cast<float>(wss[m] > 1.1754943508222875e-38 ? w[m] / (N * wss[m]) : w[m] / N);
   }
   p->window_f32 = wf;
+  // edge-frame synthesis scales (librosa.istft divides by the window-sum-square of the frames that exist)
+  const int nov = (win - 1) / hop;
+  d.nov = nov;
+  std::vector<float> wedge(static_cast<size_t>(2) * std::max(nov, 1) * win, 0.f);
+  for (int side = 0; side < 2; ++side)
+    for (int t = 0; t < nov; ++t)
+      for (int m = 0; m < win; ++m) {
+        float acc = 0.f;   // same float accumulation order as synth_scale_edge (gl.cuh)
+        for (int dd = -nov; dd <= nov; ++dd) {
+          const int off = m - dd * hop;
+          const bool exists = side == 0 ? (t + dd >= 0) : (dd <= t);
+          if (exists && off >= 0 && off < win) acc += wsq[off];
+        }
+        const float wv = wf[m] / N;
+        wedge[(static_cast<size_t>(side) * nov + t) * win + m] = acc > 1.1754943508222875e-38f ? wv / acc : wv;
+      }
   std::vector<float2> tw(static_cast<size_t>(R2 - 1) * 32), ws(Nz / 2 + 2);
   for (int k1 = 1; k1 < R2; ++k1)
     for (int l = 0; l < 32; ++l) {
@@ -279,7 +298,7 @@ inline std::string build_plan(const sb200_config& c, sb200_plan* p, int* st) {
   cudaError_t e;
 #define SB200_UP(vec, field) \
   if ((e = upload(p, vec, &d.field)) != cudaSuccess) return std::string("cuda upload: ") + cudaGetErrorString(e);
-  SB200_UP(wf, window) SB200_UP(wout, wout) SB200_UP(wnorm, wnorm) SB200_UP(wsq, wsq) SB200_UP(tw, tw) SB200_UP(ws, ws) SB200_UP(sp2, sp2)
+  SB200_UP(wf, window) SB200_UP(wout, wout) SB200_UP(wnorm, wnorm) SB200_UP(wsq, wsq) SB200_UP(wedge, wedge) SB200_UP(tw, tw) SB200_UP(ws, ws) SB200_UP(sp2, sp2)
   SB200_UP(melw, melw) SB200_UP(slots, mel_lo) SB200_UP(r0, col_r0) SB200_UP(c0, col_c0) SB200_UP(c1, col_c1)
 #undef SB200_UP
   *st = SB200_OK;

@@ -8,6 +8,7 @@
 #include "feat.cuh"
 #include "feat2.cuh"
 #include "gl.cuh"
+#include "gl2.cuh"
 #include "mstft.cuh"
 #include "misc.cuh"
 
