@@ -81,6 +81,12 @@ __device__ __forceinline__ float2 rot_i(float2 a, int j) {
   return make_float2((j == 1 || j == 2) ? -x : x, (j >= 2) ? -y : y);
 }
 
+// Edge-frame synthesis weights for an utterance too short for the plan's head / tail tables (rolled, out of line).
+__device__ __noinline__ void gl2_edge_weights(const PlanDev& p, int t, int n_frames, float* out, int lane) {
+#pragma unroll 1
+  for (int m = lane; m < p.win; m += 32) out[m] = synth_scale_edge(p, t, n_frames, m);
+}
+
 template <int N, int MODE>
 __global__ void __launch_bounds__(kGl2Warps * 32, 1) gl2_kernel(const PlanDev p, const Gl2Args a) {
   using C = Fft2Cfg<N>;
@@ -112,12 +118,28 @@ __global__ void __launch_bounds__(kGl2Warps * 32, 1) gl2_kernel(const PlanDev p,
       const int span = (nf - 1) * hop + C::kWin;
       const float* ya = a.ya_in + sbase;
       const float* yb = a.yb_in + sbase;
-      for (int j = threadIdx.x; j < span; j += blockDim.x) {
-        long long i = u0 + j - N / 4;               // signal index of offset coordinate u0 + j
-        if (i < 0) i = -i;
-        if (i >= row.Ly) i = 2 * (row.Ly - 1) - i;
-        const long long uu = i + N / 4;
-        sm.ytile[j] = uu < cover ? __ldg(ya + uu) + __ldg(yb + uu) : 0.f;
+      const long long i_lo = u0 - N / 4, i_hi = u0 + span - 1 - N / 4;   // signal indices under the tile
+      if (i_lo >= 0 && i_hi < row.Ly && u0 + span <= cover && (hop & 3) == 0) {
+        // no reflection: offset coordinate u0 + j maps to itself; 16-byte loads (sbase, u0 and span are multiples of 4)
+        const float4* ya4 = reinterpret_cast<const float4*>(ya + u0);
+        const float4* yb4 = reinterpret_cast<const float4*>(yb + u0);
+        float4* yt4 = reinterpret_cast<float4*>(sm.ytile);
+#pragma unroll 5
+        for (int j = threadIdx.x; j < span / 4; j += kGl2Warps * 32) {
+          const float4 p4 = __ldg(ya4 + j), q4 = __ldg(yb4 + j);
+          yt4[j] = make_float4(p4.x + q4.x, p4.y + q4.y, p4.z + q4.z, p4.w + q4.w);
+        }
+      } else {
+        const int Ly = static_cast<int>(row.Ly), cov = static_cast<int>(cover), base = static_cast<int>(u0) - N / 4;
+#pragma unroll 4
+        for (int j = threadIdx.x; j < span; j += kGl2Warps * 32) {
+          int i = base + j;                            // signal index of offset coordinate u0 + j
+          i = i < 0 ? -i : i;
+          i = i >= Ly ? 2 * (Ly - 1) - i : i;
+          const int uu = min(i + N / 4, cov - 1);
+          const float val = __ldg(ya + uu) + __ldg(yb + uu);
+          sm.ytile[j] = (i + N / 4 < cov) ? val : 0.f;
+        }
       }
       __syncthreads();
     }
@@ -176,11 +198,43 @@ __global__ void __launch_bounds__(kGl2Warps * 32, 1) gl2_kernel(const PlanDev p,
         r.im = conj_it ? pk(-xa.y, -xb.y) : pk(xa.y, xb.y);
         return r;
       };
-      // phase update of one held value (modes 2 / 3); `on` = this lane owns the bin
-      auto update = [&](const PC& X, int kb, bool on, int rot, bool conj_held) -> PC {
-        float sA = 0.f, sB = 0.f;
-        if (on && okA) sA = __ldg(a.S + rowA + kb);
-        if (on && okB) sB = __ldg(a.S + rowA + C::kF + kb);
+      // ---- modes 2 / 3: per-bin state of the phase update, fetched one slot ahead of its use -------------------------
+      // Loads are unconditional (frames past the end are clamped to the last one and masked), addresses are one base
+      // register per (side, frame) plus a compile-time offset.
+      const long long rowAc = (row.frame_base + min(fA, row.T - 1)) * C::kF, rowBc = (row.frame_base + min(fA + 1, row.T - 1)) * C::kF;
+      const float mA = okA ? 1.f : 0.f, mB = okB ? 1.f : 0.f;
+      const float* const SaA = a.S + rowAc + k1;                // a side, bin k1 + R2 s: + R2 s
+      const float* const SaB = a.S + rowBc + k1;
+      const float* const SbA = a.S + rowAc + C::kNz - k1;       // b side, bin Nz - k1 - R2 s: - R2 s
+      const float* const SbB = a.S + rowBc + C::kNz - k1;
+      float2* const TaA = a.tprev + rowAc + k1;
+      float2* const TaB = a.tprev + rowBc + k1;
+      float2* const TbA = a.tprev + rowAc + C::kNz - k1;
+      float2* const TbB = a.tprev + rowBc + C::kNz - k1;
+      struct SlotLd {
+        float saA, saB, sbA, sbB;
+        float2 taA, taB, tbA, tbB;
+      };
+      auto load_slot = [&](auto sc) -> SlotLd {
+        constexpr int off = C::kR2 * decltype(sc)::value;
+        SlotLd L;
+        L.saA = __ldg(SaA + off) * mA;
+        L.saB = __ldg(SaB + off) * mB;
+        L.sbA = __ldg(SbA - off) * mA;
+        L.sbB = __ldg(SbB - off) * mB;
+        if constexpr (MODE == 3) {
+          if (!a.first) {
+            L.taA = TaA[off];
+            L.taB = TaB[off];
+            L.tbA = TbA[-off];
+            L.tbB = TbB[-off];
+          }
+        }
+        return L;
+      };
+      // phase update of one held value X of both frames: magnitudes sA / sB, previous spectrum tA / tB, stored to dA / dB
+      auto update = [&](const PC& X, float sA, float sB, float2 tA, float2 tB, float2* dA, float2* dB, bool on, int rot,
+                        bool conj_held) -> PC {
         PC o;
         if constexpr (MODE == 2) {
           const pf n2 = norm2(X);
@@ -198,14 +252,11 @@ __global__ void __launch_bounds__(kGl2Warps * 32, 1) gl2_kernel(const PlanDev p,
         } else {
           PC c = X;
           if (!a.first) {
-            float2 tA = make_float2(0.f, 0.f), tB = make_float2(0.f, 0.f);
-            if (on && okA) tA = a.tprev[rowA + kb];
-            if (on && okB) tB = a.tprev[rowA + C::kF + kb];
             c.re = fma2s(pk(tA.x, tB.x), -a.alpha, X.re);
             c.im = fma2s(pk(tA.y, tB.y), -a.alpha, X.im);
           }
-          if (on && okA) a.tprev[rowA + kb] = make_float2(plo(X.re), plo(X.im));
-          if (on && okB) a.tprev[rowA + C::kF + kb] = make_float2(phi(X.re), phi(X.im));
+          if (on && okA) *dA = make_float2(plo(X.re), plo(X.im));
+          if (on && okB) *dB = make_float2(phi(X.re), phi(X.im));
           const pf n2 = norm2(c);
           const pf sc = pk(sA / (sqrtf(plo(n2)) + 1e-16f), sB / (sqrtf(phi(n2)) + 1e-16f));
           o.re = mul2(c.re, sc);
@@ -218,7 +269,17 @@ __global__ void __launch_bounds__(kGl2Warps * 32, 1) gl2_kernel(const PlanDev p,
         // self pair of column 0 (bin Nz/2) first: the exchange below overwrites v[16]
         PC ak, am;
         split2<true>(v[16], v[16], sp[16 * 32], ak, am);
-        ak = update(ak, C::kNz / 2, col0, 0, false);
+        {
+          const float sA = __ldg(a.S + rowAc + C::kNz / 2) * mA, sB = __ldg(a.S + rowBc + C::kNz / 2) * mB;
+          float2 tA = make_float2(0.f, 0.f), tB = tA;
+          if constexpr (MODE == 3) {
+            if (!a.first) {
+              tA = a.tprev[rowAc + C::kNz / 2];
+              tB = a.tprev[rowBc + C::kNz / 2];
+            }
+          }
+          ak = update(ak, sA, sB, tA, tB, a.tprev + rowAc + C::kNz / 2, a.tprev + rowBc + C::kNz / 2, col0, 0, false);
+        }
         PC q;
         q.re = ak.re;
         q.im = sub2(0ull, ak.im);
@@ -238,15 +299,19 @@ __global__ void __launch_bounds__(kGl2Warps * 32, 1) gl2_kernel(const PlanDev p,
         PC zr;
         split2_inv<true>(pS, q, sp[16 * 32], zself, zr);
       }
+      SlotLd nxt{};
+      if constexpr (MODE >= 2) nxt = load_slot(std::integral_constant<int, 0>{});
       static_for<0, 16>([&](auto sc) {
         constexpr int s = decltype(sc)::value;
-        const int ka = k1 + C::kR2 * s, kb = C::kNz - ka;
         PC P, Q;
         if constexpr (MODE >= 2) {
+          const SlotLd cur = nxt;
+          if constexpr (s < 15) nxt = load_slot(std::integral_constant<int, s + 1>{});
           split2<(s >= 8)>(v[s], v[31 - s], sp[s * 32], P, Q);
-          P = update(P, ka, true, rk, false);
-          Q = update(Q, kb, true, rm, true);
+          P = update(P, cur.saA, cur.saB, cur.taA, cur.taB, TaA + C::kR2 * s, TaB + C::kR2 * s, true, rk, false);
+          Q = update(Q, cur.sbA, cur.sbB, cur.tbA, cur.tbB, TbA - C::kR2 * s, TbB - C::kR2 * s, true, rm, true);
         } else {
+          const int ka = k1 + C::kR2 * s, kb = C::kNz - ka;
           P = fetch(ka, rk, false);
           Q = fetch(kb, rm, true);
         }
@@ -276,28 +341,31 @@ __global__ void __launch_bounds__(kGl2Warps * 32, 1) gl2_kernel(const PlanDev p,
           const int t = tA + h;
           float* dst = stage + (2 * pp + h) * C::kWin + 2 * lane;
           const bool live = t < row.n_frames;
-          const float* wt = sm.wnorm + 2 * lane;   // interior frames
-          bool slow = false;
+          const float* wt = sm.wnorm;   // interior frames
           if (live) {
             const bool head = t < p.nov, tail = t > row.n_frames - 1 - p.nov;
-            if (head && tail) slow = true;
-            else if (head) wt = p.wedge + static_cast<long long>(t) * C::kWin + 2 * lane;
-            else if (tail) wt = p.wedge + static_cast<long long>(p.nov + row.n_frames - 1 - t) * C::kWin + 2 * lane;
+            if (head && tail) {
+              // utterance shorter than 2 nov + 1 frames (rare): weights computed by a rolled loop into the free upper part of the buffer
+              float* wtmp = stage + C::kFrames * C::kWin;
+              gl2_edge_weights(p, t, row.n_frames, wtmp, lane);
+              __syncwarp();
+              wt = wtmp;
+            } else if (head) {
+              wt = p.wedge + static_cast<long long>(t) * C::kWin;
+            } else if (tail) {
+              wt = p.wedge + static_cast<long long>(p.nov + row.n_frames - 1 - t) * C::kWin;
+            }
           }
+          wt += 2 * lane;
+          const float lv = live ? 1.f : 0.f;
           static_for<0, C::kR>([&](auto rc) {
             constexpr int r = decltype(rc)::value;
             const PC z = v[pp * C::kR2 + r];
             const float zr = h ? phi(z.re) : plo(z.re), zi = h ? phi(z.im) : plo(z.im);
-            float2 o = make_float2(0.f, 0.f);
-            if (live) {
-              float2 w;
-              if (slow) w = make_float2(synth_scale_edge(p, t, row.n_frames, 2 * lane + 64 * r),
-                                        synth_scale_edge(p, t, row.n_frames, 2 * lane + 64 * r + 1));
-              else w = *reinterpret_cast<const float2*>(wt + 64 * r);
-              o = make_float2(zr * w.x, zi * w.y);
-            }
-            *reinterpret_cast<float2*>(dst + 64 * r) = o;
+            const float2 w = *reinterpret_cast<const float2*>(wt + 64 * r);   // generic load: shared or global table
+            *reinterpret_cast<float2*>(dst + 64 * r) = make_float2(zr * w.x * lv, zi * w.y * lv);
           });
+          __syncwarp();   // wtmp may be rewritten by the next frame
         });
       });
     }
