@@ -22,7 +22,14 @@
 
 namespace sb200 {
 
-constexpr int kGl2Warps = 8;
+constexpr int kGl2Warps = 8;        // warps per CTA
+constexpr int kGl2GroupWarps = 4;   // warps per tile group: a CTA runs kGl2Warps / kGl2GroupWarps tiles concurrently, each
+                                    // group synchronising on its own named barrier so their phases interleave
+constexpr int kGl2Groups = kGl2Warps / kGl2GroupWarps;
+
+__device__ __forceinline__ void gl2_group_sync(int group) {
+  asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(kGl2GroupWarps * 32) : "memory");
+}
 
 struct Gl2Args {
   GlBatch g;
@@ -52,10 +59,10 @@ struct Gl2Smem {
   float* wnorm;    // [win] synthesis window / (N * interior window-sum-square)
   float2* tw;      // [kTwCount]
   float2* sp2;     // [17*32]
-  float* ytile;    // [span]
+  float* ytile;    // [groups][span]
   __host__ __device__ static size_t bytes(int span) {
     return static_cast<size_t>(kGl2Warps) * C::kXBytes + sizeof(float) * 2 * C::kWin + sizeof(float2) * (C::kTwCount + 17 * 32) +
-           sizeof(float) * span;
+           sizeof(float) * span * kGl2Groups;
   }
   __device__ __forceinline__ void init(unsigned char* raw, const PlanDev& p) {
     xbufs = reinterpret_cast<uint4*>(raw);
@@ -90,12 +97,15 @@ __device__ __noinline__ void gl2_edge_weights(const PlanDev& p, int t, int n_fra
 template <int N, int MODE>
 __global__ void __launch_bounds__(kGl2Warps * 32, 1) gl2_kernel(const PlanDev p, const Gl2Args a) {
   using C = Fft2Cfg<N>;
-  constexpr int FT = kGl2Warps * C::kFrames;   // frames per tile
+  constexpr int FT = kGl2GroupWarps * C::kFrames;   // frames per tile
+  constexpr int GT = kGl2GroupWarps * 32;           // threads per group
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Gl2Smem<N> sm;
   sm.init(smem_raw, p);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int group = warp / kGl2GroupWarps, wg = warp % kGl2GroupWarps, gt = threadIdx.x % GT;   // tile group, warp / thread in it
   const int hop = p.hop;
+  float* const ytile = sm.ytile + group * ((FT - 1) * hop + C::kWin);
   uint4* xbuf = sm.xbufs + warp * C::kXElems;
   float* stage = reinterpret_cast<float*>(xbuf);   // [kFrames][win] synthesised frames of this warp (aliases the exchange buffer)
   const int k1 = lane & (C::kR2 - 1), pl = lane / C::kR2;   // spectral role of this lane: column k1 of pair pl
@@ -104,11 +114,12 @@ __global__ void __launch_bounds__(kGl2Warps * 32, 1) gl2_kernel(const PlanDev p,
   const int rk = k1 & 3, rm = (4 - rk) & 3;                 // bin index mod 4 of the a side (k1 + R2 s) and b side (Nz - k)
   const float2* const sp = sm.sp2 + lane;
   const long long n_tiles = static_cast<long long>(a.g.bd.B) * a.tiles_per_row;
-  for (long long vt = blockIdx.x; vt < n_tiles; vt += gridDim.x) {
+  for (long long vt = static_cast<long long>(blockIdx.x) * kGl2Groups + group; vt < n_tiles;
+       vt += static_cast<long long>(gridDim.x) * kGl2Groups) {
     const int b = static_cast<int>(vt / a.tiles_per_row), tk = static_cast<int>(vt - static_cast<long long>(b) * a.tiles_per_row);
     const GlRow row = gl_row(a.g, b, N, hop);
     const int tile_t0 = tk * FT;
-    if (tile_t0 >= row.T) continue;   // uniform over the CTA
+    if (tile_t0 >= row.T) continue;   // uniform over the group
     const long long sbase = gl2_sig_base(row, b, hop, C::kWin);
     const long long cover = static_cast<long long>(row.T - 1) * hop + C::kWin;   // elements of this utterance in the signal buffers
     const long long u0 = static_cast<long long>(tile_t0) * hop;
@@ -123,36 +134,49 @@ __global__ void __launch_bounds__(kGl2Warps * 32, 1) gl2_kernel(const PlanDev p,
         // no reflection: offset coordinate u0 + j maps to itself; 16-byte loads (sbase, u0 and span are multiples of 4)
         const float4* ya4 = reinterpret_cast<const float4*>(ya + u0);
         const float4* yb4 = reinterpret_cast<const float4*>(yb + u0);
-        float4* yt4 = reinterpret_cast<float4*>(sm.ytile);
+        float4* yt4 = reinterpret_cast<float4*>(ytile);
 #pragma unroll 5
-        for (int j = threadIdx.x; j < span / 4; j += kGl2Warps * 32) {
+        for (int j = gt; j < span / 4; j += GT) {
           const float4 p4 = __ldg(ya4 + j), q4 = __ldg(yb4 + j);
           yt4[j] = make_float4(p4.x + q4.x, p4.y + q4.y, p4.z + q4.z, p4.w + q4.w);
         }
       } else {
         const int Ly = static_cast<int>(row.Ly), cov = static_cast<int>(cover), base = static_cast<int>(u0) - N / 4;
 #pragma unroll 4
-        for (int j = threadIdx.x; j < span; j += kGl2Warps * 32) {
+        for (int j = gt; j < span; j += GT) {
           int i = base + j;                            // signal index of offset coordinate u0 + j
           i = i < 0 ? -i : i;
           i = i >= Ly ? 2 * (Ly - 1) - i : i;
           const int uu = min(i + N / 4, cov - 1);
           const float val = __ldg(ya + uu) + __ldg(yb + uu);
-          sm.ytile[j] = (i + N / 4 < cov) ? val : 0.f;
+          ytile[j] = (i + N / 4 < cov) ? val : 0.f;
         }
       }
-      __syncthreads();
+      gl2_group_sync(group);
     }
     // ---- 2. per warp: analysis, phase update, synthesis ---------------------------------------------------------
     {
-      const int item_t0 = tile_t0 + warp * C::kFrames;
+      const int item_t0 = tile_t0 + wg * C::kFrames;
+      if constexpr (MODE >= 2) {
+        // the per-bin state of this item's frames is consecutive in memory: pull it into L2 while the analysis FFT runs
+        const long long r0 = (row.frame_base + min(item_t0, row.T - 1)) * C::kF;
+        const int nfr = max(0, min(C::kFrames, row.T - item_t0));
+        const char* sp0 = reinterpret_cast<const char*>(a.S + r0);
+        for (int o = lane * 128; o < nfr * C::kF * 4; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(sp0 + o));
+        if constexpr (MODE == 3) {
+          if (!a.first) {
+            const char* tp0 = reinterpret_cast<const char*>(a.tprev + r0);
+            for (int o = lane * 128; o < nfr * C::kF * 8; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(tp0 + o));
+          }
+        }
+      }
       PC v[32];
       if constexpr (MODE >= 2) {
         static_for<0, C::kP>([&](auto pc_) {
           constexpr int pp = decltype(pc_)::value;
           const int tA = item_t0 + 2 * pp;
           const bool okA = tA < row.T, okB = tA + 1 < row.T;
-          const float* yA = sm.ytile + (tA - tile_t0) * hop + 2 * lane;
+          const float* yA = ytile + (tA - tile_t0) * hop + 2 * lane;
           static_for<0, C::kR>([&](auto rc) {
             constexpr int r = decltype(rc)::value;
             const float2 w = *reinterpret_cast<const float2*>(sm.win + 2 * lane + 64 * r);
@@ -369,7 +393,7 @@ __global__ void __launch_bounds__(kGl2Warps * 32, 1) gl2_kernel(const PlanDev p,
         });
       });
     }
-    __syncthreads();
+    gl2_group_sync(group);
     // ---- 3. overlap-add of the tile's frames, written as this tile's span of the signal ----------------------------
     {
       const bool last_tile = tile_t0 + FT >= row.T;
@@ -378,22 +402,23 @@ __global__ void __launch_bounds__(kGl2Warps * 32, 1) gl2_kernel(const PlanDev p,
       const int span = static_cast<int>(min(static_cast<long long>(span_full), left));
       float* mine = ((tk & 1) ? a.yb_out : a.ya_out) + sbase + u0;
       float* other = ((tk & 1) ? a.ya_out : a.yb_out) + sbase + u0;
-      const float* frames0 = reinterpret_cast<const float*>(sm.xbufs);
+      const float* frames0 = reinterpret_cast<const float*>(sm.xbufs + group * kGl2GroupWarps * C::kXElems);
       constexpr int kWarpStride = C::kXBytes / 4;   // floats between the staging buffers of consecutive warps
-      for (int j = threadIdx.x; j < span; j += blockDim.x) {
-        int f = min(j / hop, FT - 1);
+      const int nov = p.nov;
+      for (int j = gt; j < span; j += GT) {
+        const int q = j / hop;   // newest frame covering sample j
         float acc = 0.f;
-        for (; f >= 0; --f) {
-          const int off = j - f * hop;
-          if (off >= C::kWin) break;
-          acc += frames0[(f / C::kFrames) * kWarpStride + (f % C::kFrames) * C::kWin + off];
+#pragma unroll 4
+        for (int d = 0; d <= nov; ++d) {
+          const int f = q - d, off = j - f * hop;
+          if (f >= 0 && f < FT && off < C::kWin) acc += frames0[(f / C::kFrames) * kWarpStride + (f % C::kFrames) * C::kWin + off];
         }
         mine[j] = acc;
         const bool interior = j >= C::kWin - hop && j < FT * hop;
         if (interior || (tk == 0 && j < C::kWin - hop) || (last_tile && j >= FT * hop)) other[j] = 0.f;
       }
     }
-    __syncthreads();
+    gl2_group_sync(group);
   }
 }
 
