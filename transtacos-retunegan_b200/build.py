@@ -24,7 +24,7 @@ def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
            "-Xcompiler", "-fPIC", "-shared", "--split-compile", "0", "-Xptxas", "-v" if verbose else "-O3",
-           "-o", OUT, SRC]
+           "-o", OUT, SRC] + os.environ.get("SB200_NVCC_FLAGS", "").split()
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

@@ -16,6 +16,13 @@ constexpr int kFeat2Warps = kFeat2WarpsOverride;
 #else
 constexpr int kFeat2Warps = 8;
 #endif
+// true: the next item's samples are requested before the mel phase of the current one and held in registers
+// (needs ~60 more registers: 8 warps per SM); false: fetched at the start of the item (fits 12 warps per SM)
+#ifdef kFeat2PrefetchOverride
+constexpr bool kFeat2Prefetch = kFeat2PrefetchOverride;
+#else
+constexpr bool kFeat2Prefetch = true;
+#endif
 
 template <int N>
 struct Smem2 {
@@ -38,13 +45,26 @@ struct Smem2 {
     melw = reinterpret_cast<float*>(sp2 + 17 * 32);
     mel_lo = reinterpret_cast<int*>(melw + p.melw_count);
   }
+  // 16-byte copies, several in flight per thread (all tables are multiples of 16 bytes and 16-byte aligned)
+  template <class T>
+  static __device__ __forceinline__ void copy16(T* dst, const T* src, int count, float scale = 1.f) {
+    const int n16 = count * static_cast<int>(sizeof(T)) / 16;
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n16; i += kFeat2Warps * 32) {
+      float4 t = __ldg(s4 + i);
+      if (scale != 1.f) t = make_float4(t.x * scale, t.y * scale, t.z * scale, t.w * scale);
+      d4[i] = t;
+    }
+  }
   __device__ __forceinline__ void fill(const PlanDev& p, bool with_mel) {
-    for (int i = threadIdx.x; i < C::kWin; i += blockDim.x) win[i] = 0.5f * p.window[i];
-    for (int i = threadIdx.x; i < C::kTwCount; i += blockDim.x) tw[i] = p.tw[i];
-    for (int i = threadIdx.x; i < 17 * 32; i += blockDim.x) sp2[i] = p.sp2[i];
+    copy16(win, p.window, C::kWin, 0.5f);
+    copy16(tw, p.tw, C::kTwCount);
+    copy16(sp2, p.sp2, 17 * 32);
     if (with_mel) {
-      for (int i = threadIdx.x; i < p.melw_count; i += blockDim.x) melw[i] = p.melw[i];
-      for (int i = threadIdx.x; i < 32 * p.mel_rounds; i += blockDim.x) mel_lo[i] = p.mel_lo[i];
+      copy16(melw, p.melw, p.melw_count);
+      copy16(mel_lo, p.mel_lo, 32 * p.mel_rounds);
     }
   }
 };
@@ -205,8 +225,9 @@ __global__ void __launch_bounds__(kFeat2Warps * 32, 1) stft_feature2_kernel(cons
   long long item = static_cast<long long>(blockIdx.x) * kFeat2Warps + warp;
   Fetch2<N, PRE, HS> nx;
   bool have = item < a.bd.total_items;
-  if (have) nx.issue(a.bd, item, a.x, p.hop, lane);
+  if (kFeat2Prefetch && have) nx.issue(a.bd, item, a.x, p.hop, lane);
   while (have) {
+    if (!kFeat2Prefetch) nx.issue(a.bd, item, a.x, p.hop, lane);
     const Item it = nx.it;
     PC v[32];
     load_item2<N, PRE, HS>(v, nx, a.x, p.hop, a.pre, sm.win, reinterpret_cast<float*>(xbuf), lane);
@@ -261,7 +282,7 @@ __global__ void __launch_bounds__(kFeat2Warps * 32, 1) stft_feature2_kernel(cons
     // next item's samples are requested now and land during the mel phase
     item += warps_total;
     have = item < a.bd.total_items;
-    if (have) nx.issue(a.bd, item, a.x, p.hop, lane);
+    if (kFeat2Prefetch && have) nx.issue(a.bd, item, a.x, p.hop, lane);
     __syncwarp();
     if (want_mel) {
 #pragma unroll
