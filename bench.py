@@ -303,21 +303,32 @@ def main():
                      "griffinlim_tt": "griffinlim_tt_1x5s_30it", "griffinlim_batch": "griffinlim_rtg_64x5s_4it",
                      "mstft": "mstft_fwd_bwd_16x22050_lossonly", "mstft_specs": "mstft_fwd_bwd_16x22050_specs"}[a.workload]
 
+    config = {"workload": workload_name, "per_gpu": workload_name, "sample_rate": SR, "n_fft": N_FFT, "hop": HOP, "win": WIN,
+              "n_mel": N_MEL, "sharding": "utterances per rank, no data-path collective"}
+
     if a.impl == "reference":
+        # The reference's own CPU implementation of the path (oracle port: librosa / TF are not installable) on
+        # all host cores, parallelised as the reference does (process pool over utterances).  A step is a bounded sample of
+        # the workload: 8 utterances per core (~0.3 s); at most 20 steps so the run ends within minutes.
         if rank != 0:
             return
-        n_utt = {"stft_mel": max(cores, 64), "griffinlim": max(cores, 16), "mstft": 64}[cpu_kind]
-        vals = []
-        for _ in range(max(1, min(a.steps, 3))):
+        n_utt = {"stft_mel": max(8 * cores, 64), "griffinlim": max(2 * cores, 16), "mstft": 64}[cpu_kind]
+        cpu_reference_rate(cpu_kind, max(cores, 16), L5, cores)          # warm-up step (imports, page-in)
+        vals, t_tot = [], 0.0
+        for _ in range(max(1, min(a.steps, 20))):
             v, dt = cpu_reference_rate(cpu_kind, n_utt, L5, cores)
             vals.append(v)
+            t_tot += dt
+            if t_tot > 120.0:
+                break
         v = float(np.median(vals))
-        sample = f"{n_utt} x 5 s utterances per step through the oracle restatement of the reference path, {cores} worker processes"
+        sample = (f"{n_utt} x 5 s utterances per step through the oracle restatement of the reference path, "
+                  f"{cores} worker processes, {len(vals)} steps, {t_tot:.1f} s")
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": len(vals),
             "warmup": 1, "ms_per_step": 1e3 * n_utt * L5 / SR / v, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64" if cpu_kind != "mstft" else "f32", "data": "synthetic",
-            "config": {"workload": workload_name, "sample_rate": SR, "n_fft": N_FFT, "hop": HOP, "win": WIN, "n_mel": N_MEL},
+            "config": config,
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}))
@@ -422,7 +433,8 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not a.kernel_only:
-        n_utt = {"stft_mel": max(cores, 64), "griffinlim": max(cores, 16), "mstft": 32}[cpu_kind]
+        # bounded sample: ~30 utterances per core (10-30 CPU-seconds of the reference path in all)
+        n_utt = {"stft_mel": max(32 * cores, 64), "griffinlim": max(4 * cores, 16), "mstft": 64}[cpu_kind]
         v, dt = cpu_reference_rate(cpu_kind, n_utt, L5, cores)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": f"{n_utt} x 5 s utterances, oracle restatement of the reference path, {cores} processes, {dt:.1f} s"}
@@ -432,8 +444,7 @@ def main():
             "metric": METRIC, "value": world * w.units * a.steps / dev_s, "unit": UNIT, "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * dev_s / a.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w.name, "per_gpu": w.name, "sample_rate": SR, "n_fft": N_FFT, "hop": HOP, "win": WIN,
-                       "n_mel": N_MEL, "l2": w.note, "sharding": "utterances per rank, no data-path collective"},
+            "config": dict(config, workload=w.name, per_gpu=w.name, l2=w.note),
             "clocks": sampler.summary(window),
             "e2e": e2e, "gpu_launches": int(timed_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
