@@ -53,6 +53,7 @@ SIGNATURES = {
     "sb200_mstft_workspace_bytes": (_I64, [C.POINTER(_P), _I32, _I32, _I64]),
     "sb200_mstft_forward": (C.c_int, [C.POINTER(_P), _I32, _P, _P, _I32, _I64, _I32, _P, C.POINTER(_P),
                                       C.POINTER(_P), _P, _P, _P]),
+    "sb200_mstft_loss_and_grad": (C.c_int, [C.POINTER(_P), _I32, _P, _P, _I32, _I64, _P, _P, _P, _P]),
     "sb200_mstft_backward": (C.c_int, [C.POINTER(_P), _I32, _P, _I32, _I64, _I32, _P, C.POINTER(_P), _P, _P, _P, _P]),
 }
 

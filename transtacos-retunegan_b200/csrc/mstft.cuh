@@ -164,9 +164,13 @@ struct MstftBwdArgs {
   const float* g_spec;     // [B, 2, Tf, F] upstream or null
   int phd_phase;
   float* gfb;              // [B*Tf, win] gradient frames
+  const float* y;          // FUSED: real audio (its mel rows are computed here instead of read from mel_r)
+  float* partials;         // FUSED: [gridDim.x * kMstftWarps] loss partial sums
 };
 
-template <int N>
+// FUSED = loss value and its gradient in ONE pass (loss-only training steps): analyses y, then does the backward work on
+// y_g with a unit upstream gradient while accumulating the loss -- no recomputation, no second launch per resolution.
+template <int N, bool FUSED>
 __global__ void __launch_bounds__(kMstftWarps * 32, 2) mstft_bwd_kernel(const PlanDev p, const MstftBwdArgs a) {
   using C = FftCfg<N>;
   constexpr int kPairs = C::kQ * C::kPairIters;   // 16
@@ -179,7 +183,8 @@ __global__ void __launch_bounds__(kMstftWarps * 32, 2) mstft_bwd_kernel(const Pl
   float2* buf = sm.bufs + warp * C::kBufF2;
   float* gmbuf = reinterpret_cast<float*>(buf);   // [Q][128] mel-row gradients, after the mel phase
   const int rk = lane & 3, rm = (4 - rk) & 3;
-  const float gl = a.g_loss ? __ldg(a.g_loss) * a.loss_scale : 0.f;
+  const float gl = FUSED ? a.loss_scale : (a.g_loss ? __ldg(a.g_loss) * a.loss_scale : 0.f);
+  float loss_acc = 0.f;
   const long long chs = static_cast<long long>(a.Tf) * C::kF;
   for (long long sub = static_cast<long long>(blockIdx.x) * kMstftWarps + warp; sub < 2 * a.bd.total_items;
        sub += static_cast<long long>(gridDim.x) * kMstftWarps) {
@@ -187,6 +192,12 @@ __global__ void __launch_bounds__(kMstftWarps * 32, 2) mstft_bwd_kernel(const Pl
     it.t0 += static_cast<int>(sub & 1) * C::kQ;
     if (it.t0 < it.T) {
     float2 v[32];
+    float mr[kMaxMelRounds][C::kQ];
+    if constexpr (FUSED) {
+      mstft_analyse<N>(p, sm, buf, v, a.y + it.sig_base, it.L, it.t0, it.T, lane, nullptr, nullptr, nullptr, 0, 0);
+      mel_project_smem<N>(p, sm.melw, sm.mel_lo, buf, lane, [&](int q, int rd, int, float val) { mr[rd][q] = val; });
+      __syncwarp();
+    }
     load_frames<N, false>(v, a.yg + it.sig_base, it.L, it.t0, it.T, p.hop, 0.f, sm.win, lane);
     fft_forward<N>(v, buf, sm.tw, lane);
     float2 Xk[kPairs], Xm[kPairs], Xs[C::kQ];
@@ -227,7 +238,13 @@ __global__ void __launch_bounds__(kMstftWarps * 32, 2) mstft_bwd_kernel(const Pl
     mel_project_smem<N>(p, sm.melw, sm.mel_lo, buf, lane, [&](int q, int rd, int m, float mg) {
       float g = 0.f;
       if (gl != 0.f && m < p.n_mel && it.t0 + q < it.T) {
-        const float r = __ldg(a.mel_r + (it.frame_base + it.t0 + q) * p.n_mel + m);
+        float r;
+        if constexpr (FUSED) {
+          r = mr[rd][q];
+          loss_acc += fabsf(r - mg) + fabsf(logf(r) - logf(mg));
+        } else {
+          r = __ldg(a.mel_r + (it.frame_base + it.t0 + q) * p.n_mel + m);
+        }
         const float sgn = (mg > r) ? 1.f : ((mg < r) ? -1.f : 0.f);
         g = gl * (sgn + sgn / mg);
       }
@@ -315,6 +332,11 @@ __global__ void __launch_bounds__(kMstftWarps * 32, 2) mstft_bwd_kernel(const Pl
     });
     __syncwarp();
     }
+  }
+  if constexpr (FUSED) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) loss_acc += __shfl_xor_sync(kFullMask, loss_acc, d);
+    if (lane == 0) a.partials[blockIdx.x * kMstftWarps + warp] = loss_acc;
   }
 }
 

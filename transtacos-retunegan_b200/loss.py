@@ -49,6 +49,17 @@ class _MultiStftFn(torch.autograd.Function):
         ws_bytes = lib.sb200_mstft_workspace_bytes(handles, n_res, B, T)
         if saved_bytes < 0 or ws_bytes < 0:
             _lib.check(-1)
+        ctx.fused = bool(want_loss and not want_specs and ctx.needs_input_grad[1])
+        if ctx.fused:
+            # loss-only training step: value and gradient (for a unit upstream gradient) in one pass; backward just scales it
+            ws = core._workspace(int(ws_bytes), dev, "mstft")
+            loss = torch.empty((), device=dev, dtype=torch.float32)
+            grad = torch.empty((B, T), device=dev, dtype=torch.float32)
+            _lib.check(lib.sb200_mstft_loss_and_grad(handles, n_res, core.ptr(yc), core.ptr(gc), B, T, core.ptr(loss),
+                                                     core.ptr(grad), core.ptr(ws), core.stream_ptr()), "mstft_loss_and_grad")
+            ctx.in_shape, ctx.in_dtype = y_g.shape, y_g.dtype
+            ctx.save_for_backward(grad)
+            return (loss,)
         saved = torch.empty(int(saved_bytes), device=dev, dtype=torch.uint8)
         ws = core._workspace(int(ws_bytes), dev, "mstft")
         loss = torch.empty((), device=dev, dtype=torch.float32) if want_loss else None
@@ -76,6 +87,10 @@ class _MultiStftFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, *grads):
+        if ctx.fused:
+            (grad,) = ctx.saved_tensors
+            g = grads[0].to(device=grad.device, dtype=torch.float32) * grad
+            return None, g.to(ctx.in_dtype).reshape(ctx.in_shape), None, None, None
         lib = _lib.load()
         gc, saved = ctx.saved_tensors
         B, T = ctx.shape
