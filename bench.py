@@ -262,6 +262,63 @@ def make_mstft(sb, torch, B=16, T=22050, specs=False, rot=4):
     return w
 
 
+def corpus_lengths(n=10000):
+    """frame counts T_i = clip(round(N(307, 100)), 101, 524) from RandomState(114514),
+    L_i = 256 T_i - 1 (min / mean / max of stats/DataBaker.stats:6-11)."""
+    rs = np.random.RandomState(114514)
+    T = np.clip(np.round(rs.normal(307, 100, n)), 101, 524).astype(np.int64)
+    return T, 256 * T - 1
+
+
+def make_corpus(sb, torch, rank, world, n_utt=10000, chunk=256):
+    """BASELINE.json configs[4]: corpus-scale preprocessing, 10k synthetic utterances sharded over the ranks (length-
+    balanced, no collective).  Per utterance, as retunegan/data.py:60-76 + transtacos get_specs: dB-normalised linear + mel
+    features (A3) and the Griffin-Lim reference wav (R4: ln-magnitude -> exp -> ^1.2 -> 4 iterations, momentum 0.7).
+    A step is one pass over this rank's shard, in ragged chunks of `chunk` utterances."""
+    import ctypes as C
+    w = Workload()
+    w.name = f"corpus_{n_utt}utt_specs+griffinlim"
+    ta, ra = sb.transtacos_audio, sb.retunegan_audio
+    plan = sb.core.get_plan(ta.hp)
+    T_all, L_all = corpus_lengths(n_utt)
+    mine = sorted(sb.sharding.shard_utterances(L_all, world)[rank])
+    T, L = T_all[mine], L_all[mine]
+    g = torch.Generator(device="cuda").manual_seed(114514 + rank)
+    lib = sb._lib.load()
+    sc_db, sc_ln = ta.db_norm_scale(ta.hp), ra.ln_scale(True)
+    chunks = []
+    for c0 in range(0, len(mine), chunk):
+        Lc, Tc = L[c0:c0 + chunk], T[c0:c0 + chunk]
+        ys = [(0.1 * torch.randn(int(l), device="cuda", generator=g)).clamp_(-0.999, 0.999) for l in Lc]
+        chunks.append((sb.core.SignalBatch(plan, ys), sb.core.FramesBatch(plan, Tc, Lc, torch.device("cuda")), None))
+    fmax = max(b.total_frames for b, _, _ in chunks)
+    mag = torch.empty((fmax, F), device="cuda")
+    mel = torch.empty((fmax, N_MEL), device="cuda")
+    lnm = torch.empty((fmax, F), device="cuda")
+    phase = torch.rand((fmax, F), device="cuda", generator=g)      # throughput mode: device RNG, drawn once
+
+    def step(i):
+        out = None
+        for batch, Tc, Lc in chunks:
+            n = batch.total_frames
+            sb._lib.check(lib.sb200_stft_features(plan.handle, sb.core.ptr(batch.x), C.byref(batch.c), float(ta.hp.preemphasis),
+                                                  sc_db, sc_db, sb.core.ptr(mag), sb.core.ptr(mel), None, sb.core.stream_ptr()))
+            sb._lib.check(lib.sb200_stft_features(plan.handle, sb.core.ptr(batch.x), C.byref(batch.c), 0.0,
+                                                  sc_ln, sb.core.RAW, sb.core.ptr(lnm), None, None, sb.core.stream_ptr()))
+            out, _ = ra.inv_mag_batch(lnm[:n], Tc, Lc, init_phase=phase[:n])
+        return out
+    w.step, w.e2e = step, None
+    w.units = float(L.sum()) / SR
+    nf = int(T.sum())
+    w.alg_bytes = 4.0 * L.sum() * 2 + 4.0 * nf * (F + N_MEL) + 4.0 * nf * F + nf * (4 * F * 5 + 16 * F * 4) + 8.0 * L.sum() * 5
+    w.dominant = "gl2_kernel<2048,3> (4 per chunk) + stft_feature2_kernel (2 per chunk)"
+    w.launches_dominant_per_step = 1
+    w.note = (f"{len(mine)} of {n_utt} utterances on this rank ({nf} frames, {w.units / 3600:.2f} h), ragged chunks of {chunk}; "
+              "features + ln-magnitude + Griffin-Lim (4 it, m 0.7, device-drawn initial phase); outputs stay in HBM")
+    w.check = lambda: torch.isfinite(step(0)).all().item()
+    return w
+
+
 # ----------------------------------------------------------------------------- timing ---------------
 
 def time_steps(torch, fn, steps, warmup, barrier):
@@ -289,7 +346,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="stft_mel", choices=["stft_mel", "griffinlim", "griffinlim_tt",
-                                                               "griffinlim_batch", "mstft", "mstft_specs"])
+                                                               "griffinlim_batch", "mstft", "mstft_specs", "corpus"])
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--kernel-only", action="store_true", help="profiling runs: skip e2e, extra workloads and the CPU baseline")
     a = ap.parse_args()
@@ -298,10 +355,11 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     cores = len(os.sched_getaffinity(0))
     cpu_kind = {"stft_mel": "stft_mel", "griffinlim": "griffinlim", "griffinlim_tt": "griffinlim",
-                "griffinlim_batch": "griffinlim", "mstft": "mstft", "mstft_specs": "mstft"}[a.workload]
+                "griffinlim_batch": "griffinlim", "mstft": "mstft", "mstft_specs": "mstft", "corpus": "griffinlim"}[a.workload]
     workload_name = {"stft_mel": "stft_mel_64x5s", "griffinlim": "griffinlim_rtg_1x5s_4it",
                      "griffinlim_tt": "griffinlim_tt_1x5s_30it", "griffinlim_batch": "griffinlim_rtg_64x5s_4it",
-                     "mstft": "mstft_fwd_bwd_16x22050_lossonly", "mstft_specs": "mstft_fwd_bwd_16x22050_specs"}[a.workload]
+                     "mstft": "mstft_fwd_bwd_16x22050_lossonly", "mstft_specs": "mstft_fwd_bwd_16x22050_specs",
+                     "corpus": "corpus_10000utt_specs+griffinlim"}[a.workload]
 
     config = {"workload": workload_name, "per_gpu": workload_name, "sample_rate": SR, "n_fft": N_FFT, "hop": HOP, "win": WIN,
               "n_mel": N_MEL, "sharding": "utterances per rank, no data-path collective"}
@@ -348,6 +406,12 @@ def main():
         if dist is not None:
             dist.all_reduce(sync_t)
 
+    def allsum(x):
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t)
+        return float(t.item())
+
     def allmax(x):
         t = torch.tensor([x], device="cuda", dtype=torch.float64)
         if dist is not None:
@@ -357,7 +421,8 @@ def main():
     makers = {"stft_mel": lambda: make_stft_mel(sb, torch), "griffinlim": lambda: make_griffinlim(sb, torch, 1, "rtg"),
               "griffinlim_tt": lambda: make_griffinlim(sb, torch, 1, "tt"),
               "griffinlim_batch": lambda: make_griffinlim(sb, torch, 64, "rtg"),
-              "mstft": lambda: make_mstft(sb, torch), "mstft_specs": lambda: make_mstft(sb, torch, specs=True)}
+              "mstft": lambda: make_mstft(sb, torch), "mstft_specs": lambda: make_mstft(sb, torch, specs=True),
+              "corpus": lambda: make_corpus(sb, torch, rank, world)}
     w = makers[a.workload]()
     assert w.check(), "workload produced non-finite output"
 
@@ -381,6 +446,7 @@ def main():
         window = "warmup+timed+1s continuation of the same loop"
     sampler.active = False
     dev_s = allmax(dev_s)
+    total_units = allsum(w.units)          # audio seconds per step over all ranks (corpus shards differ slightly)
     timed_launches = launches * a.steps // (a.steps + a.warmup)
 
     # dominant kernel duration, live: for single-kernel steps it is the step; otherwise re-time it alone is not possible
@@ -419,7 +485,8 @@ def main():
                            ("griffinlim_tt_1x5s_30it", makers["griffinlim_tt"], 10),
                            ("griffinlim_rtg_64x5s_4it", makers["griffinlim_batch"], 5),
                            ("mstft_fwd_bwd_16x22050_lossonly", makers["mstft"], 50),
-                           ("mstft_fwd_bwd_16x22050_specs", makers["mstft_specs"], 20)):
+                           ("mstft_fwd_bwd_16x22050_specs", makers["mstft_specs"], 20),
+                           ("corpus_10000utt_specs+griffinlim", makers["corpus"], 2)):
             try:
                 ww = mk()
                 d, _ = time_steps(torch, ww.step, k, 3, lambda: None)
@@ -441,9 +508,9 @@ def main():
 
     if rank == 0:
         out = {
-            "metric": METRIC, "value": world * w.units * a.steps / dev_s, "unit": UNIT, "n_gpus": world,
+            "metric": METRIC, "value": total_units * a.steps / dev_s, "unit": UNIT, "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * dev_s / a.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "strong" if a.workload == "corpus" else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(config, workload=w.name, per_gpu=w.name, l2=w.note),
             "clocks": sampler.summary(window),
             "e2e": e2e, "gpu_launches": int(timed_launches),

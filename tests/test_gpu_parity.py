@@ -254,6 +254,45 @@ def test_griffinlim_5s_vs_oracle(sb, form):
     _gl_check(out, ref, S.astype(np.float64) ** 1.2, None)
 
 
+def test_inv_mag_ragged_batch_equals_single_calls(sb):
+    """Ragged Griffin-Lim batch (corpus path): every utterance of the batch must equal its own single call bit for bit
+    (tiles never span utterances), including an utterance that ends inside a tile and the tile-parity hand-over."""
+    ra = sb.retunegan_audio
+    frames = [101, 16, 431, 57, 8, 9]
+    lens = [256 * t - 1 for t in frames]
+    ys = [O.synth_speechlike(L, 114514 + i) for i, L in enumerate(lens)]
+    plan = sb.core.get_plan(ra.hp)
+    batch = sb.core.SignalBatch(plan, ys)
+    mag_fm, _, _ = sb.core.stft_features(plan, batch, 0.0, ra.ln_scale(True), None, True, False)
+    wav, off = ra.inv_mag_batch(mag_fm, frames, lens, init_phase="seeded")
+    wav = wav.cpu().numpy()
+    assert off[-1] == sum(lens) == wav.size
+    o = 0
+    for i, (t, L) in enumerate(zip(frames, lens)):
+        single = ra.inv_mag(mag_fm[o:o + t].t(), wavlen=L).cpu().numpy()
+        np.testing.assert_array_equal(wav[off[i]:off[i + 1]], single)
+        o += t
+    # and the batch agrees with the oracle on one of them
+    ref = O.rtg_inv_mag(O.rtg_get_mag(ys[0]), wavlen=lens[0])
+    assert rel_fro(wav[off[0]:off[1]], ref) <= 1e-3
+
+
+@pytest.mark.parametrize("T", [5, 6, 7])
+def test_istft_short_utterances_edge_weights(sb, T):
+    """Utterances shorter than 2*nov+1 frames: every frame is both a head and a tail frame of the window-sum-square
+    normaliser (librosa.istft divides by the sum over the frames that exist)."""
+    rng = np.random.RandomState(T)
+    D = (rng.randn(1025, T) + 1j * rng.randn(1025, T)).astype(np.complex64)
+    D[0].imag = 0
+    D[-1].imag = 0
+    ref = O.istft(D, 256, 1024)
+    plan = sb.core.get_plan(sb.transtacos_audio.hp)
+    fb = sb.core.FramesBatch(plan, [T], None, torch.device("cuda"))
+    out = sb.core.istft(plan, torch.from_numpy(np.ascontiguousarray(D.T)).cuda(), fb).cpu().numpy()
+    assert out.shape == ref.shape == (256 * (T - 1),)
+    assert rel_fro(out, ref) < 1e-5
+
+
 # ------------------------------------------------------------------ get_stft_torch / mstft -----
 
 @pytest.mark.parametrize("ri", [0, 1, 2])

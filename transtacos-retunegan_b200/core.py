@@ -203,6 +203,7 @@ class FramesBatch:
     def __init__(self, plan: Plan, frames: Sequence[int], lengths: Optional[Sequence[int]], device):
         frames = np.asarray(frames, np.int64)
         hop, Q = plan.hop_length, plan.Q
+        self.frames = frames
         self.B = len(frames)
         out_len = np.asarray(lengths, np.int64) if lengths is not None else hop * (frames - 1)
         self.out_len = out_len

@@ -112,6 +112,42 @@ def inv_mag(mag, wavlen=None, init_phase=None):
     return y.cpu().numpy().astype(np.float32) if isinstance(mag, np.ndarray) else y
 
 
+def inv_mag_batch(mag_fm: torch.Tensor, frames, wavlens=None, init_phase="seeded"):
+    """Addition: ``inv_mag`` for a ragged batch in ONE Griffin-Lim call (the corpus path of retunegan/data.py:60-76).
+
+    mag_fm: float32 CUDA ``[sum(frames), n_freq]`` ln-magnitudes, frame-major, utterances back to back (what
+    ``core.stft_features`` writes for a list input).  frames: per-utterance frame counts; wavlens: per-utterance output
+    lengths (``1 + wavlen // hop == frames``) or None for ``hop * (T - 1)``; ``frames`` may also be a prebuilt
+    ``core.FramesBatch`` (then ``wavlens`` is ignored).  init_phase: "seeded" = the reference's
+    ``RandomState(randseed).rand(F, T)`` per utterance (host MT19937 draw, cached per length), "device" = on-device
+    RNG (throughput mode), or a float32 CUDA ``[sum(frames), n_freq]`` tensor of draws in [0, 1).
+    Returns (flat float32 CUDA wav, offsets int64 numpy [B + 1]).
+    """
+    plan = core.get_plan(hp)
+    fb = None
+    if isinstance(frames, core.FramesBatch):       # prebuilt descriptor (device offset tables already uploaded)
+        fb, frames = frames, frames.frames
+    frames = [int(t) for t in frames]
+    if mag_fm.shape != (sum(frames), plan.F):
+        raise ValueError(f"expected mag_fm of shape {(sum(frames), plan.F)}, got {tuple(mag_fm.shape)}")
+    S = core.spec_to_amplitude(mag_fm.contiguous(), 1, power=hp.gl_power if hp.gl_power else 1.0)
+    if isinstance(init_phase, str):
+        if init_phase == "device":
+            ph = torch.rand(S.shape, device=S.device, dtype=torch.float32)
+        elif init_phase == "seeded":
+            ph = torch.cat([_seeded_phase(plan.F, t) for t in frames])
+        else:
+            raise ValueError("init_phase must be 'seeded', 'device' or a tensor")
+    else:
+        ph = init_phase.to(device=S.device, dtype=torch.float32).contiguous()
+        if ph.shape != S.shape:
+            raise ValueError(f"init_phase must have shape {tuple(S.shape)}")
+    if fb is None:
+        fb = core.FramesBatch(plan, frames, wavlens, S.device)
+    y = core.griffinlim(plan, S, ph, fb, hp.gl_iters, hp.gl_momentum, 1, 0.0)
+    return y, fb.out_off
+
+
 def get_stft_torch(y, n_fft, win_length, hop_length):
     """S = |D + 1e-9|, M = mel_basis @ S, P = angle(D) for y [B, T] (retunegan/audio.py:150-170).
 
