@@ -26,6 +26,11 @@ constexpr int kGl2Warps = 8;        // warps per CTA
 constexpr int kGl2GroupWarps = 4;   // warps per tile group: a CTA runs kGl2Warps / kGl2GroupWarps tiles concurrently, each
                                     // group synchronising on its own named barrier so their phases interleave
 constexpr int kGl2Groups = kGl2Warps / kGl2GroupWarps;
+#ifdef kGl2TprevAheadOverride
+constexpr bool kGl2TprevAhead = kGl2TprevAheadOverride;
+#else
+constexpr bool kGl2TprevAhead = true;   // fast form: fetch the previous spectrum one slot ahead (more registers) or at its use
+#endif
 
 __device__ __forceinline__ void gl2_group_sync(int group) {
   asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(kGl2GroupWarps * 32) : "memory");
@@ -227,14 +232,9 @@ __global__ void __launch_bounds__(kGl2Warps * 32, 1) gl2_kernel(const PlanDev p,
       // register per (side, frame) plus a compile-time offset.
       const long long rowAc = (row.frame_base + min(fA, row.T - 1)) * C::kF, rowBc = (row.frame_base + min(fA + 1, row.T - 1)) * C::kF;
       const float mA = okA ? 1.f : 0.f, mB = okB ? 1.f : 0.f;
-      const float* const SaA = a.S + rowAc + k1;                // a side, bin k1 + R2 s: + R2 s
-      const float* const SaB = a.S + rowBc + k1;
-      const float* const SbA = a.S + rowAc + C::kNz - k1;       // b side, bin Nz - k1 - R2 s: - R2 s
-      const float* const SbB = a.S + rowBc + C::kNz - k1;
-      float2* const TaA = a.tprev + rowAc + k1;
-      float2* const TaB = a.tprev + rowBc + k1;
-      float2* const TbA = a.tprev + rowAc + C::kNz - k1;
-      float2* const TbB = a.tprev + rowBc + C::kNz - k1;
+      // element offsets of (side, frame); S and tprev share them (the bases are kernel parameters: no registers)
+      const long long oaA = rowAc + k1, oaB = rowBc + k1;                       // a side, bin k1 + R2 s: + R2 s
+      const long long obA = rowAc + C::kNz - k1, obB = rowBc + C::kNz - k1;     // b side, bin Nz - k1 - R2 s: - R2 s
       struct SlotLd {
         float saA, saB, sbA, sbB;
         float2 taA, taB, tbA, tbB;
@@ -242,16 +242,16 @@ __global__ void __launch_bounds__(kGl2Warps * 32, 1) gl2_kernel(const PlanDev p,
       auto load_slot = [&](auto sc) -> SlotLd {
         constexpr int off = C::kR2 * decltype(sc)::value;
         SlotLd L;
-        L.saA = __ldg(SaA + off) * mA;
-        L.saB = __ldg(SaB + off) * mB;
-        L.sbA = __ldg(SbA - off) * mA;
-        L.sbB = __ldg(SbB - off) * mB;
-        if constexpr (MODE == 3) {
+        L.saA = __ldg(a.S + oaA + off) * mA;
+        L.saB = __ldg(a.S + oaB + off) * mB;
+        L.sbA = __ldg(a.S + obA - off) * mA;
+        L.sbB = __ldg(a.S + obB - off) * mB;
+        if constexpr (MODE == 3 && kGl2TprevAhead) {
           if (!a.first) {
-            L.taA = TaA[off];
-            L.taB = TaB[off];
-            L.tbA = TbA[-off];
-            L.tbB = TbB[-off];
+            L.taA = a.tprev[oaA + off];
+            L.taB = a.tprev[oaB + off];
+            L.tbA = a.tprev[obA - off];
+            L.tbB = a.tprev[obB - off];
           }
         }
         return L;
@@ -329,11 +329,19 @@ __global__ void __launch_bounds__(kGl2Warps * 32, 1) gl2_kernel(const PlanDev p,
         constexpr int s = decltype(sc)::value;
         PC P, Q;
         if constexpr (MODE >= 2) {
-          const SlotLd cur = nxt;
+          SlotLd cur = nxt;
+          if constexpr (MODE == 3 && !kGl2TprevAhead) {   // previous spectrum fetched at its use (it was pulled into L2 at item start)
+            if (!a.first) {
+              cur.taA = a.tprev[oaA + C::kR2 * s];
+              cur.taB = a.tprev[oaB + C::kR2 * s];
+              cur.tbA = a.tprev[obA - C::kR2 * s];
+              cur.tbB = a.tprev[obB - C::kR2 * s];
+            }
+          }
           if constexpr (s < 15) nxt = load_slot(std::integral_constant<int, s + 1>{});
           split2<(s >= 8)>(v[s], v[31 - s], sp[s * 32], P, Q);
-          P = update(P, cur.saA, cur.saB, cur.taA, cur.taB, TaA + C::kR2 * s, TaB + C::kR2 * s, true, rk, false);
-          Q = update(Q, cur.sbA, cur.sbB, cur.tbA, cur.tbB, TbA - C::kR2 * s, TbB - C::kR2 * s, true, rm, true);
+          P = update(P, cur.saA, cur.saB, cur.taA, cur.taB, a.tprev + oaA + C::kR2 * s, a.tprev + oaB + C::kR2 * s, true, rk, false);
+          Q = update(Q, cur.sbA, cur.sbB, cur.tbA, cur.tbB, a.tprev + obA - C::kR2 * s, a.tprev + obB - C::kR2 * s, true, rm, true);
         } else {
           const int ka = k1 + C::kR2 * s, kb = C::kNz - ka;
           P = fetch(ka, rk, false);
@@ -380,14 +388,26 @@ __global__ void __launch_bounds__(kGl2Warps * 32, 1) gl2_kernel(const PlanDev p,
               wt = p.wedge + static_cast<long long>(p.nov + row.n_frames - 1 - t) * C::kWin;
             }
           }
+          const bool edge = wt != sm.wnorm;
           wt += 2 * lane;
           const float lv = live ? 1.f : 0.f;
+          float2 w[C::kR];
+          if (!edge) {   // interior frame: shared-memory table
+            static_for<0, C::kR>([&](auto rc) {
+              constexpr int r = decltype(rc)::value;
+              w[r] = *reinterpret_cast<const float2*>(sm.wnorm + 2 * lane + 64 * r);
+            });
+          } else {       // head / tail frame: plan table in global memory, or the buffer filled above (generic loads)
+            static_for<0, C::kR>([&](auto rc) {
+              constexpr int r = decltype(rc)::value;
+              w[r] = *reinterpret_cast<const float2*>(wt + 64 * r);
+            });
+          }
           static_for<0, C::kR>([&](auto rc) {
             constexpr int r = decltype(rc)::value;
             const PC z = v[pp * C::kR2 + r];
             const float zr = h ? phi(z.re) : plo(z.re), zi = h ? phi(z.im) : plo(z.im);
-            const float2 w = *reinterpret_cast<const float2*>(wt + 64 * r);   // generic load: shared or global table
-            *reinterpret_cast<float2*>(dst + 64 * r) = make_float2(zr * w.x * lv, zi * w.y * lv);
+            *reinterpret_cast<float2*>(dst + 64 * r) = make_float2(zr * w[r].x * lv, zi * w[r].y * lv);
           });
           __syncwarp();   // wtmp may be rewritten by the next frame
         });
@@ -405,17 +425,19 @@ __global__ void __launch_bounds__(kGl2Warps * 32, 1) gl2_kernel(const PlanDev p,
       const float* frames0 = reinterpret_cast<const float*>(sm.xbufs + group * kGl2GroupWarps * C::kXElems);
       constexpr int kWarpStride = C::kXBytes / 4;   // floats between the staging buffers of consecutive warps
       const int nov = p.nov;
-      for (int j = gt; j < span; j += GT) {
-        const int q = j / hop;   // newest frame covering sample j
-        float acc = 0.f;
+      // thread owns offsets o within a hop; sample j = q * hop + o is covered by frames q - d at offset o + d * hop, d <= nov
+      for (int o = gt; o < hop; o += GT) {
+        for (int q = 0, j = o; j < span; ++q, j += hop) {
+          float acc = 0.f;
 #pragma unroll 4
-        for (int d = 0; d <= nov; ++d) {
-          const int f = q - d, off = j - f * hop;
-          if (f >= 0 && f < FT && off < C::kWin) acc += frames0[(f / C::kFrames) * kWarpStride + (f % C::kFrames) * C::kWin + off];
+          for (int d = 0; d <= nov; ++d) {
+            const int f = q - d, off = o + d * hop;
+            if (f >= 0 && f < FT && off < C::kWin) acc += frames0[(f / C::kFrames) * kWarpStride + (f % C::kFrames) * C::kWin + off];
+          }
+          mine[j] = acc;
+          const bool interior = j >= C::kWin - hop && j < FT * hop;
+          if (interior || (tk == 0 && j < C::kWin - hop) || (last_tile && j >= FT * hop)) other[j] = 0.f;
         }
-        mine[j] = acc;
-        const bool interior = j >= C::kWin - hop && j < FT * hop;
-        if (interior || (tk == 0 && j < C::kWin - hop) || (last_tile && j >= FT * hop)) other[j] = 0.f;
       }
     }
     gl2_group_sync(group);
