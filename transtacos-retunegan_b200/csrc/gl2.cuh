@@ -63,10 +63,10 @@ struct Gl2Smem {
   float* win;      // [win] 0.5 * analysis window
   float* wnorm;    // [win] synthesis window / (N * interior window-sum-square)
   float2* tw;      // [kTwCount]
-  float2* sp2;     // [17*32]
+  float2* spn;     // [Nz/2 + 1] split twiddles in natural bin order (padded to a multiple of 2)
   float* ytile;    // [groups][span]
   __host__ __device__ static size_t bytes(int span) {
-    return static_cast<size_t>(kGl2Warps) * C::kXBytes + sizeof(float) * 2 * C::kWin + sizeof(float2) * (C::kTwCount + 17 * 32) +
+    return static_cast<size_t>(kGl2Warps) * C::kXBytes + sizeof(float) * 2 * C::kWin + sizeof(float2) * (C::kTwCount + C::kNz / 2 + 2) +
            sizeof(float) * span * kGl2Groups;
   }
   __device__ __forceinline__ void init(unsigned char* raw, const PlanDev& p) {
@@ -74,14 +74,14 @@ struct Gl2Smem {
     win = reinterpret_cast<float*>(raw + static_cast<size_t>(kGl2Warps) * C::kXBytes);
     wnorm = win + C::kWin;
     tw = reinterpret_cast<float2*>(wnorm + C::kWin);
-    sp2 = tw + C::kTwCount;
-    ytile = reinterpret_cast<float*>(sp2 + 17 * 32);
+    spn = tw + C::kTwCount;
+    ytile = reinterpret_cast<float*>(spn + C::kNz / 2 + 2);
     for (int i = threadIdx.x; i < C::kWin; i += blockDim.x) {
       win[i] = 0.5f * p.window[i];
       wnorm[i] = p.wnorm[i];
     }
     for (int i = threadIdx.x; i < C::kTwCount; i += blockDim.x) tw[i] = p.tw[i];
-    for (int i = threadIdx.x; i < 17 * 32; i += blockDim.x) sp2[i] = p.sp2[i];
+    for (int i = threadIdx.x; i < C::kNz / 2 + 1; i += blockDim.x) spn[i] = p.spn[i];
     __syncthreads();
   }
 };
@@ -97,6 +97,69 @@ __device__ __forceinline__ float2 rot_i(float2 a, int j) {
 __device__ __noinline__ void gl2_edge_weights(const PlanDev& p, int t, int n_frames, float* out, int lane) {
 #pragma unroll 1
   for (int m = lane; m < p.win; m += 32) out[m] = synth_scale_edge(p, t, n_frames, m);
+}
+
+// Phase update of one held spectral value X of both frames of a pair (modes 2 / 3): magnitudes sA / sB, previous
+// spectrum tA / tB.  rot = bin index mod 4, conj_held = b side (value held conjugated): only used for the exact-zero case.
+template <int MODE>
+__device__ __forceinline__ PC gl2_update(const PC& X, float sA, float sB, float2 tA, float2 tB, float alpha, int first, int rot,
+                                         bool conj_held) {
+  PC o;
+  if constexpr (MODE == 2) {   // transtacos/audio.py:137-138: angles = exp(1j * angle(X))
+    const pf n2 = norm2(X);
+    const float nA = plo(n2), nB = phi(n2);
+    const float iA = nA > 0.f ? rsqrtf(nA) : 0.f, iB = nB > 0.f ? rsqrtf(nB) : 0.f;
+    const pf sc = pk(sA * iA, sB * iB);
+    o.re = mul2(X.re, sc);
+    o.im = mul2(X.im, sc);
+    if (nA == 0.f || nB == 0.f) {   // exp(1j * angle(0)) = 1, in the engine's internal form: i^k (conjugated on the b side)
+      float2 un = rot_i(make_float2(1.f, 0.f), rot);
+      if (conj_held) un.y = -un.y;
+      o.re = pk(nA > 0.f ? plo(o.re) : sA * un.x, nB > 0.f ? phi(o.re) : sB * un.x);
+      o.im = pk(nA > 0.f ? plo(o.im) : sA * un.y, nB > 0.f ? phi(o.im) : sB * un.y);
+    }
+  } else {                     // librosa.griffinlim: c = rebuilt - alpha * tprev; angles = c / (|c| + 1e-16)
+    PC c = X;
+    if (!first) {
+      c.re = fma2s(pk(tA.x, tB.x), -alpha, X.re);
+      c.im = fma2s(pk(tA.y, tB.y), -alpha, X.im);
+    }
+    const pf n2 = norm2(c);
+    const pf sc = pk(sA / (sqrtf(plo(n2)) + 1e-16f), sB / (sqrtf(phi(n2)) + 1e-16f));
+    o.re = mul2(c.re, sc);
+    o.im = mul2(c.im, sc);
+  }
+  return o;
+}
+
+// Input spectrum of bin kb of both frames in the engine's internal form (modes 0 / 1): i^kb X, conjugated on the b side.
+template <int MODE>
+__device__ __forceinline__ PC gl2_fetch(const Gl2Args& a, long long rowA, long long rowB, bool okA, bool okB, int kb, int rot,
+                                        bool conj_it) {
+  float2 xa = make_float2(0.f, 0.f), xb = make_float2(0.f, 0.f);
+  if constexpr (MODE == 0) {
+    if (okA) xa = __ldg(a.spec + rowA + kb);
+    if (okB) xb = __ldg(a.spec + rowB + kb);
+  } else {
+    if (okA) {
+      float s, c;
+      sincospif(2.f * __ldg(a.init_phase + rowA + kb), &s, &c);
+      const float mg = __ldg(a.S + rowA + kb);
+      xa = make_float2(mg * c, mg * s);
+    }
+    if (okB) {
+      float s, c;
+      sincospif(2.f * __ldg(a.init_phase + rowB + kb), &s, &c);
+      const float mg = __ldg(a.S + rowB + kb);
+      xb = make_float2(mg * c, mg * s);
+    }
+  }
+  xa = rot_i(xa, rot);
+  xb = rot_i(xb, rot);
+  PC r;
+  r.re = pk(xa.x, xb.x);
+  r.im = conj_it ? pk(-xa.y, -xb.y) : pk(xa.y, xb.y);
+  return r;
 }
 
 template <int N, int MODE>
@@ -117,7 +180,6 @@ __global__ void __launch_bounds__(kGl2Warps * 32, 1) gl2_kernel(const PlanDev p,
   const bool col0 = (k1 == 0);
   const int partner = (lane & ~(C::kR2 - 1)) | ((C::kR2 - k1) & (C::kR2 - 1));
   const int rk = k1 & 3, rm = (4 - rk) & 3;                 // bin index mod 4 of the a side (k1 + R2 s) and b side (Nz - k)
-  const float2* const sp = sm.sp2 + lane;
   const long long n_tiles = static_cast<long long>(a.g.bd.B) * a.tiles_per_row;
   for (long long vt = static_cast<long long>(blockIdx.x) * kGl2Groups + group; vt < n_tiles;
        vt += static_cast<long long>(gridDim.x) * kGl2Groups) {
@@ -196,173 +258,155 @@ __global__ void __launch_bounds__(kGl2Warps * 32, 1) gl2_kernel(const PlanDev p,
         });
         fft2_forward<N>(v, xbuf, sm.tw, lane);
       }
-      // lane (pl, k1) handles frames fA = item_t0 + 2 pl (low halves) and fB = fA + 1 (high halves)
-      const int fA = item_t0 + 2 * pl;
-      const bool okA = fA < row.T, okB = fA + 1 < row.T;
-      const long long rowA = (row.frame_base + fA) * C::kF;   // frame B: + F
-      // spectral value of bin kb of both frames in the engine's internal form (modes 0 / 1): i^kb X, conjugated on the b side
-      auto fetch = [&](int kb, int rot, bool conj_it) -> PC {
-        float2 xa = make_float2(0.f, 0.f), xb = make_float2(0.f, 0.f);
-        if constexpr (MODE == 0) {
-          if (okA) xa = __ldg(a.spec + rowA + kb);
-          if (okB) xb = __ldg(a.spec + rowA + C::kF + kb);
-        } else {
-          if (okA) {
-            float s, c;
-            sincospif(2.f * __ldg(a.init_phase + rowA + kb), &s, &c);
-            const float mg = __ldg(a.S + rowA + kb);
-            xa = make_float2(mg * c, mg * s);
-          }
-          if (okB) {
-            float s, c;
-            sincospif(2.f * __ldg(a.init_phase + rowA + C::kF + kb), &s, &c);
-            const float mg = __ldg(a.S + rowA + C::kF + kb);
-            xb = make_float2(mg * c, mg * s);
-          }
-        }
-        xa = rot_i(xa, rot);
-        xb = rot_i(xb, rot);
-        PC r;
-        r.re = pk(xa.x, xb.x);
-        r.im = conj_it ? pk(-xa.y, -xb.y) : pk(xa.y, xb.y);
-        return r;
-      };
-      // ---- modes 2 / 3: per-bin state of the phase update, fetched one slot ahead of its use -------------------------
-      // Loads are unconditional (frames past the end are clamped to the last one and masked), addresses are one base
-      // register per (side, frame) plus a compile-time offset.
-      const long long rowAc = (row.frame_base + min(fA, row.T - 1)) * C::kF, rowBc = (row.frame_base + min(fA + 1, row.T - 1)) * C::kF;
-      const float mA = okA ? 1.f : 0.f, mB = okB ? 1.f : 0.f;
-      // element offsets of (side, frame); S and tprev share them (the bases are kernel parameters: no registers)
-      const long long oaA = rowAc + k1, oaB = rowBc + k1;                       // a side, bin k1 + R2 s: + R2 s
-      const long long obA = rowAc + C::kNz - k1, obB = rowBc + C::kNz - k1;     // b side, bin Nz - k1 - R2 s: - R2 s
-      struct SlotLd {
-        float saA, saB, sbA, sbB;
-        float2 taA, taB, tbA, tbB;
-      };
-      auto load_slot = [&](auto sc) -> SlotLd {
-        constexpr int off = C::kR2 * decltype(sc)::value;
-        SlotLd L;
-        L.saA = __ldg(a.S + oaA + off) * mA;
-        L.saB = __ldg(a.S + oaB + off) * mB;
-        L.sbA = __ldg(a.S + obA - off) * mA;
-        L.sbB = __ldg(a.S + obB - off) * mB;
-        if constexpr (MODE == 3 && kGl2TprevAhead) {
-          if (!a.first) {
-            L.taA = a.tprev[oaA + off];
-            L.taB = a.tprev[oaB + off];
-            L.tbA = a.tprev[obA - off];
-            L.tbB = a.tprev[obB - off];
-          }
-        }
-        return L;
-      };
-      // phase update of one held value X of both frames: magnitudes sA / sB, previous spectrum tA / tB, stored to dA / dB
-      auto update = [&](const PC& X, float sA, float sB, float2 tA, float2 tB, float2* dA, float2* dB, bool on, int rot,
-                        bool conj_held) -> PC {
-        PC o;
-        if constexpr (MODE == 2) {
-          const pf n2 = norm2(X);
-          const float nA = plo(n2), nB = phi(n2);
-          const float iA = nA > 0.f ? rsqrtf(nA) : 0.f, iB = nB > 0.f ? rsqrtf(nB) : 0.f;
-          const pf sc = pk(sA * iA, sB * iB);
-          o.re = mul2(X.re, sc);
-          o.im = mul2(X.im, sc);
-          if (nA == 0.f || nB == 0.f) {   // exp(1j * angle(0)) = 1 (transtacos/audio.py:138), in the internal form: i^kb (conjugated on the b side)
-            float2 un = rot_i(make_float2(1.f, 0.f), rot);
-            if (conj_held) un.y = -un.y;
-            o.re = pk(nA > 0.f ? plo(o.re) : sA * un.x, nB > 0.f ? phi(o.re) : sB * un.x);
-            o.im = pk(nA > 0.f ? plo(o.im) : sA * un.y, nB > 0.f ? phi(o.im) : sB * un.y);
-          }
-        } else {
-          PC c = X;
-          if (!a.first) {
-            c.re = fma2s(pk(tA.x, tB.x), -a.alpha, X.re);
-            c.im = fma2s(pk(tA.y, tB.y), -a.alpha, X.im);
-          }
-          if (on && okA) *dA = make_float2(plo(X.re), plo(X.im));
-          if (on && okB) *dB = make_float2(phi(X.re), phi(X.im));
-          const pf n2 = norm2(c);
-          const pf sc = pk(sA / (sqrtf(plo(n2)) + 1e-16f), sB / (sqrtf(phi(n2)) + 1e-16f));
-          o.re = mul2(c.re, sc);
-          o.im = mul2(c.im, sc);
-        }
-        return o;
-      };
-      PC zself;
+      // ---- spectrum pass.  The analysed spectrum Z goes to the warp's buffer in natural bin order (16 bytes per bin: both
+      // frames of a pair), the registers of the FFT are released, and the Hermitian pairs (k, Nz - k) are updated in place
+      // by a short loop: forward split -> phase update against S (and the previous spectrum) -> inverse split.  Lanes take
+      // consecutive bins, so S / tprev accesses are coalesced and several pairs are in flight per lane.
+      ulonglong2* const xz = reinterpret_cast<ulonglong2*>(xbuf);   // [P][Nz] (re pair, im pair)
       if constexpr (MODE >= 2) {
-        // self pair of column 0 (bin Nz/2) first: the exchange below overwrites v[16]
-        PC ak, am;
-        split2<true>(v[16], v[16], sp[16 * 32], ak, am);
-        {
-          const float sA = __ldg(a.S + rowAc + C::kNz / 2) * mA, sB = __ldg(a.S + rowBc + C::kNz / 2) * mB;
-          float2 tA = make_float2(0.f, 0.f), tB = tA;
-          if constexpr (MODE == 3) {
-            if (!a.first) {
-              tA = a.tprev[rowAc + C::kNz / 2];
-              tB = a.tprev[rowBc + C::kNz / 2];
-            }
-          }
-          ak = update(ak, sA, sB, tA, tB, a.tprev + rowAc + C::kNz / 2, a.tprev + rowBc + C::kNz / 2, col0, 0, false);
-        }
-        PC q;
-        q.re = ak.re;
-        q.im = sub2(0ull, ak.im);
-        PC zr;
-        split2_inv<true>(ak, q, sp[16 * 32], zself, zr);
-        // partner exchange: slot s receives Z[Nz - k] into v[31 - s]
-        static_for<0, 16>([&](auto sc) {
-          constexpr int s = 15 - decltype(sc)::value;
-          const PC send = pc_sel(col0, v[(32 - s) & 31], v[31 - s]);
-          v[31 - s] = pc_shfl(send, partner);
+        const unsigned wz = smem_u32(xz + pl * C::kNz + k1);
+        static_for<0, 32>([&](auto kc) {
+          constexpr int k2 = decltype(kc)::value;
+          sts_pc<16 * C::kR2 * k2>(wz, v[k2].re, v[k2].im);
         });
-      } else {
-        const PC pS = fetch(C::kNz / 2, 0, false);
-        PC q;
-        q.re = pS.re;
-        q.im = sub2(0ull, pS.im);
-        PC zr;
-        split2_inv<true>(pS, q, sp[16 * 32], zself, zr);
+        __syncwarp();
       }
-      SlotLd nxt{};
-      if constexpr (MODE >= 2) nxt = load_slot(std::integral_constant<int, 0>{});
-      static_for<0, 16>([&](auto sc) {
-        constexpr int s = decltype(sc)::value;
-        PC P, Q;
-        if constexpr (MODE >= 2) {
-          SlotLd cur = nxt;
-          if constexpr (MODE == 3 && !kGl2TprevAhead) {   // previous spectrum fetched at its use (it was pulled into L2 at item start)
-            if (!a.first) {
-              cur.taA = a.tprev[oaA + C::kR2 * s];
-              cur.taB = a.tprev[oaB + C::kR2 * s];
-              cur.tbA = a.tprev[obA - C::kR2 * s];
-              cur.tbB = a.tprev[obB - C::kR2 * s];
+      static_for<0, C::kP>([&](auto pc_) {
+        constexpr int pp = decltype(pc_)::value;
+        const int fA = item_t0 + 2 * pp;
+        const bool okA = fA < row.T, okB = fA + 1 < row.T;
+        // frames past the end are clamped to the last one (loads stay in bounds) and masked
+        const long long rowA = (row.frame_base + min(fA, row.T - 1)) * C::kF, rowB = (row.frame_base + min(fA + 1, row.T - 1)) * C::kF;
+        const float mA = okA ? 1.f : 0.f, mB = okB ? 1.f : 0.f;
+        ulonglong2* const zp = xz + pp * C::kNz;
+        // everything one Hermitian pair (k, Nz - k) reads, fetched one trip ahead of its use
+        struct PairLd {
+          ulonglong2 zk, zr;
+          float sAa, sBa, sAb, sBb;
+          float2 tAa, tBa, tAb, tBb;
+        };
+        auto ld_pair = [&](int k) -> PairLd {
+          PairLd L;
+          if constexpr (MODE >= 2) {
+            const int km = (C::kNz - k) & (C::kNz - 1), kb = C::kNz - k;
+            L.zk = zp[k];
+            L.zr = zp[km];
+            L.sAa = __ldg(a.S + rowA + k) * mA;
+            L.sBa = __ldg(a.S + rowB + k) * mB;
+            L.sAb = __ldg(a.S + rowA + kb) * mA;
+            L.sBb = __ldg(a.S + rowB + kb) * mB;
+            L.tAa = L.tBa = L.tAb = L.tBb = make_float2(0.f, 0.f);
+            if constexpr (MODE == 3) {
+              if (!a.first) {
+                L.tAa = a.tprev[rowA + k];
+                L.tBa = a.tprev[rowB + k];
+                L.tAb = a.tprev[rowA + kb];
+                L.tBb = a.tprev[rowB + kb];
+              }
             }
           }
-          if constexpr (s < 15) nxt = load_slot(std::integral_constant<int, s + 1>{});
-          split2<(s >= 8)>(v[s], v[31 - s], sp[s * 32], P, Q);
-          P = update(P, cur.saA, cur.saB, cur.taA, cur.taB, a.tprev + oaA + C::kR2 * s, a.tprev + oaB + C::kR2 * s, true, rk, false);
-          Q = update(Q, cur.sbA, cur.sbB, cur.tbA, cur.tbB, a.tprev + obA - C::kR2 * s, a.tprev + obB - C::kR2 * s, true, rm, true);
-        } else {
-          const int ka = k1 + C::kR2 * s, kb = C::kNz - ka;
-          P = fetch(ka, rk, false);
-          Q = fetch(kb, rm, true);
-        }
-        if constexpr (s == 0) {
-          if (col0) {   // irfft ignores the imaginary parts of DC and Nyquist
+          return L;
+        };
+        // one Hermitian pair: bins k (a side) and Nz - k (b side, held conjugated)
+        auto do_pair = [&](int k, const PairLd& L, auto sinform_c) {
+          constexpr bool SINFORM = decltype(sinform_c)::value;
+          const int km = (C::kNz - k) & (C::kNz - 1), kb = C::kNz - k;
+          const float2 tws = sm.spn[k];
+          PC P, Q;
+          if constexpr (MODE >= 2) {
+            PC Zk, Zr;
+            Zk.re = L.zk.x; Zk.im = L.zk.y;
+            Zr.re = L.zr.x; Zr.im = L.zr.y;
+            split2<SINFORM>(Zk, Zr, tws, P, Q);
+            if constexpr (MODE == 3) {   // the rebuilt spectrum becomes the next iteration's tprev
+              if (okA) {
+                a.tprev[rowA + k] = make_float2(plo(P.re), plo(P.im));
+                a.tprev[rowA + kb] = make_float2(plo(Q.re), plo(Q.im));
+              }
+              if (okB) {
+                a.tprev[rowB + k] = make_float2(phi(P.re), phi(P.im));
+                a.tprev[rowB + kb] = make_float2(phi(Q.re), phi(Q.im));
+              }
+            }
+            P = gl2_update<MODE>(P, L.sAa, L.sBa, L.tAa, L.tBa, a.alpha, a.first, k & 3, false);
+            Q = gl2_update<MODE>(Q, L.sAb, L.sBb, L.tAb, L.tBb, a.alpha, a.first, (4 - (k & 3)) & 3, true);
+          } else {
+            P = gl2_fetch<MODE>(a, rowA, rowB, okA, okB, k, k & 3, false);
+            Q = gl2_fetch<MODE>(a, rowA, rowB, okA, okB, kb, (4 - (k & 3)) & 3, true);
+          }
+          if (k == 0) {   // irfft ignores the imaginary parts of DC and Nyquist
             P.im = 0ull;
             Q.im = 0ull;
           }
+          PC Zk2, Zr2;
+          split2_inv<SINFORM>(P, Q, tws, Zk2, Zr2);
+          zp[k] = make_ulonglong2(Zk2.re, Zk2.im);
+          if (k != 0) zp[km] = make_ulonglong2(Zr2.re, Zr2.im);
+        };
+        // bins [0, Nz/4) use the tan / cos form of the split twiddle, [Nz/4, Nz/2) the cot / sin form: one of each per trip;
+        // the loads of the next trip are issued before the current one is computed
+        {
+          constexpr int kTrips = C::kNz / 128;
+          PairLd c0 = ld_pair(lane), c1 = ld_pair(lane + C::kNz / 4);
+#pragma unroll 1
+          for (int ii = 0; ii < kTrips; ++ii) {
+            const int k = lane + 32 * ii;
+            PairLd n0 = c0, n1 = c1;
+            if (ii + 1 < kTrips) {
+              n0 = ld_pair(k + 32);
+              n1 = ld_pair(k + 32 + C::kNz / 4);
+            }
+            do_pair(k, c0, std::false_type{});
+            do_pair(k + C::kNz / 4, c1, std::true_type{});
+            c0 = n0;
+            c1 = n1;
+          }
         }
-        split2_inv<(s >= 8)>(P, Q, sp[s * 32], v[s], v[31 - s]);
+        // bin Nz/2 pairs with itself: Q = conj(P) (computed by every lane, stored by lane 0)
+        {
+          constexpr int k = C::kNz / 2;
+          const float2 tws = sm.spn[k];
+          PC P, Q;
+          if constexpr (MODE >= 2) {
+            const ulonglong2 zk = zp[k];
+            const float sAa = __ldg(a.S + rowA + k) * mA, sBa = __ldg(a.S + rowB + k) * mB;
+            float2 tAa = make_float2(0.f, 0.f), tBa = tAa;
+            if constexpr (MODE == 3) {
+              if (!a.first) {
+                tAa = a.tprev[rowA + k];
+                tBa = a.tprev[rowB + k];
+              }
+            }
+            PC Zk;
+            Zk.re = zk.x; Zk.im = zk.y;
+            split2<true>(Zk, Zk, tws, P, Q);
+            if constexpr (MODE == 3) {
+              if (lane == 0 && okA) a.tprev[rowA + k] = make_float2(plo(P.re), plo(P.im));
+              if (lane == 0 && okB) a.tprev[rowB + k] = make_float2(phi(P.re), phi(P.im));
+            }
+            P = gl2_update<MODE>(P, sAa, sBa, tAa, tBa, a.alpha, a.first, 0, false);
+          } else {
+            P = gl2_fetch<MODE>(a, rowA, rowB, okA, okB, k, 0, false);
+          }
+          Q.re = P.re;
+          Q.im = sub2(0ull, P.im);
+          PC Zk2, Zr2;
+          split2_inv<true>(P, Q, tws, Zk2, Zr2);
+          __syncwarp();   // (MODE 3: all lanes have read tprev[k] before lane 0's store above is visible -- same value anyway)
+          if (lane == 0) zp[k] = make_ulonglong2(Zk2.re, Zk2.im);
+        }
       });
-      // reverse exchange: v[31 - s] <- Z'[Nz - k] computed by the partner (column 0: by this lane's slot s + 1, bin Nz/2: self pair)
-      static_for<0, 16>([&](auto sc) {
-        constexpr int s = decltype(sc)::value;
-        PC send;
-        if constexpr (s < 15) send = pc_sel(col0, v[30 - s], v[31 - s]);
-        else send = pc_sel(col0, zself, v[16]);
-        v[31 - s] = pc_shfl(send, partner);
-      });
+      __syncwarp();
+      {
+        const ulonglong2* rz = xz + pl * C::kNz + k1;
+        static_for<0, 32>([&](auto kc) {
+          constexpr int k2 = decltype(kc)::value;
+          const ulonglong2 z = rz[C::kR2 * k2];
+          v[k2].re = z.x;
+          v[k2].im = z.y;
+        });
+      }
+      __syncwarp();   // spectrum read before the inverse transform reuses the buffer
       fft2_inverse<N>(v, xbuf, sm.tw, lane);
       // synthesis window and window-sum-square normaliser (librosa.istft), frames into this warp's staging buffer
       static_for<0, C::kP>([&](auto pc_) {

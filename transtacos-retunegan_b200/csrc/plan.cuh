@@ -33,6 +33,8 @@ struct PlanDev {
   const float2* ws;       // [Nz/2+1]         -0.5i * w_N^k
   const float2* sp2;      // [17*32]          packed-engine split twiddles, slot s, lane l: k = l%R2 + R2*s, phi = 2 pi k/N:
                           //                  s < 8: (tan phi, cos phi); s >= 8: (cot phi, sin phi)   (fft2.cuh split2)
+  const float2* spn;      // [Nz/2+2]         split twiddles in natural bin order, phi = 2 pi k/N: k < Nz/4: (tan phi, cos phi),
+                          //                  k >= Nz/4: (cot phi, sin phi)   (gl2.cuh spectrum pass)
   // banded mel, ELL per round of 32 rows: melw[round_off[r] + it*32 + lane], it < round_len[r]
   const float* melw;
   const int* mel_lo;      // [32*rounds]      slot (round, lane): first bin read | mel row << 16 (row 0x7fff: empty slot)
@@ -194,6 +196,12 @@ inline std::string build_plan(const sb200_config& c, sb200_plan* p, int* st) {
                               : make_float2(static_cast<float>(std::cos(ph) / std::sin(ph)), static_cast<float>(std::sin(ph)));
     }
 
+  std::vector<float2> spn(Nz / 2 + 2, make_float2(0.f, 0.f));
+  for (int k = 0; k <= Nz / 2; ++k) {
+    const double ph = 2.0 * pi * k / N;
+    spn[k] = k < Nz / 4 ? make_float2(static_cast<float>(std::tan(ph)), static_cast<float>(std::cos(ph)))
+                        : make_float2(static_cast<float>(std::cos(ph) / std::sin(ph)), static_cast<float>(std::sin(ph)));
+  }
   p->mel_dense = mel_filterbank(c.sample_rate, N, c.n_mel, c.fmin, c.fmax, c.mel_htk != 0);
   const std::vector<float>& mb = p->mel_dense;
   const int rounds = (c.n_mel + 31) / 32;
@@ -298,7 +306,7 @@ inline std::string build_plan(const sb200_config& c, sb200_plan* p, int* st) {
   cudaError_t e;
 #define SB200_UP(vec, field) \
   if ((e = upload(p, vec, &d.field)) != cudaSuccess) return std::string("cuda upload: ") + cudaGetErrorString(e);
-  SB200_UP(wf, window) SB200_UP(wout, wout) SB200_UP(wnorm, wnorm) SB200_UP(wsq, wsq) SB200_UP(wedge, wedge) SB200_UP(tw, tw) SB200_UP(ws, ws) SB200_UP(sp2, sp2)
+  SB200_UP(wf, window) SB200_UP(wout, wout) SB200_UP(wnorm, wnorm) SB200_UP(wsq, wsq) SB200_UP(wedge, wedge) SB200_UP(tw, tw) SB200_UP(ws, ws) SB200_UP(sp2, sp2) SB200_UP(spn, spn)
   SB200_UP(melw, melw) SB200_UP(slots, mel_lo) SB200_UP(r0, col_r0) SB200_UP(c0, col_c0) SB200_UP(c1, col_c1)
 #undef SB200_UP
   *st = SB200_OK;
