@@ -99,6 +99,12 @@ __device__ __noinline__ void gl2_edge_weights(const PlanDev& p, int t, int n_fra
   for (int m = lane; m < p.win; m += 32) out[m] = synth_scale_edge(p, t, n_frames, m);
 }
 
+__device__ __forceinline__ float gl2_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 // Phase update of one held spectral value X of both frames of a pair (modes 2 / 3): magnitudes sA / sB, previous
 // spectrum tA / tB.  rot = bin index mod 4, conj_held = b side (value held conjugated): only used for the exact-zero case.
 template <int MODE>
@@ -125,7 +131,8 @@ __device__ __forceinline__ PC gl2_update(const PC& X, float sA, float sB, float2
       c.im = fma2s(pk(tA.y, tB.y), -alpha, X.im);
     }
     const pf n2 = norm2(c);
-    const pf sc = pk(sA / (sqrtf(plo(n2)) + 1e-16f), sB / (sqrtf(phi(n2)) + 1e-16f));
+    // MUFU sqrt / reciprocal (~1e-7 relative): far inside the Griffin-Lim tolerance, and branch-free
+    const pf sc = pk(sA * gl2_rcp(fast_sqrt(plo(n2)) + 1e-16f), sB * gl2_rcp(fast_sqrt(phi(n2)) + 1e-16f));
     o.re = mul2(c.re, sc);
     o.im = mul2(c.im, sc);
   }
@@ -349,7 +356,7 @@ __global__ void __launch_bounds__(kGl2Warps * 32, 1) gl2_kernel(const PlanDev p,
           constexpr int kTrips = C::kNz / 128;
           PairLd c0 = ld_pair(lane), c1 = ld_pair(lane + C::kNz / 4);
 #pragma unroll 1
-          for (int ii = 0; ii < kTrips; ++ii) {
+          for (int ii = 0; ii < kTrips; ++ii) {   // rolled on purpose: a single-tile launch runs this code once, from a cold instruction cache
             const int k = lane + 32 * ii;
             PairLd n0 = c0, n1 = c1;
             if (ii + 1 < kTrips) {
