@@ -9,7 +9,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libspectral_b200.so")
+# SB200_LIB: kernel-experiment builds (tools/variants.py); the default is the in-tree library
+LIB_PATH = os.environ.get("SB200_LIB") or os.path.join(_HERE, "libspectral_b200.so")
 
 
 class Config(C.Structure):

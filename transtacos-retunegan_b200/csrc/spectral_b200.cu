@@ -5,33 +5,31 @@
 #include <mutex>
 #include <string>
 
+#include "capi_common.cuh"
 #include "feat.cuh"
-#include "feat2.cuh"
-#include "gl.cuh"
-#include "gl2.cuh"
-#include "mstft.cuh"
 #include "misc.cuh"
 
 using namespace sb200;
+using namespace sb200::host;
 
 namespace {
-
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
+}  // namespace
 
-int fail(int st, const std::string& msg) {
+int sb200::host::fail(int st, const std::string& msg) {
   g_err = msg;
   return st;
 }
 
-int check_launch(const char* what) {
+int sb200::host::check_launch(const char* what) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(SB200_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
   return SB200_OK;
 }
 
-int sm_count() {
+int sb200::host::sm_count() {
   static int n = 0;
   if (n == 0) {
     int dev = 0;
@@ -42,7 +40,7 @@ int sm_count() {
   return n;
 }
 
-ScaleDev to_dev(const sb200_scale& s) { return ScaleDev{s.log, s.a, s.b, s.floor}; }
+namespace {
 
 // Signal-described batch (STFT direction): frames = 1 + len/hop.
 int make_batch_signal(const sb200_plan* plan, const sb200_batch* b, BatchDev* out, long long* total_frames) {
@@ -88,43 +86,7 @@ int launch_features_spec(const sb200_plan* plan, const FeatArgs& a, cudaStream_t
   return check_launch("stft_feature_kernel");
 }
 
-template <int N, bool PRE, bool LOGMAG, int HS>
-void launch_features2_t(const sb200_plan* plan, const FeatArgs& a, int grid, size_t smem, cudaStream_t st) {
-  cudaFuncSetAttribute(stft_feature2_kernel<N, PRE, LOGMAG, HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  stft_feature2_kernel<N, PRE, LOGMAG, HS><<<grid, kFeat2Warps * 32, smem, st>>>(plan->dev, a);
-}
-
-// Packed engine: magnitude / mel features (the hot path).
-template <int N>
-int launch_features2(const sb200_plan* plan, const FeatArgs& a, cudaStream_t st) {
-  const size_t smem = feat2_smem_bytes<N>(plan->dev);
-  const long long ctas_needed = (a.bd.total_items + kFeat2Warps - 1) / kFeat2Warps;
-  const int grid = static_cast<int>(std::min<long long>(ctas_needed, sm_count()));
-  const bool pre = a.pre != 0.f, lg = a.mag_scale.log != 0;
-  if constexpr (N == 2048) {
-    if (plan->cfg.hop_length == 256) {   // the reference hop (hparam.py): frames of a pair share 3/4 of their samples
-      if (pre && lg) launch_features2_t<N, true, true, 4>(plan, a, grid, smem, st);
-      else if (pre) launch_features2_t<N, true, false, 4>(plan, a, grid, smem, st);
-      else if (lg) launch_features2_t<N, false, true, 4>(plan, a, grid, smem, st);
-      else launch_features2_t<N, false, false, 4>(plan, a, grid, smem, st);
-      return check_launch("stft_feature2_kernel");
-    }
-  }
-  if (pre && lg) launch_features2_t<N, true, true, 0>(plan, a, grid, smem, st);
-  else if (pre) launch_features2_t<N, true, false, 0>(plan, a, grid, smem, st);
-  else if (lg) launch_features2_t<N, false, true, 0>(plan, a, grid, smem, st);
-  else launch_features2_t<N, false, false, 0>(plan, a, grid, smem, st);
-  return check_launch("stft_feature2_kernel");
-}
-
 }  // namespace
-
-#define SB200_DISPATCH_N(plan, ...)                           \
-  switch ((plan)->cfg.n_fft) {                                \
-    case 2048: { constexpr int kN = 2048; __VA_ARGS__; } break; \
-    case 1024: { constexpr int kN = 1024; __VA_ARGS__; } break; \
-    default:   { constexpr int kN = 512;  __VA_ARGS__; } break; \
-  }
 
 // All sb200_* definitions below get C linkage from their declarations in include/spectral_b200.h.
 
@@ -191,9 +153,68 @@ int sb200_stft_features(const sb200_plan* plan, const float* x, const sb200_batc
   if (spec) {
     SB200_DISPATCH_N(plan, rc = launch_features_spec<kN>(plan, a, static_cast<cudaStream_t>(stream)));
   } else {
-    SB200_DISPATCH_N(plan, rc = launch_features2<kN>(plan, a, static_cast<cudaStream_t>(stream)));
+    rc = launch_features2_any(plan, a, static_cast<cudaStream_t>(stream));
   }
   return rc;
 }
 
-#include "capi_rest.inc"
+int sb200_mel_project(const sb200_plan* plan, const float* in, int64_t frames, sb200_scale scale, float* out,
+                      sb200_stream stream) {
+  if (!plan || !in || !out || frames < 1) return fail(SB200_ERR_INVALID, "mel_project: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SB200_DISPATCH_N(plan, {
+    const size_t smem = feat_smem_bytes<kN>(plan->dev);
+    const long long items = (frames + FftCfg<kN>::kQ - 1) / FftCfg<kN>::kQ;
+    const int grid = static_cast<int>(std::min<long long>((items + kFeatWarps - 1) / kFeatWarps, 2LL * sm_count()));
+    cudaFuncSetAttribute(mel_project_kernel<kN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    mel_project_kernel<kN><<<grid, kFeatWarps * 32, smem, st>>>(plan->dev, in, frames, to_dev(scale), out);
+  });
+  return check_launch("mel_project_kernel");
+}
+
+int sb200_spec_to_amplitude(const float* in, int64_t n, int32_t mode, float p0, float p1, float p2, float power,
+                            float* out, sb200_stream stream) {
+  if (!in || !out || n < 1 || mode < 0 || mode > 2) return fail(SB200_ERR_INVALID, "spec_to_amplitude: bad argument");
+  spec_to_amplitude_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, n, mode, p0, p1, p2, power, out);
+  return check_launch("spec_to_amplitude_kernel");
+}
+
+static int make_batch_rows(const sb200_batch* b, BatchDev* out) {
+  if (!b || b->B < 1) return fail(SB200_ERR_INVALID, "batch: B must be >= 1");
+  BatchDev d{};
+  d.B = b->B;
+  if (b->sig_off == nullptr) {
+    if (b->len < 1) return fail(SB200_ERR_INVALID, "batch: len must be >= 1");
+    d.len = b->len;
+    d.stride = b->stride > 0 ? b->stride : b->len;
+  } else {
+    if (!b->sig_len) return fail(SB200_ERR_INVALID, "ragged batch: missing sig_len");
+    d.sig_off = reinterpret_cast<const long long*>(b->sig_off);
+    d.sig_len = reinterpret_cast<const long long*>(b->sig_len);
+  }
+  *out = d;
+  return SB200_OK;
+}
+
+int sb200_preemphasis(const float* x, const sb200_batch* batch, float k, float* y, sb200_stream stream) {
+  if (!x || !y) return fail(SB200_ERR_INVALID, "preemphasis: null argument");
+  BatchDev bd;
+  if (int rc = make_batch_rows(batch, &bd)) return rc;
+  const long long per_row = bd.sig_off ? (1 << 20) : bd.len;
+  dim3 grid(grid_for(per_row, 256, 4), bd.B);
+  preemphasis_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, bd, k, y);
+  return check_launch("preemphasis_kernel");
+}
+
+int sb200_inv_preemphasis(const float* x, const sb200_batch* batch, float k, float* y, sb200_stream stream) {
+  if (!x || !y) return fail(SB200_ERR_INVALID, "inv_preemphasis: null argument");
+  BatchDev bd;
+  if (int rc = make_batch_rows(batch, &bd)) return rc;
+  return host::launch_inv_preemphasis(x, bd, k, y, static_cast<cudaStream_t>(stream));
+}
+
+int sb200::host::launch_inv_preemphasis(const float* x, const BatchDev& rows, float k, float* y, cudaStream_t st) {
+  inv_preemphasis_kernel<<<rows.B, kScanThreads, 0, st>>>(x, rows, k, y);
+  return check_launch("inv_preemphasis_kernel");
+}
+
