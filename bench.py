@@ -191,7 +191,7 @@ def make_stft_mel(sb, torch, B=64, rot=6):
     w.step, w.e2e = step, e2e
     w.units = B * L5 / SR
     w.alg_bytes = B * (4 * L5 + 4 * T5 * (F + N_MEL))          # 4L + 4T(F+M) per utterance
-    w.dominant = "stft_feature2_kernel<2048,true,true,4>"
+    w.dominant = "stft_feature3_kernel<2048,true,4>"
     w.h2d = B * L5 * 4
     w.d2h = B * T5 * (F + N_MEL) * 4
     w.note = (f"{rot} rotating input/output sets ({rot * (w.alg_bytes) / 1e6:.0f} MB) > 126 MB L2 between reuses; "
@@ -311,7 +311,7 @@ def make_corpus(sb, torch, rank, world, n_utt=10000, chunk=256):
     w.units = float(L.sum()) / SR
     nf = int(T.sum())
     w.alg_bytes = 4.0 * L.sum() * 2 + 4.0 * nf * (F + N_MEL) + 4.0 * nf * F + nf * (4 * F * 5 + 16 * F * 4) + 8.0 * L.sum() * 5
-    w.dominant = "gl2_kernel<2048,3> (4 per chunk) + stft_feature2_kernel (2 per chunk)"
+    w.dominant = "gl2_kernel<2048,3> (4 per chunk) + stft_feature3_kernel (2 per chunk)"
     w.launches_dominant_per_step = 1
     w.note = (f"{len(mine)} of {n_utt} utterances on this rank ({nf} frames, {w.units / 3600:.2f} h), ragged chunks of {chunk}; "
               "features + ln-magnitude + Griffin-Lim (4 it, m 0.7, device-drawn initial phase); outputs stay in HBM")

@@ -202,13 +202,6 @@ __global__ void __launch_bounds__(kFeat2Warps * 32, 1) stft_feature2_kernel(cons
   sm.fill(p, a.mel != nullptr);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#ifdef kFeat2Stagger
-  // the second warp of every scheduler starts half an item late: FMA-heavy and MUFU/LSU-heavy phases then overlap
-  if (warp >= kFeat2Warps / 2) {
-    const long long t0 = clock64();
-    while (clock64() - t0 < kFeat2Stagger) {}
-  }
-#endif
   uint4* xbuf = sm.xbufs + warp * C::kXElems;
   pf* sbuf = reinterpret_cast<pf*>(xbuf);   // [P][Nz] magnitudes of both frames of a pair (aliases the exchange buffer)
   const int k1 = lane & (C::kR2 - 1), pl = lane / C::kR2;   // pass-B role of this lane: column k1 of pair pl

@@ -1,0 +1,380 @@
+// Warp-specialised STFT-magnitude + mel feature kernel (packed FFT engine, fft2.cuh):
+//   [pre-emphasis ->] reflect pad -> frame gather -> window -> real FFT -> |.|^2   (8 "analysis" warps, FMA pipe)
+//   |.|^2 -> dB-normalise / ln / raw magnitude stores, sqrt -> banded mel -> scale   (8 "epilogue" warps, MUFU / LSU)
+//   transtacos/audio.py:73-77 get_specs;  retunegan/audio.py:116-128 get_mag / get_mel.
+// Why two roles: in the single-role kernel (feat2.cuh) the 8 warps of an SM drift into lock-step, so the FMA-bound
+// FFT, the shared-memory-bound exchange / mel phases and the MUFU-bound log phase run one after the other and each
+// pipe idles most of the time.  Here analysis warp w hands the squared magnitudes of one item (a frame pair set,
+// see feat2.cuh) to epilogue warp w through a private shared-memory buffer guarded by two mbarriers (full / empty),
+// and moves on to the next item's FFT while the epilogue warp takes logs, stores and runs the mel filterbank.
+// Registers are re-partitioned with setmaxnreg (analysis 200, epilogue 56 per thread; 128 at launch).
+#pragma once
+#include "feat2.cuh"
+
+namespace sb200 {
+
+constexpr int kFeat3Pairs = 8;                 // analysis / epilogue warp pairs per CTA
+constexpr int kFeat3Threads = 2 * kFeat3Pairs * 32;
+constexpr int kFeat3PbufElems = 1024 + 16;     // [P][Nz] powers of both frames of a pair + P Nyquist bins + zero pad
+#ifndef kFeat3AnalysisRegs
+#define kFeat3AnalysisRegs 200
+#endif
+#ifndef kFeat3SplitInterleaved
+#define kFeat3SplitInterleaved 1
+#endif
+#ifndef kFeat3L2Prefetch
+#define kFeat3L2Prefetch 0
+#endif
+#ifndef kFeat3EpilogueRegs
+#define kFeat3EpilogueRegs 56
+#endif
+
+__device__ __forceinline__ void mbar_init(unsigned addr, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned addr) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned addr, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}" ::"r"(addr), "r"(parity)
+      : "memory");
+}
+
+template <int N>
+struct Smem3 {
+  using C = Fft2Cfg<N>;
+  uint4* xbufs;             // [pairs][kXElems] exchange buffers of the analysis warps
+  pf* pbufs;                // [pairs][kFeat3PbufElems]
+  float* win;               // [win] 0.5 * analysis window
+  float2* tw;               // [kTwCount]
+  float2* sp2;              // [17*32]
+  float* melw;              // [melw_count]
+  int* mel_lo;              // [32*rounds]
+  unsigned long long* bar;  // [2*pairs]: full[w], empty[w]
+  __host__ __device__ static size_t bytes(int melw_count, int mel_rounds) {
+    return static_cast<size_t>(kFeat3Pairs) * (C::kXBytes + kFeat3PbufElems * sizeof(pf)) + sizeof(float) * C::kWin +
+           sizeof(float2) * (C::kTwCount + 17 * 32) + sizeof(float) * melw_count + sizeof(int) * 32 * mel_rounds +
+           sizeof(unsigned long long) * 2 * kFeat3Pairs;
+  }
+  __device__ __forceinline__ void carve(unsigned char* raw, const PlanDev& p) {
+    xbufs = reinterpret_cast<uint4*>(raw);
+    pbufs = reinterpret_cast<pf*>(raw + static_cast<size_t>(kFeat3Pairs) * C::kXBytes);
+    win = reinterpret_cast<float*>(pbufs + kFeat3Pairs * kFeat3PbufElems);
+    tw = reinterpret_cast<float2*>(win + C::kWin);
+    sp2 = tw + C::kTwCount;
+    melw = reinterpret_cast<float*>(sp2 + 17 * 32);
+    mel_lo = reinterpret_cast<int*>(melw + p.melw_count);
+    bar = reinterpret_cast<unsigned long long*>(mel_lo + 32 * p.mel_rounds);
+  }
+  template <class T>
+  static __device__ __forceinline__ void copy16(T* dst, const T* src, int count, float scale = 1.f) {
+    const int n16 = count * static_cast<int>(sizeof(T)) / 16;
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll 2
+    for (int i = threadIdx.x; i < n16; i += kFeat3Threads) {
+      float4 t = __ldg(s4 + i);
+      if (scale != 1.f) t = make_float4(t.x * scale, t.y * scale, t.z * scale, t.w * scale);
+      d4[i] = t;
+    }
+  }
+  __device__ __forceinline__ void fill(const PlanDev& p, bool with_mel) {
+    copy16(win, p.window, C::kWin, 0.5f);
+    copy16(tw, p.tw, C::kTwCount);
+    copy16(sp2, p.sp2, 17 * 32);
+    if (with_mel) {
+      copy16(melw, p.melw, p.melw_count);
+      copy16(mel_lo, p.mel_lo, 32 * p.mel_rounds);
+    }
+    for (int i = threadIdx.x; i < kFeat3Pairs * kFeat3PbufElems; i += kFeat3Threads) pbufs[i] = 0ull;
+  }
+};
+
+// Pass-A registers of one item (layout: load_item2 in feat2.cuh).  HS > 0 (hop == 64 HS, n_fft 2048): the two frames
+// of an interior pair overlap by R - HS lane slots, so the pair needs R + HS slots of (even, odd) samples once.  The
+// "previous sample" of the pre-emphasis FIR, x[p0 + 2 lane + 64 r - 1], is the odd sample of lane - 1 (slot r), or of
+// lane 31 (slot r - 1) for lane 0: it comes from a shuffle, only x[p0 - 1] is loaded on top.
+template <int N, bool PRE, int HS>
+struct Gather3 {
+  using C = Fft2Cfg<N>;
+  static constexpr int kSlots = HS > 0 ? C::kR + HS : 1;
+  Item it;
+  bool shared;
+  float lo[kSlots], hi[kSlots], pm1;
+  // Request the samples of `item`.  Every register is (re)defined on every call (an item that is not an interior pair
+  // reads one valid dummy address): values that are only conditionally defined end up in local memory.
+  __device__ __forceinline__ void issue(const BatchDev& bd, long long item, const float* __restrict__ x, int hop, int lane) {
+    it = decode_item(bd, item, C::kFrames);
+    shared = false;
+    if constexpr (HS > 0) {
+      const long long p0 = static_cast<long long>(it.t0) * hop - N / 4;
+      shared = (it.t0 + 1 < it.T) && p0 >= 1 && p0 + hop + C::kWin <= it.L;
+      const float* xp = x + it.sig_base + (shared ? p0 + 2 * lane : 0);
+      const int st = shared ? 64 : 0, od = shared ? 1 : 0;
+      static_for<0, kSlots>([&](auto rc) {
+        constexpr int r = decltype(rc)::value;
+        lo[r] = __ldg(xp + st * r);
+        hi[r] = __ldg(xp + st * r + od);
+      });
+      pm1 = PRE ? __ldg(x + it.sig_base + (shared ? p0 - 1 : 0)) : 0.f;
+    }
+  }
+  // Pass-A registers from the requested samples (interior pair) or through the generic edge path.
+  __device__ __forceinline__ void consume(PC (&v)[32], const float* __restrict__ x, int hop, float pre,
+                                          const float* __restrict__ s_win, float* stage, int lane) {
+    if (HS > 0 && shared) {
+      if constexpr (HS > 0) {
+        if constexpr (PRE) {
+          float carry = pm1;
+          static_for<0, kSlots>([&](auto rc) {
+            constexpr int r = decltype(rc)::value;
+            const float t = __shfl_sync(kFullMask, hi[r], (lane + 31) & 31);
+            const float pv = lane == 0 ? carry : t;
+            carry = t;
+            const float l = lo[r];
+            lo[r] = fmaf(-pre, pv, l);
+            hi[r] = fmaf(-pre, l, hi[r]);
+          });
+        }
+        static_for<0, C::kR>([&](auto rc) {
+          constexpr int r = decltype(rc)::value;
+          const float2 w = *reinterpret_cast<const float2*>(s_win + 2 * lane + 64 * r);
+          constexpr int idx = brev(r, C::kLogR2);
+          v[idx].re = mul2(pk(lo[r], lo[r + HS]), pk(w.x, w.x));
+          v[idx].im = mul2(pk(hi[r], hi[r + HS]), pk(w.y, w.y));
+          v[idx + 1] = v[idx];
+        });
+      }
+    } else {
+      static_for<0, C::kP>([&](auto pc_) {
+        constexpr int p = decltype(pc_)::value;
+        float re[2][C::kR], im[2][C::kR];
+        const int t = it.t0 + 2 * p;
+        load_frame2<N, PRE>(re[0], im[0], x + it.sig_base, it.L, t, it.T, hop, pre, s_win, stage, lane);
+        load_frame2<N, PRE>(re[1], im[1], x + it.sig_base, it.L, t + 1, it.T, hop, pre, s_win, stage, lane);
+        static_for<0, C::kR>([&](auto rc) {
+          constexpr int r = decltype(rc)::value;
+          constexpr int idx = p * C::kR2 + brev(r, C::kLogR2);
+          v[idx].re = pk(re[0][r], re[1][r]);
+          v[idx].im = pk(im[0][r], im[1][r]);
+          v[idx + 1] = v[idx];
+        });
+      });
+    }
+  }
+};
+
+// ---- analysis warp: gather + window + FFT + Hermitian split; |A|^2 of every bin goes to the pair's power buffer ----
+template <int N, bool PRE, int HS>
+__device__ __forceinline__ void feat3_analysis(const PlanDev& p, const FeatArgs& a, Smem3<N>& sm, int w, int lane) {
+  using C = Fft2Cfg<N>;
+  uint4* xbuf = sm.xbufs + w * C::kXElems;
+  pf* pbuf = sm.pbufs + w * kFeat3PbufElems;
+  const unsigned full = smem_u32(sm.bar + w), empty = smem_u32(sm.bar + kFeat3Pairs + w);
+  const int k1 = lane & (C::kR2 - 1), pl = lane / C::kR2;   // pass-B role of this lane: column k1 of pair pl
+  const bool col0 = (k1 == 0);
+  const int partner = (lane & ~(C::kR2 - 1)) | ((C::kR2 - k1) & (C::kR2 - 1));
+  pf* const sa = pbuf + pl * C::kNz + k1;                                  // bins k1 + R2 s
+  pf* const sb = pbuf + pl * C::kNz + C::kNz - k1;     // bins Nz - k1 - R2 s
+  pf* const sb0 = col0 ? pbuf + C::kP * C::kNz + pl : sb;   // s = 0: column 0 holds the Nyquist bin, kept after the P rows
+  const float2* const sp = sm.sp2 + lane;
+  const long long warps_total = static_cast<long long>(gridDim.x) * kFeat3Pairs;
+  long long item = static_cast<long long>(blockIdx.x) * kFeat3Pairs + w;
+  unsigned round = 0;
+  for (; item < a.bd.total_items; item += warps_total, ++round) {
+    // No register prefetch across items: ptxas spills whatever stays live over the loop edge when the register budget comes
+    // from setmaxnreg.  The epilogue warp prefetches the next item's samples into L2 instead, and the other three warps
+    // of the scheduler cover the remaining latency.
+    Gather3<N, PRE, HS> nx;
+    nx.issue(a.bd, item, a.x, p.hop, lane);
+    PC v[32];
+    nx.consume(v, a.x, p.hop, a.pre, sm.win, reinterpret_cast<float*>(xbuf), lane);
+    fft2_forward<N>(v, xbuf, sm.tw, lane);
+    // lane (pl, k1) now holds Z[k1 + R2*k2] of frames t0 + 2 pl, t0 + 2 pl + 1
+    // all split twiddles up front: a table load written after a store to the power buffer cannot be hoisted above it
+    float2 spv[17];
+    static_for<0, 17>([&](auto sc) {
+      constexpr int s = decltype(sc)::value;
+      spv[s] = sp[s * 32];
+    });
+    mbar_wait(empty, (round & 1) ^ 1);   // the epilogue warp is done with the previous item's powers
+    {
+      // self pair of column 0 (bin Nz/2) first: the exchange below overwrites v[16]
+      PC ak, am;
+      split2<true>(v[16], v[16], spv[16], ak, am);
+      if (col0) sa[C::kR2 * 16] = norm2(ak);
+    }
+#if kFeat3SplitInterleaved
+    // Z[Nz - k] comes from the partner lane slot by slot, consumed at once (nothing is overwritten: no ordering constraint)
+    static_for<0, 16>([&](auto sc) {
+      constexpr int s = decltype(sc)::value;
+      const PC zr = pc_shfl(pc_sel(col0, v[(32 - s) & 31], v[31 - s]), partner);
+      PC ak, am;
+      split2<(s >= 8)>(v[s], zr, spv[s], ak, am);
+      sa[C::kR2 * s] = norm2(ak);
+      if constexpr (s == 0) sb0[0] = norm2(am);
+      else sb[-C::kR2 * s] = norm2(am);
+    });
+#else
+    // exchange with the partner lane, all slots back to back and in place: slot s receives Z[Nz - k] into v[31 - s]
+    static_for<0, 16>([&](auto sc) {
+      constexpr int s = 15 - decltype(sc)::value;
+      const PC send = pc_sel(col0, v[(32 - s) & 31], v[31 - s]);
+      v[31 - s] = pc_shfl(send, partner);
+    });
+    static_for<0, 16>([&](auto sc) {
+      constexpr int s = decltype(sc)::value;
+      PC ak, am;
+      split2<(s >= 8)>(v[s], v[31 - s], spv[s], ak, am);
+      sa[C::kR2 * s] = norm2(ak);
+      if constexpr (s == 0) sb0[0] = norm2(am);
+      else sb[-C::kR2 * s] = norm2(am);
+    });
+#endif
+    mbar_arrive(full);
+  }
+}
+
+// ---- epilogue warp: powers -> scaled magnitudes (coalesced row stores), sqrt -> banded mel -> scale -> stores ----
+template <int N>
+__device__ __forceinline__ void feat3_epilogue(const PlanDev& p, const FeatArgs& a, Smem3<N>& sm, int w, int lane) {
+  using C = Fft2Cfg<N>;
+  pf* pbuf = sm.pbufs + w * kFeat3PbufElems;
+  const unsigned full = smem_u32(sm.bar + w), empty = smem_u32(sm.bar + kFeat3Pairs + w);
+  const bool want_mag = a.mag != nullptr, want_mel = a.mel != nullptr;
+  const bool logmag = a.mag_scale.log != 0;
+  // squared-magnitude form of the log scale: a log2 max(floor, sqrt p) + b = a/2 log2 max(floor^2, p) + b
+  const float mag_a = 0.5f * a.mag_scale.a, mag_b = a.mag_scale.b, mag_fl = a.mag_scale.floor * a.mag_scale.floor;
+  const int c_lo = want_mel ? p.mel_kmin / 32 : 1 << 30, c_hi = want_mel ? p.mel_kmax / 32 : -1;   // chunks the mel filters read
+  const long long warps_total = static_cast<long long>(gridDim.x) * kFeat3Pairs;
+  unsigned round = 0;
+  for (long long item = static_cast<long long>(blockIdx.x) * kFeat3Pairs + w; item < a.bd.total_items; item += warps_total, ++round) {
+    const Item it = decode_item(a.bd, item, C::kFrames);
+    if (kFeat3L2Prefetch && item + warps_total < a.bd.total_items) {   // the analysis warp gathers these samples one item from now
+      const Item nx = decode_item(a.bd, item + warps_total, C::kFrames);
+      const long long s0 = max(0LL, static_cast<long long>(nx.t0) * p.hop - N / 4 - 1);
+      const long long s1 = min(nx.L, static_cast<long long>(nx.t0 + C::kFrames - 1) * p.hop - N / 4 + C::kWin);
+      const char* base = reinterpret_cast<const char*>(a.x + nx.sig_base + s0);
+      const long long bytes = (s1 - s0) * 4;
+      for (long long off = 128LL * lane; off < bytes; off += 128 * 32)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+    }
+    mbar_wait(full, round & 1);
+#pragma unroll
+    for (int q = 0; q < C::kP; ++q) {
+      const int fA = it.t0 + 2 * q;
+      const bool stA = want_mag && fA < it.T, stB = want_mag && fA + 1 < it.T;
+      float* const rowA = a.mag + (it.frame_base + fA) * C::kF + lane;
+      pf* const src = pbuf + q * C::kNz + lane;
+      // 4 chunks of 32 bins per trip, all loads first: the write-back of the square roots may alias later loads as far
+      // as the compiler can tell, so loads written after a store are not hoisted
+#pragma unroll 1
+      for (int j0 = 0; j0 < C::kNz / 32; j0 += 4) {
+        pf pw[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) pw[u] = src[32 * (j0 + u)];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = j0 + u;
+          const bool band = (j >= c_lo && j <= c_hi);
+          if (logmag) {
+            const pf o = fma2s(pk(fast_lg2(fmaxf(mag_fl, plo(pw[u]))), fast_lg2(fmaxf(mag_fl, phi(pw[u])))), mag_a, pk(mag_b, mag_b));
+            if (stA) rowA[32 * j] = plo(o);
+            if (stB) rowA[C::kF + 32 * j] = phi(o);
+            if (band) src[32 * j] = sqrt2(pw[u]);
+          } else {
+            const pf o = sqrt2(pw[u]);
+            if (stA) rowA[32 * j] = plo(o);
+            if (stB) rowA[C::kF + 32 * j] = phi(o);
+            if (band) src[32 * j] = o;
+          }
+        }
+      }
+    }
+    if (want_mag && lane < C::kP) {   // Nyquist bins
+      const int fA = it.t0 + 2 * lane;
+      const pf pw = pbuf[C::kP * C::kNz + lane];
+      const pf o = logmag ? fma2s(pk(fast_lg2(fmaxf(mag_fl, plo(pw))), fast_lg2(fmaxf(mag_fl, phi(pw)))), mag_a, pk(mag_b, mag_b))
+                          : sqrt2(pw);
+      float* const row = a.mag + (it.frame_base + fA) * C::kF + C::kNz;
+      if (fA < it.T) row[0] = plo(o);
+      if (fA + 1 < it.T) row[C::kF] = phi(o);
+    }
+    __syncwarp();
+    if (want_mel) {
+#pragma unroll
+      for (int rd = 0; rd < kMaxMelRounds; ++rd) {
+        if (rd < p.mel_rounds) {
+          const int slot = sm.mel_lo[rd * 32 + lane];
+          const int m = slot >> 16, lo = slot & 0xffff;
+          const float* wr = sm.melw + p.mel_round_off[rd] + lane;
+          const pf* sr = pbuf + lo;   // reads may run past the row end (zero weights) into finite stale data
+          const int n = p.mel_round_len[rd];   // multiple of 8
+          pf acc[C::kP][4];
+#pragma unroll
+          for (int q = 0; q < C::kP; ++q)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[q][j] = 0ull;
+          constexpr int kChunk = C::kP == 1 ? 8 : 4;   // loads in flight per trip (round lengths are multiples of 8)
+#pragma unroll 1
+          for (int i0 = 0; i0 < n; i0 += kChunk) {
+            float wv[kChunk];
+            pf sv[C::kP][kChunk];
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j) wv[j] = wr[(i0 + j) * 32];
+#pragma unroll
+            for (int q = 0; q < C::kP; ++q)
+#pragma unroll
+              for (int j = 0; j < kChunk; ++j) sv[q][j] = sr[q * C::kNz + i0 + j];
+#pragma unroll
+            for (int q = 0; q < C::kP; ++q)
+#pragma unroll
+              for (int j = 0; j < kChunk; ++j) acc[q][j & 3] = fma2s(sv[q][j], wv[j], acc[q][j & 3]);
+          }
+          if (m < p.n_mel) {
+#pragma unroll
+            for (int q = 0; q < C::kP; ++q) {
+              const pf s = add2(add2(acc[q][0], acc[q][1]), add2(acc[q][2], acc[q][3]));
+              const int f = it.t0 + 2 * q;
+              float* dst = a.mel + (it.frame_base + f) * p.n_mel + m;
+              if (f < it.T) dst[0] = apply_scale(a.mel_scale, plo(s));
+              if (f + 1 < it.T) dst[p.n_mel] = apply_scale(a.mel_scale, phi(s));
+            }
+          }
+        }
+      }
+    }
+    mbar_arrive(empty);
+  }
+}
+
+template <int N, bool PRE, int HS>
+__global__ void __launch_bounds__(kFeat3Threads, 1) stft_feature3_kernel(const PlanDev p, const FeatArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem3<N> sm;
+  sm.carve(smem_raw, p);
+  sm.fill(p, a.mel != nullptr);
+  if (threadIdx.x < 2 * kFeat3Pairs) mbar_init(smem_u32(sm.bar + threadIdx.x), 32);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp < kFeat3Pairs) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kFeat3AnalysisRegs));
+    feat3_analysis<N, PRE, HS>(p, a, sm, warp, lane);
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kFeat3EpilogueRegs));
+    feat3_epilogue<N>(p, a, sm, warp - kFeat3Pairs, lane);
+  }
+}
+
+template <int N>
+inline size_t feat3_smem_bytes(const PlanDev& p) {
+  return Smem3<N>::bytes(p.melw_count, p.mel_rounds);
+}
+
+}  // namespace sb200

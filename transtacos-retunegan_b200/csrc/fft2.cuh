@@ -199,25 +199,46 @@ __device__ __forceinline__ void fft2_forward(PC (&v)[32], uint4* __restrict__ xb
     constexpr int p = decltype(pc_)::value;
     dit<C::kR2, p * C::kR2, false, 4>(v);
   });
-  // twiddle (shared by all pairs) + transposed store: element (row = lane, col = p*R2 + k1)
+  // twiddle (shared by all pairs) + transposed store: element (row = lane, col = p*R2 + k1).  The twiddles are read in
+  // batches of 8, one batch ahead of their use: the stores are volatile asm with a memory clobber, so a table load
+  // written after a store is never hoisted above it and would cost one shared-memory round trip per column.
   const unsigned wrow = smem_u32(xbuf + C::xoff(lane));
-  static_for<0, C::kR2>([&](auto kc) {
-    constexpr int k1 = decltype(kc)::value;
-    if constexpr (k1 == 0) {
-      static_for<0, C::kP>([&](auto pc_) {
-        constexpr int p = decltype(pc_)::value;
-        sts_pc<16 * (p * C::kR2)>(wrow, v[p * C::kR2].re, v[p * C::kR2].im);
-      });
-    } else {
-      const float2 w = tw[(k1 - 1) * 32 + lane];
-      static_for<0, C::kP>([&](auto pc_) {
-        constexpr int p = decltype(pc_)::value;
-        const PC& y = v[p * C::kR2 + k1];
-        const pf re = fma2s(y.im, -w.y, mul2s(y.re, w.x));
-        const pf im = fma2s(y.im, w.x, mul2s(y.re, w.y));
-        sts_pc<16 * (p * C::kR2 + k1)>(wrow, re, im);
-      });
-    }
+  constexpr int kTwBatch = 8;
+  float2 wcur[kTwBatch], wnext[kTwBatch];
+  static_for<0, kTwBatch>([&](auto jc) {
+    constexpr int j = decltype(jc)::value;
+    if constexpr (j >= 1 && j < C::kR2) wcur[j] = tw[(j - 1) * 32 + lane];
+  });
+  static_for<0, (C::kR2 + kTwBatch - 1) / kTwBatch>([&](auto bc) {
+    constexpr int b = decltype(bc)::value;
+    static_for<0, kTwBatch>([&](auto jc) {
+      constexpr int j = decltype(jc)::value;
+      constexpr int k1n = (b + 1) * kTwBatch + j;
+      if constexpr (k1n < C::kR2) wnext[j] = tw[(k1n - 1) * 32 + lane];
+    });
+    static_for<0, kTwBatch>([&](auto jc) {
+      constexpr int j = decltype(jc)::value;
+      constexpr int k1 = b * kTwBatch + j;
+      if constexpr (k1 == 0) {
+        static_for<0, C::kP>([&](auto pc_) {
+          constexpr int p = decltype(pc_)::value;
+          sts_pc<16 * (p * C::kR2)>(wrow, v[p * C::kR2].re, v[p * C::kR2].im);
+        });
+      } else if constexpr (k1 < C::kR2) {
+        const float2 w = wcur[j];
+        static_for<0, C::kP>([&](auto pc_) {
+          constexpr int p = decltype(pc_)::value;
+          const PC& y = v[p * C::kR2 + k1];
+          const pf re = fma2s(y.im, -w.y, mul2s(y.re, w.x));
+          const pf im = fma2s(y.im, w.x, mul2s(y.re, w.y));
+          sts_pc<16 * (p * C::kR2 + k1)>(wrow, re, im);
+        });
+      }
+    });
+    static_for<0, kTwBatch>([&](auto jc) {
+      constexpr int j = decltype(jc)::value;
+      wcur[j] = wnext[j];
+    });
   });
   __syncwarp();
   // transposed read: lane j takes column j of every row n1, placed bit-reversed for the DIT
