@@ -101,74 +101,61 @@ struct Smem3 {
 // "previous sample" of the pre-emphasis FIR, x[p0 + 2 lane + 64 r - 1], is the odd sample of lane - 1 (slot r), or of
 // lane 31 (slot r - 1) for lane 0: it comes from a shuffle, only x[p0 - 1] is loaded on top.
 template <int N, bool PRE, int HS>
-struct Gather3 {
+__device__ __forceinline__ void gather_item3(PC (&v)[32], const Item& it, const float* __restrict__ x, int hop, float pre,
+                                             const float* __restrict__ s_win, float* stage, int lane) {
   using C = Fft2Cfg<N>;
-  static constexpr int kSlots = HS > 0 ? C::kR + HS : 1;
-  Item it;
-  bool shared;
-  float lo[kSlots], hi[kSlots], pm1;
-  // Request the samples of `item`.  Every register is (re)defined on every call (an item that is not an interior pair
-  // reads one valid dummy address): values that are only conditionally defined end up in local memory.
-  __device__ __forceinline__ void issue(const BatchDev& bd, long long item, const float* __restrict__ x, int hop, int lane) {
-    it = decode_item(bd, item, C::kFrames);
-    shared = false;
-    if constexpr (HS > 0) {
-      const long long p0 = static_cast<long long>(it.t0) * hop - N / 4;
-      shared = (it.t0 + 1 < it.T) && p0 >= 1 && p0 + hop + C::kWin <= it.L;
-      const float* xp = x + it.sig_base + (shared ? p0 + 2 * lane : 0);
-      const int st = shared ? 64 : 0, od = shared ? 1 : 0;
+  bool shared = false;
+  if constexpr (HS > 0) {
+    const long long p0 = static_cast<long long>(it.t0) * hop - N / 4;
+    shared = (it.t0 + 1 < it.T) && p0 >= 1 && p0 + hop + C::kWin <= it.L;
+    if (shared) {   // loads and their use stay inside one block: conditionally defined registers end up in local memory
+      constexpr int kSlots = C::kR + HS;
+      float lo[kSlots], hi[kSlots];
+      const float* xp = x + it.sig_base + p0 + 2 * lane;
       static_for<0, kSlots>([&](auto rc) {
         constexpr int r = decltype(rc)::value;
-        lo[r] = __ldg(xp + st * r);
-        hi[r] = __ldg(xp + st * r + od);
+        lo[r] = __ldg(xp + 64 * r);
+        hi[r] = __ldg(xp + 64 * r + 1);
       });
-      pm1 = PRE ? __ldg(x + it.sig_base + (shared ? p0 - 1 : 0)) : 0.f;
-    }
-  }
-  // Pass-A registers from the requested samples (interior pair) or through the generic edge path.
-  __device__ __forceinline__ void consume(PC (&v)[32], const float* __restrict__ x, int hop, float pre,
-                                          const float* __restrict__ s_win, float* stage, int lane) {
-    if (HS > 0 && shared) {
-      if constexpr (HS > 0) {
-        if constexpr (PRE) {
-          float carry = pm1;
-          static_for<0, kSlots>([&](auto rc) {
-            constexpr int r = decltype(rc)::value;
-            const float t = __shfl_sync(kFullMask, hi[r], (lane + 31) & 31);
-            const float pv = lane == 0 ? carry : t;
-            carry = t;
-            const float l = lo[r];
-            lo[r] = fmaf(-pre, pv, l);
-            hi[r] = fmaf(-pre, l, hi[r]);
-          });
-        }
-        static_for<0, C::kR>([&](auto rc) {
+      if constexpr (PRE) {
+        float carry = __ldg(x + it.sig_base + p0 - 1);
+        static_for<0, kSlots>([&](auto rc) {
           constexpr int r = decltype(rc)::value;
-          const float2 w = *reinterpret_cast<const float2*>(s_win + 2 * lane + 64 * r);
-          constexpr int idx = brev(r, C::kLogR2);
-          v[idx].re = mul2(pk(lo[r], lo[r + HS]), pk(w.x, w.x));
-          v[idx].im = mul2(pk(hi[r], hi[r + HS]), pk(w.y, w.y));
-          v[idx + 1] = v[idx];
+          const float t = __shfl_sync(kFullMask, hi[r], (lane + 31) & 31);
+          const float pv = lane == 0 ? carry : t;
+          carry = t;
+          const float l = lo[r];
+          lo[r] = fmaf(-pre, pv, l);
+          hi[r] = fmaf(-pre, l, hi[r]);
         });
       }
-    } else {
-      static_for<0, C::kP>([&](auto pc_) {
-        constexpr int p = decltype(pc_)::value;
-        float re[2][C::kR], im[2][C::kR];
-        const int t = it.t0 + 2 * p;
-        load_frame2<N, PRE>(re[0], im[0], x + it.sig_base, it.L, t, it.T, hop, pre, s_win, stage, lane);
-        load_frame2<N, PRE>(re[1], im[1], x + it.sig_base, it.L, t + 1, it.T, hop, pre, s_win, stage, lane);
-        static_for<0, C::kR>([&](auto rc) {
-          constexpr int r = decltype(rc)::value;
-          constexpr int idx = p * C::kR2 + brev(r, C::kLogR2);
-          v[idx].re = pk(re[0][r], re[1][r]);
-          v[idx].im = pk(im[0][r], im[1][r]);
-          v[idx + 1] = v[idx];
-        });
+      static_for<0, C::kR>([&](auto rc) {
+        constexpr int r = decltype(rc)::value;
+        const float2 w = *reinterpret_cast<const float2*>(s_win + 2 * lane + 64 * r);
+        constexpr int idx = brev(r, C::kLogR2);
+        v[idx].re = pk(lo[r] * w.x, lo[r + HS] * w.x);   // scalar products land in the two halves directly: no packing MOVs
+        v[idx].im = pk(hi[r] * w.y, hi[r + HS] * w.y);
+        v[idx + 1] = v[idx];
       });
     }
   }
-};
+  if (!shared) {
+    static_for<0, C::kP>([&](auto pc_) {
+      constexpr int p = decltype(pc_)::value;
+      float re[2][C::kR], im[2][C::kR];
+      const int t = it.t0 + 2 * p;
+      load_frame2<N, PRE>(re[0], im[0], x + it.sig_base, it.L, t, it.T, hop, pre, s_win, stage, lane);
+      load_frame2<N, PRE>(re[1], im[1], x + it.sig_base, it.L, t + 1, it.T, hop, pre, s_win, stage, lane);
+      static_for<0, C::kR>([&](auto rc) {
+        constexpr int r = decltype(rc)::value;
+        constexpr int idx = p * C::kR2 + brev(r, C::kLogR2);
+        v[idx].re = pk(re[0][r], re[1][r]);
+        v[idx].im = pk(im[0][r], im[1][r]);
+        v[idx + 1] = v[idx];
+      });
+    });
+  }
+}
 
 // ---- analysis warp: gather + window + FFT + Hermitian split; |A|^2 of every bin goes to the pair's power buffer ----
 template <int N, bool PRE, int HS>
@@ -191,10 +178,9 @@ __device__ __forceinline__ void feat3_analysis(const PlanDev& p, const FeatArgs&
     // No register prefetch across items: ptxas spills whatever stays live over the loop edge when the register budget comes
     // from setmaxnreg.  The epilogue warp prefetches the next item's samples into L2 instead, and the other three warps
     // of the scheduler cover the remaining latency.
-    Gather3<N, PRE, HS> nx;
-    nx.issue(a.bd, item, a.x, p.hop, lane);
+    const Item it = decode_item(a.bd, item, C::kFrames);
     PC v[32];
-    nx.consume(v, a.x, p.hop, a.pre, sm.win, reinterpret_cast<float*>(xbuf), lane);
+    gather_item3<N, PRE, HS>(v, it, a.x, p.hop, a.pre, sm.win, reinterpret_cast<float*>(xbuf), lane);
     fft2_forward<N>(v, xbuf, sm.tw, lane);
     // lane (pl, k1) now holds Z[k1 + R2*k2] of frames t0 + 2 pl, t0 + 2 pl + 1
     // all split twiddles up front: a table load written after a store to the power buffer cannot be hoisted above it

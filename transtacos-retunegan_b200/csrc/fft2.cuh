@@ -9,7 +9,7 @@
 // Transform (same mathematics as fftcore.cuh): a frame is win = N/2 window taps a[m] centred in N points,
 //   z[n] = a[2n] + i a[2n+1]   (n < Nz/2, Nz = N/2; upper half of the Nz-point input is zero)
 //   Z = DFT_Nz(z) = pass A (in-lane radix-2R DIT, first stage pruned) -> twiddle -> 32x32 transpose through
-//       shared memory (one 16-byte packed complex per element) -> pass B (in-lane radix-32 DIT)
+//       shared memory (two planes of 8-byte packed reals) -> pass B (in-lane radix-32 DIT)
 //   split: A[k] = Zk + conj Zr + g_k (Zk - conj Zr), A[Nz-k] = conj(Zk + conj Zr - g_k (Zk - conj Zr)),
 //          Zr = Z[Nz-k], g_k = -i w_N^k, with the 1/2 folded into the window table;  X[k] = (-i)^k A[k].
 // Butterflies are in Linzer-Feig form: w b = c (b.re + t b.im, b.im - t b.re), t = tan, and the scale c is
@@ -92,6 +92,20 @@ template <int OFF>
 __device__ __forceinline__ PC lds_pc(unsigned addr) {
   PC r;
   asm volatile("ld.shared.v2.b64 {%0, %1}, [%2+%3];" : "=l"(r.re), "=l"(r.im) : "r"(addr), "n"(OFF) : "memory");
+  return r;
+}
+
+// 8-byte accesses of one packed real (both frames of a pair).  The forward transpose keeps the real and imaginary parts
+// in two planes of 8-byte elements: a 16-byte st.shared.v2.b64 needs its four source registers consecutive, which costs
+// four MOVs per store after packed arithmetic (ptxas does not allocate the producers into quads).
+template <int OFF>
+__device__ __forceinline__ void sts_pf(unsigned addr, pf x) {
+  asm volatile("st.shared.b64 [%0+%2], %1;" ::"r"(addr), "l"(x), "n"(OFF) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ pf lds_pf(unsigned addr) {
+  pf r;
+  asm volatile("ld.shared.b64 %0, [%1+%2];" : "=l"(r) : "r"(addr), "n"(OFF) : "memory");
   return r;
 }
 
@@ -185,6 +199,7 @@ struct Fft2Cfg {
   __host__ __device__ static constexpr int xoff(int row) { return row * 33; }
   static constexpr int kXElems = 32 * 33;
   static constexpr int kXBytes = kXElems * 16;   // per-warp exchange buffer
+  static constexpr int kPlane = kXElems * 8;     // forward transpose: imaginary plane offset (8-byte elements, same 33 padding)
 };
 
 // ---- pass A + twiddle + transpose + pass B: v (pass-A inputs, see below) -> v[k2] = Z_p[k1 + R2 k2] --------
@@ -202,7 +217,7 @@ __device__ __forceinline__ void fft2_forward(PC (&v)[32], uint4* __restrict__ xb
   // twiddle (shared by all pairs) + transposed store: element (row = lane, col = p*R2 + k1).  The twiddles are read in
   // batches of 8, one batch ahead of their use: the stores are volatile asm with a memory clobber, so a table load
   // written after a store is never hoisted above it and would cost one shared-memory round trip per column.
-  const unsigned wrow = smem_u32(xbuf + C::xoff(lane));
+  const unsigned wrow = smem_u32(xbuf) + 8 * C::xoff(lane);
   constexpr int kTwBatch = 8;
   float2 wcur[kTwBatch], wnext[kTwBatch];
   static_for<0, kTwBatch>([&](auto jc) {
@@ -222,7 +237,8 @@ __device__ __forceinline__ void fft2_forward(PC (&v)[32], uint4* __restrict__ xb
       if constexpr (k1 == 0) {
         static_for<0, C::kP>([&](auto pc_) {
           constexpr int p = decltype(pc_)::value;
-          sts_pc<16 * (p * C::kR2)>(wrow, v[p * C::kR2].re, v[p * C::kR2].im);
+          sts_pf<8 * (p * C::kR2)>(wrow, v[p * C::kR2].re);
+          sts_pf<C::kPlane + 8 * (p * C::kR2)>(wrow, v[p * C::kR2].im);
         });
       } else if constexpr (k1 < C::kR2) {
         const float2 w = wcur[j];
@@ -231,7 +247,8 @@ __device__ __forceinline__ void fft2_forward(PC (&v)[32], uint4* __restrict__ xb
           const PC& y = v[p * C::kR2 + k1];
           const pf re = fma2s(y.im, -w.y, mul2s(y.re, w.x));
           const pf im = fma2s(y.im, w.x, mul2s(y.re, w.y));
-          sts_pc<16 * (p * C::kR2 + k1)>(wrow, re, im);
+          sts_pf<8 * (p * C::kR2 + k1)>(wrow, re);
+          sts_pf<C::kPlane + 8 * (p * C::kR2 + k1)>(wrow, im);
         });
       }
     });
@@ -242,10 +259,11 @@ __device__ __forceinline__ void fft2_forward(PC (&v)[32], uint4* __restrict__ xb
   });
   __syncwarp();
   // transposed read: lane j takes column j of every row n1, placed bit-reversed for the DIT
-  const unsigned rcol = smem_u32(xbuf + lane);
+  const unsigned rcol = smem_u32(xbuf) + 8 * lane;
   static_for<0, 32>([&](auto nc) {
     constexpr int n1 = decltype(nc)::value;
-    v[brev(n1, 5)] = lds_pc<16 * C::xoff(n1)>(rcol);
+    v[brev(n1, 5)].re = lds_pf<8 * C::xoff(n1)>(rcol);
+    v[brev(n1, 5)].im = lds_pf<C::kPlane + 8 * C::xoff(n1)>(rcol);
   });
   dit<32, 0, false, 2>(v);
   __syncwarp();   // exchange buffer free again
