@@ -19,12 +19,6 @@ constexpr int kFeat3PbufElems = 1024 + 16;     // [P][Nz] powers of both frames 
 #ifndef kFeat3AnalysisRegs
 #define kFeat3AnalysisRegs 200
 #endif
-#ifndef kFeat3SplitInterleaved
-#define kFeat3SplitInterleaved 1
-#endif
-#ifndef kFeat3L2Prefetch
-#define kFeat3L2Prefetch 0
-#endif
 #ifndef kFeat3EpilogueRegs
 #define kFeat3EpilogueRegs 56
 #endif
@@ -176,8 +170,8 @@ __device__ __forceinline__ void feat3_analysis(const PlanDev& p, const FeatArgs&
   unsigned round = 0;
   for (; item < a.bd.total_items; item += warps_total, ++round) {
     // No register prefetch across items: ptxas spills whatever stays live over the loop edge when the register budget comes
-    // from setmaxnreg.  The epilogue warp prefetches the next item's samples into L2 instead, and the other three warps
-    // of the scheduler cover the remaining latency.
+    // from setmaxnreg; the other three warps of the scheduler cover the load latency.  (Measured and dropped: an L2 prefetch
+    // of the next item from the epilogue warp, +1 us; a second copy of the loop body for the edge path, +3.7 us.)
     const Item it = decode_item(a.bd, item, C::kFrames);
     PC v[32];
     gather_item3<N, PRE, HS>(v, it, a.x, p.hop, a.pre, sm.win, reinterpret_cast<float*>(xbuf), lane);
@@ -196,7 +190,6 @@ __device__ __forceinline__ void feat3_analysis(const PlanDev& p, const FeatArgs&
       split2<true>(v[16], v[16], spv[16], ak, am);
       if (col0) sa[C::kR2 * 16] = norm2(ak);
     }
-#if kFeat3SplitInterleaved
     // Z[Nz - k] comes from the partner lane slot by slot, consumed at once (nothing is overwritten: no ordering constraint)
     static_for<0, 16>([&](auto sc) {
       constexpr int s = decltype(sc)::value;
@@ -207,22 +200,6 @@ __device__ __forceinline__ void feat3_analysis(const PlanDev& p, const FeatArgs&
       if constexpr (s == 0) sb0[0] = norm2(am);
       else sb[-C::kR2 * s] = norm2(am);
     });
-#else
-    // exchange with the partner lane, all slots back to back and in place: slot s receives Z[Nz - k] into v[31 - s]
-    static_for<0, 16>([&](auto sc) {
-      constexpr int s = 15 - decltype(sc)::value;
-      const PC send = pc_sel(col0, v[(32 - s) & 31], v[31 - s]);
-      v[31 - s] = pc_shfl(send, partner);
-    });
-    static_for<0, 16>([&](auto sc) {
-      constexpr int s = decltype(sc)::value;
-      PC ak, am;
-      split2<(s >= 8)>(v[s], v[31 - s], spv[s], ak, am);
-      sa[C::kR2 * s] = norm2(ak);
-      if constexpr (s == 0) sb0[0] = norm2(am);
-      else sb[-C::kR2 * s] = norm2(am);
-    });
-#endif
     mbar_arrive(full);
   }
 }
@@ -242,15 +219,6 @@ __device__ __forceinline__ void feat3_epilogue(const PlanDev& p, const FeatArgs&
   unsigned round = 0;
   for (long long item = static_cast<long long>(blockIdx.x) * kFeat3Pairs + w; item < a.bd.total_items; item += warps_total, ++round) {
     const Item it = decode_item(a.bd, item, C::kFrames);
-    if (kFeat3L2Prefetch && item + warps_total < a.bd.total_items) {   // the analysis warp gathers these samples one item from now
-      const Item nx = decode_item(a.bd, item + warps_total, C::kFrames);
-      const long long s0 = max(0LL, static_cast<long long>(nx.t0) * p.hop - N / 4 - 1);
-      const long long s1 = min(nx.L, static_cast<long long>(nx.t0 + C::kFrames - 1) * p.hop - N / 4 + C::kWin);
-      const char* base = reinterpret_cast<const char*>(a.x + nx.sig_base + s0);
-      const long long bytes = (s1 - s0) * 4;
-      for (long long off = 128LL * lane; off < bytes; off += 128 * 32)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
-    }
     mbar_wait(full, round & 1);
 #pragma unroll
     for (int q = 0; q < C::kP; ++q) {
