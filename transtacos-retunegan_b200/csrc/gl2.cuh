@@ -169,6 +169,26 @@ __device__ __forceinline__ PC gl2_fetch(const Gl2Args& a, long long rowA, long l
   return r;
 }
 
+// Same from values fetched ahead of their use (modes 0 / 1): mode 0: tA / tB = spectrum values (already masked); mode 1:
+// sA / sB = magnitudes (masked), tA.x / tB.x = initial phase u in [0, 1).
+template <int MODE>
+__device__ __forceinline__ PC gl2_fetch_v(float sA, float sB, float2 tA, float2 tB, int rot, bool conj_it) {
+  float2 xa = tA, xb = tB;
+  if constexpr (MODE == 1) {
+    float s, c;
+    sincospif(2.f * tA.x, &s, &c);
+    xa = make_float2(sA * c, sA * s);
+    sincospif(2.f * tB.x, &s, &c);
+    xb = make_float2(sB * c, sB * s);
+  }
+  xa = rot_i(xa, rot);
+  xb = rot_i(xb, rot);
+  PC r;
+  r.re = pk(xa.x, xb.x);
+  r.im = conj_it ? pk(-xa.y, -xb.y) : pk(xa.y, xb.y);
+  return r;
+}
+
 template <int N, int MODE>
 __global__ void __launch_bounds__(kGl2Warps * 32, 1) gl2_kernel(const PlanDev p, const Gl2Args a) {
   using C = Fft2Cfg<N>;
@@ -294,6 +314,25 @@ __global__ void __launch_bounds__(kGl2Warps * 32, 1) gl2_kernel(const PlanDev p,
         };
         auto ld_pair = [&](int k) -> PairLd {
           PairLd L;
+          if constexpr (MODE == 0) {   // the input spectrum, masked (rows past the end are clamped)
+            const int kb = C::kNz - k;
+            const float2 a0 = __ldg(a.spec + rowA + k), b0 = __ldg(a.spec + rowB + k);
+            const float2 a1 = __ldg(a.spec + rowA + kb), b1 = __ldg(a.spec + rowB + kb);
+            L.tAa = make_float2(a0.x * mA, a0.y * mA);
+            L.tBa = make_float2(b0.x * mB, b0.y * mB);
+            L.tAb = make_float2(a1.x * mA, a1.y * mA);
+            L.tBb = make_float2(b1.x * mB, b1.y * mB);
+          } else if constexpr (MODE == 1) {   // magnitudes and initial phases: without this the loads sit behind each sincospif
+            const int kb = C::kNz - k;
+            L.sAa = __ldg(a.S + rowA + k) * mA;
+            L.sBa = __ldg(a.S + rowB + k) * mB;
+            L.sAb = __ldg(a.S + rowA + kb) * mA;
+            L.sBb = __ldg(a.S + rowB + kb) * mB;
+            L.tAa.x = __ldg(a.init_phase + rowA + k);
+            L.tBa.x = __ldg(a.init_phase + rowB + k);
+            L.tAb.x = __ldg(a.init_phase + rowA + kb);
+            L.tBb.x = __ldg(a.init_phase + rowB + kb);
+          }
           if constexpr (MODE >= 2) {
             const int km = (C::kNz - k) & (C::kNz - 1), kb = C::kNz - k;
             L.zk = zp[k];
@@ -338,8 +377,8 @@ __global__ void __launch_bounds__(kGl2Warps * 32, 1) gl2_kernel(const PlanDev p,
             P = gl2_update<MODE>(P, L.sAa, L.sBa, L.tAa, L.tBa, a.alpha, a.first, k & 3, false);
             Q = gl2_update<MODE>(Q, L.sAb, L.sBb, L.tAb, L.tBb, a.alpha, a.first, (4 - (k & 3)) & 3, true);
           } else {
-            P = gl2_fetch<MODE>(a, rowA, rowB, okA, okB, k, k & 3, false);
-            Q = gl2_fetch<MODE>(a, rowA, rowB, okA, okB, kb, (4 - (k & 3)) & 3, true);
+            P = gl2_fetch_v<MODE>(L.sAa, L.sBa, L.tAa, L.tBa, k & 3, false);
+            Q = gl2_fetch_v<MODE>(L.sAb, L.sBb, L.tAb, L.tBb, (4 - (k & 3)) & 3, true);
           }
           if (k == 0) {   // irfft ignores the imaginary parts of DC and Nyquist
             P.im = 0ull;
