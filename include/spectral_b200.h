@@ -120,6 +120,17 @@ int sb200_mel_project(const sb200_plan* plan, const float* in, int64_t frames, s
 int sb200_spec_to_amplitude(const float* in, int64_t n, int32_t mode, float p0, float p1, float p2, float power,
                             float* out, sb200_stream stream);
 
+/* ---- frame statistics sharing the STFT framing ------------------------------------------------------
+ * rms[t]: librosa.feature.rms(y, frame_length, hop_length) (center=True, reflect padding) -- get_c0 at
+ *   transtacos/audio.py:112-114 and retunegan/audio.py:103-105; with frame_length 512 / hop 128 it is the energy
+ *   track of librosa.effects.trim (trim_silence, transtacos/audio.py:59-61).
+ * zcr[t]: librosa.feature.zero_crossing_rate(y, frame_length, hop_length) (center=True, edge padding, threshold 1e-10)
+ *   -- get_zcr at retunegan/audio.py:98-100.
+ * The batch describes the signals; a row of length len has 1 + len / hop_length frames.  For a ragged batch
+ * frame_off must hold the frame offsets FOR THIS hop_length.  Either output may be NULL. */
+int sb200_frame_stats(const float* x, const sb200_batch* batch, int32_t frame_length, int32_t hop_length, float* rms,
+                      float* zcr, sb200_stream stream);
+
 /* ---- pre-emphasis filters (transtacos/audio.py:64-70) ---------------------------------------------
  * preemphasis: y[n] = x[n] - k x[n-1];  inv_preemphasis: y[n] = x[n] + k y[n-1] (parallel scan). */
 int sb200_preemphasis(const float* x, const sb200_batch* batch, float k, float* y, sb200_stream stream);

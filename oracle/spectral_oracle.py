@@ -524,3 +524,78 @@ def synth_speechlike(L, seed, sr=22050):
     env = 0.5 * (1 + np.sin(2 * np.pi * 1.3 * t)) ** 2 / 4 + 0.02
     y = 0.15 * y * env + 0.003 * rs.randn(L)
     return np.clip(y, -0.999, 0.999).astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Frame statistics: librosa 0.8.1 feature.rms / feature.zero_crossing_rate / effects.trim,
+# called at transtacos/audio.py:59-61,112-114 and retunegan/audio.py:98-113.  librosa is not installable here:
+# "parity unpinned" upstream; tests cross-check against an independent torch.unfold formulation.
+
+def _frame(y, frame_length, hop_length):
+    """librosa.util.frame(y, frame_length, hop_length) -> [frame_length, n_frames] (a strided view in librosa)."""
+    n = 1 + (len(y) - frame_length) // hop_length
+    idx = np.arange(frame_length)[:, None] + hop_length * np.arange(n)[None, :]
+    return y[idx]
+
+
+def rms(y, frame_length=2048, hop_length=512):
+    """librosa.feature.rms(y=y, frame_length, hop_length, center=True, pad_mode='reflect')[0] (dtype of y)."""
+    y = np.asarray(y)
+    yp = np.pad(y, int(frame_length // 2), mode="reflect")
+    x = _frame(yp, frame_length, hop_length)
+    power = np.mean(np.abs(x) ** 2, axis=0)
+    return np.sqrt(power)
+
+
+def zero_crossing_rate(y, frame_length=2048, hop_length=512):
+    """librosa.feature.zero_crossing_rate(y, frame_length, hop_length, center=True)[0]: edge padding,
+    zero_crossings(threshold=1e-10, zero_pos=True, pad=False) along the frame axis, mean over the frame."""
+    y = np.asarray(y)
+    yp = np.pad(y, int(frame_length // 2), mode="edge")
+    x = _frame(yp, frame_length, hop_length).copy()
+    x[np.abs(x) <= 1e-10] = 0
+    sign = np.signbit(x)
+    cross = np.zeros(x.shape, dtype=bool)
+    cross[1:] = sign[1:] != sign[:-1]
+    return np.mean(cross, axis=0)
+
+
+def tt_get_c0(y, win_length=1024, hop_length=256):
+    """transtacos/audio.py:112-114 (= retunegan/audio.py:103-105)."""
+    return rms(np.asarray(y, np.float32), win_length, hop_length).astype(np.float32)
+
+
+def rtg_get_zcr(y, win_length=1024, hop_length=256):
+    """retunegan/audio.py:98-100."""
+    return zero_crossing_rate(np.asarray(y, np.float32), win_length, hop_length).astype(np.float32)
+
+
+def rtg_get_uv(zcr, dyn):
+    """retunegan/audio.py:108-113 (the loop, vectorised)."""
+    zcr = np.asarray(zcr)
+    return ((zcr > 0.18) | (np.asarray(dyn) < 0.03)).astype(zcr.dtype)
+
+
+def trim_bounds(y, top_db=35, frame_length=512, hop_length=128):
+    """librosa.effects.trim(y, top_db, ref=np.max, frame_length, hop_length)[1] -> (start, end)."""
+    y = np.asarray(y)
+    mse = rms(y, frame_length, hop_length) ** 2
+    amin = 1e-10
+    db = 10.0 * np.log10(np.maximum(amin, mse)) - 10.0 * np.log10(np.maximum(amin, np.max(mse)))
+    nz = np.flatnonzero(db > -top_db)
+    if nz.size:
+        return int(nz[0]) * hop_length, min(len(y), (int(nz[-1]) + 1) * hop_length)
+    return 0, 0
+
+
+def tt_trim_silence(y, top_db=35, frame_length=512, hop_length=128):
+    """transtacos/audio.py:59-61."""
+    s, e = trim_bounds(y, top_db, frame_length, hop_length)
+    return np.asarray(y)[s:e]
+
+
+def tt_quantilize_c0(c0, c0min=4.6309418394230306e-05, c0max=0.3751049339771271, n_c0_bins=32):
+    """transtacos/audio.py:124-128."""
+    c0 = (np.asarray(c0) - c0min) / (c0max - c0min)
+    c0 = c0 * n_c0_bins
+    return c0.clip(0, n_c0_bins - 1).astype(np.int32)

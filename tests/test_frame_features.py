@@ -1,0 +1,119 @@
+"""Frame-level side features that share the STFT framing: get_c0 (RMS), get_zcr, get_uv,
+trim_silence, quantilize_c0 -- transtacos/audio.py:59-61,112-128, retunegan/audio.py:98-113.
+
+CPU part: the oracle restatement of librosa 0.8.1 rms / zero_crossing_rate / effects.trim against an independent
+torch.unfold formulation (librosa is not installable here: parity unpinned upstream) and against the reference's
+own constants.  GPU part: the CUDA kernel through the reference-named API against the oracle.
+Tolerances: RMS 1e-5 relative (fp32 sums of 1024 squares); zero-crossing rate and trim bounds exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import spectral_oracle as O
+
+
+def _wav(L, seed, kind="speech"):
+    return O.synth_speechlike(L, seed) if kind == "speech" else O.synth_noise(L, seed)
+
+
+def _torch_frames(y, frame_length, hop, mode):
+    yp = torch.nn.functional.pad(torch.from_numpy(np.asarray(y, np.float64))[None, None], (frame_length // 2,) * 2,
+                                 mode="reflect" if mode == "reflect" else "replicate")[0, 0]
+    return yp.unfold(0, frame_length, hop)   # [T, frame_length]
+
+
+@pytest.mark.parametrize("L,fl,hop", [(256 * 40 - 1, 1024, 256), (5000, 512, 128), (1025, 1024, 256)])
+def test_oracle_rms_zcr_vs_torch_unfold(L, fl, hop):
+    y = _wav(L, 7)
+    fr = _torch_frames(y, fl, hop, "reflect")
+    ref_rms = fr.pow(2).mean(1).sqrt().numpy()
+    got = O.rms(y.astype(np.float64), fl, hop)
+    assert got.shape == (1 + L // hop,)
+    np.testing.assert_allclose(got, ref_rms, rtol=1e-12)
+    fe = _torch_frames(y, fl, hop, "edge")
+    fe = torch.where(fe.abs() <= 1e-10, torch.zeros_like(fe), fe)
+    sb = torch.signbit(fe)
+    ref_zcr = (sb[:, 1:] != sb[:, :-1]).double().sum(1).numpy() / fl
+    np.testing.assert_array_equal(O.zero_crossing_rate(y, fl, hop), ref_zcr)
+
+
+def test_oracle_trim_and_quantise():
+    L = 22050
+    y = np.zeros(L, np.float32)
+    y[6000:15000] = _wav(9000, 3)
+    s, e = O.trim_bounds(y, 35, 512, 128)
+    assert 0 < s <= 6000 + 512 and 15000 - 512 <= e < L and s % 128 == 0
+    assert s >= 6000 - 512 and e <= 15000 + 512
+    assert O.trim_bounds(np.zeros(4096, np.float32)) == (0, 4096)   # all frames equal the (floored) reference: nothing is trimmed
+    assert O.trim_bounds(np.r_[np.zeros(3000), 0.5 * np.ones(10), np.zeros(3000)].astype(np.float32))[0] > 0
+    # quantilize_c0: the reference's own constants (transtacos/hparam.py:22-28) map c0min -> 0 and c0max -> last bin
+    q = O.tt_quantilize_c0(np.array([4.6309418394230306e-05, 0.3751049339771271, 0.1, 1.0]))
+    assert q.tolist() == [0, 31, 8, 31] and q.dtype == np.int32
+    uv = O.rtg_get_uv(np.array([0.1, 0.2, 0.1], np.float32), np.array([0.5, 0.5, 0.01], np.float32))
+    assert uv.tolist() == [0.0, 1.0, 1.0] and uv.dtype == np.float32
+
+
+# ------------------------------------------------------------------------------------------------ GPU ----
+
+@pytest.fixture(scope="module")
+def sb():
+    import transtacos_retunegan_b200 as sb
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    sb._lib.load()
+    return sb
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("L", [256 * 40 - 1, 110335, 1500, 600])
+def test_c0_zcr_single(sb, L):
+    y = _wav(L, 11)
+    c0 = sb.transtacos_audio.get_c0(y)
+    assert isinstance(c0, np.ndarray) and c0.dtype == np.float32 and c0.shape == (1 + L // 256,)
+    np.testing.assert_allclose(c0, O.tt_get_c0(y), rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(sb.retunegan_audio.get_c0(y), c0, rtol=0, atol=0)
+    z = sb.retunegan_audio.get_zcr(y)
+    assert z.dtype == np.float32 and z.shape == c0.shape
+    np.testing.assert_array_equal(z, O.rtg_get_zcr(y))
+    np.testing.assert_array_equal(sb.retunegan_audio.get_uv(z, c0), O.rtg_get_uv(O.rtg_get_zcr(y), O.tt_get_c0(y)))
+
+
+@pytest.mark.gpu
+def test_c0_zcr_batched_ragged_and_torch(sb):
+    ys = [_wav(L, 20 + i, "noise" if i % 2 else "speech") for i, L in enumerate([9000, 30001, 4097, 256 * 101 - 1])]
+    c0s = sb.transtacos_audio.get_c0(ys)
+    zs = sb.retunegan_audio.get_zcr(ys)
+    for y, c0, z in zip(ys, c0s, zs):
+        np.testing.assert_allclose(c0, O.tt_get_c0(y), rtol=1e-5, atol=1e-9)
+        np.testing.assert_array_equal(z, O.rtg_get_zcr(y))
+    Y = np.stack([_wav(8191, 40 + i) for i in range(5)])
+    c0 = sb.transtacos_audio.get_c0(torch.from_numpy(Y).cuda())
+    assert c0.is_cuda and tuple(c0.shape) == (5, 32)
+    np.testing.assert_allclose(c0.cpu().numpy(), np.stack([O.tt_get_c0(y) for y in Y]), rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.gpu
+def test_zcr_exact_zeros_and_threshold(sb):
+    y = np.zeros(4096, np.float32)
+    y[100:200] = 1e-11            # below librosa's threshold: counts as +0
+    y[300:400:2] = -0.5           # alternating sign
+    y[300:400][1::2] = 0.0        # exact zeros are positive
+    y[1000] = -1e-9
+    np.testing.assert_array_equal(sb.retunegan_audio.get_zcr(y), O.rtg_get_zcr(y))
+    np.testing.assert_allclose(sb.transtacos_audio.get_c0(y), O.tt_get_c0(y), rtol=1e-5, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_trim_silence_and_quantise(sb):
+    L = 30000
+    y = (1e-4 * O.synth_noise(L, 5)).astype(np.float32)
+    y[7000:21000] += _wav(14000, 6)
+    got = sb.transtacos_audio.trim_silence(y)
+    want = O.tt_trim_silence(y)
+    assert got.shape == want.shape and 0 < len(got) < L
+    np.testing.assert_array_equal(got, want)
+    both = sb.transtacos_audio.trim_silence([y, y[:20000]])
+    np.testing.assert_array_equal(both[0], want)
+    np.testing.assert_array_equal(both[1], O.tt_trim_silence(y[:20000]))
+    c0 = sb.transtacos_audio.get_c0(got[:len(got) // 256 * 256 - 1])
+    np.testing.assert_array_equal(sb.transtacos_audio.quantilize_c0(c0), O.tt_quantilize_c0(c0))

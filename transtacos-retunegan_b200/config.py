@@ -35,6 +35,10 @@ class SpectralConfig:
     gl_power: float = 1.2
     gl_momentum: float = 0.0
     randseed: int = 114514
+    trim_below_peak_db: float = 35          # transtacos/hparam.py:15, retunegan/hparam.py:13
+    c0min: float = 4.6309418394230306e-05   # transtacos/hparam.py:22-23,28 (quantilize_c0)
+    c0max: float = 0.3751049339771271
+    n_c0_bins: int = 32
     multi_stft_params: Tuple[Tuple[int, int, int], ...] = ((2048, 1024, 240), (1024, 512, 120), (512, 256, 60))
     phd_input: str = "stft"
 

@@ -197,6 +197,65 @@ def inv_preemphasis(x: torch.Tensor, k: float) -> torch.Tensor:
     return out
 
 
+def frame_stats(ys, frame_length: int, hop_length: int, want_rms=True, want_zcr=True):
+    """Per-frame RMS and zero-crossing rate with librosa's centred framing (one launch of ``frame_stats_kernel``).
+
+    ``ys``: [L] / [B, L] samples (numpy or torch) or a list of ragged utterances.  Returns
+    ``(rms, zcr, frames)``: float32 CUDA tensors of ``sum(frames)`` values (None if not wanted) and the frame count of
+    every row (``1 + len // hop_length``)."""
+    require_cuda()
+    if isinstance(ys, (list, tuple)):
+        parts = [to_device_f32(y).reshape(-1) for y in ys]
+        if not parts:
+            raise ValueError("empty batch")
+        lens = np.array([p.numel() for p in parts], np.int64)
+        if lens.min() < 1:
+            raise ValueError("empty signal")
+        x = torch.cat(parts)
+        frames = 1 + lens // hop_length
+        tbl = np.zeros((3, len(parts) + 1), np.int64)
+        tbl[0, 1:] = np.cumsum(lens)
+        tbl[1, :-1] = lens
+        tbl[2, 1:] = np.cumsum(frames)
+        tables = torch.from_numpy(tbl).to(x.device)
+        total = int(tbl[2, -1])
+        c = Batch(len(parts), 0, 0, tables[0].data_ptr(), tables[1].data_ptr(), tables[2].data_ptr(), None, total, 0)
+    else:
+        x = to_device_f32(ys)
+        if x.dim() == 1:
+            x = x.unsqueeze(0)
+        if x.dim() != 2 or x.shape[1] < 1:
+            raise ValueError(f"expected [L] or [B, L] samples, got shape {tuple(x.shape)}")
+        x = x.contiguous()
+        B, L = x.shape
+        frames = np.full(B, 1 + L // hop_length, np.int64)
+        total = int(frames.sum())
+        tables = None
+        c = Batch(B, L, L, None, None, None, None, 0, 0)
+    rms = torch.empty(total, device=x.device, dtype=torch.float32) if want_rms else None
+    zcr = torch.empty(total, device=x.device, dtype=torch.float32) if want_zcr else None
+    check(_lib.load().sb200_frame_stats(ptr(x), C.byref(c), int(frame_length), int(hop_length), ptr(rms), ptr(zcr),
+                                        stream_ptr()), "frame_stats")
+    del tables   # (kept alive until the launch has been issued; the stream orders its use)
+    return rms, zcr, frames
+
+
+def trim_bounds(rms: torch.Tensor, frames, lens, hop_length: int, top_db: float):
+    """librosa.effects.trim on a precomputed RMS track (ref = max, amin = 1e-10): [(start, end)] sample bounds per row."""
+    out, o = [], 0
+    r = rms.double().cpu().numpy()
+    for T, L in zip(frames, lens):
+        mse = r[o:o + int(T)] ** 2
+        o += int(T)
+        db = 10.0 * np.log10(np.maximum(1e-10, mse)) - 10.0 * np.log10(np.maximum(1e-10, mse.max()))
+        nz = np.flatnonzero(db > -top_db)
+        if nz.size:
+            out.append((int(nz[0]) * hop_length, min(int(L), (int(nz[-1]) + 1) * hop_length)))
+        else:
+            out.append((0, 0))
+    return out
+
+
 class FramesBatch:
     """Batch of spectrograms described by frame counts (ISTFT / Griffin-Lim direction)."""
 

@@ -142,4 +142,79 @@ __global__ void __launch_bounds__(kScanThreads) inv_preemphasis_kernel(const flo
   }
 }
 
+// Frame statistics that share the STFT framing (frame_length samples, hop, centred):
+//   rms[t] = sqrt(mean(x_reflect[t*hop + m]^2))                 librosa.feature.rms, pad_mode='reflect'
+//            (transtacos/audio.py:112-114, retunegan/audio.py:103-105 get_c0; librosa.effects.trim at transtacos/audio.py:59-61)
+//   zcr[t] = #{m in [1, FL): signbit(x_edge[m]) != signbit(x_edge[m-1])} / FL   librosa.feature.zero_crossing_rate
+//            (retunegan/audio.py:98-100 get_zcr): edge padding, |x| <= 1e-10 counts as +0, the first sample of a frame never counts.
+// One warp per frame, lanes stride the frame; the two sums are reduced by shuffles (deterministic).  frames_per_row /
+// frame_off describe the output rows; HBM-bound: 4 B per sample (neighbouring frames hit L1 / L2), 4-8 B per frame.
+struct FrameStatsArgs {
+  const float* x;
+  BatchDev bd;          // sig_off / sig_len / frame_off (ragged) or len / stride / frames_per_row (uniform)
+  int frame_length, hop;
+  float* rms;           // [frames] or null
+  float* zcr;           // [frames] or null
+  long long total_frames;
+};
+
+__global__ void __launch_bounds__(256) frame_stats_kernel(const FrameStatsArgs a) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nwarps = (gridDim.x * static_cast<long long>(blockDim.x)) >> 5;
+  const int FL = a.frame_length, half = FL / 2;
+  for (long long f = warp; f < a.total_frames; f += nwarps) {
+    long long base, L;
+    int t;
+    if (a.bd.frame_off == nullptr) {
+      const long long b = f / a.bd.frames_per_row;
+      base = b * a.bd.stride;
+      L = a.bd.len;
+      t = static_cast<int>(f - b * a.bd.frames_per_row);
+    } else {
+      int lo = 0, hi = a.bd.B;   // largest b with frame_off[b] <= f
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(a.bd.frame_off + mid) <= f) lo = mid; else hi = mid;
+      }
+      base = __ldg(a.bd.sig_off + lo);
+      L = __ldg(a.bd.sig_len + lo);
+      t = static_cast<int>(f - __ldg(a.bd.frame_off + lo));
+    }
+    const long long i0 = static_cast<long long>(t) * a.hop - half;   // signal index of the frame's first sample
+    const float* x = a.x + base;
+    float ss = 0.f;
+    int cross = 0;
+    const bool interior = i0 >= 1 && i0 + FL <= L;
+    for (int m = lane; m < FL; m += 32) {
+      const long long i = i0 + m;
+      float xr, xe, xp;
+      if (interior) {
+        xr = xe = __ldg(x + i);
+        xp = __ldg(x + i - 1);
+      } else {
+        long long ir = i < 0 ? -i : i;
+        ir = ir >= L ? 2 * (L - 1) - ir : ir;
+        ir = min(max(ir, 0LL), L - 1);     // signals shorter than frame_length/2: librosa raises; stay in bounds
+        xr = __ldg(x + ir);
+        xe = __ldg(x + min(max(i, 0LL), L - 1));
+        xp = __ldg(x + min(max(i - 1, 0LL), L - 1));
+      }
+      ss = fmaf(xr, xr, ss);
+      const bool neg = (fabsf(xe) <= 1e-10f) ? false : signbit(xe);
+      const bool negp = (fabsf(xp) <= 1e-10f) ? false : signbit(xp);
+      cross += (m > 0 && neg != negp) ? 1 : 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ss += __shfl_xor_sync(kFullMask, ss, o);
+      cross += __shfl_xor_sync(kFullMask, cross, o);
+    }
+    if (lane == 0) {
+      if (a.rms) a.rms[f] = sqrtf(ss / static_cast<float>(FL));
+      if (a.zcr) a.zcr[f] = static_cast<float>(cross) / static_cast<float>(FL);
+    }
+  }
+}
+
 }  // namespace sb200

@@ -196,6 +196,30 @@ static int make_batch_rows(const sb200_batch* b, BatchDev* out) {
   return SB200_OK;
 }
 
+int sb200_frame_stats(const float* x, const sb200_batch* batch, int32_t frame_length, int32_t hop_length, float* rms,
+                      float* zcr, sb200_stream stream) {
+  if (!x || (!rms && !zcr)) return fail(SB200_ERR_INVALID, "frame_stats: null argument");
+  if (frame_length < 2 || hop_length < 1) return fail(SB200_ERR_INVALID, "frame_stats: need frame_length >= 2 and hop_length >= 1");
+  FrameStatsArgs a{};
+  if (int rc = make_batch_rows(batch, &a.bd)) return rc;
+  if (a.bd.sig_off) {
+    if (!batch->frame_off) return fail(SB200_ERR_INVALID, "frame_stats: ragged batch needs frame_off for this hop_length");
+    a.bd.frame_off = reinterpret_cast<const long long*>(batch->frame_off);
+    a.total_frames = batch->total_frames;
+  } else {
+    a.bd.frames_per_row = 1 + a.bd.len / hop_length;
+    a.total_frames = a.bd.frames_per_row * a.bd.B;
+  }
+  if (a.total_frames < 1) return fail(SB200_ERR_INVALID, "frame_stats: no frames");
+  a.x = x;
+  a.frame_length = frame_length;
+  a.hop = hop_length;
+  a.rms = rms;
+  a.zcr = zcr;
+  frame_stats_kernel<<<grid_for(a.total_frames * 32, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  return check_launch("frame_stats_kernel");
+}
+
 int sb200_preemphasis(const float* x, const sb200_batch* batch, float k, float* y, sb200_stream stream) {
   if (!x || !y) return fail(SB200_ERR_INVALID, "preemphasis: null argument");
   BatchDev bd;

@@ -18,7 +18,7 @@ import torch
 
 from . import core
 from .config import RETUNEGAN, SpectralConfig
-from .transtacos_audio import _is_np, _split_fm, _to_frame_major, griffin_lim_amplitude, phase_to_frame_major
+from .transtacos_audio import _frame_feature, _is_np, _split_fm, _to_frame_major, griffin_lim_amplitude, phase_to_frame_major
 
 hp: SpectralConfig = RETUNEGAN
 eps = 1e-5
@@ -65,6 +65,24 @@ def get_mel(y, clamp_low=True):
 def get_mag_mel(y, clamp_low=True):
     """Addition: both features from one launch (the reference computes the STFT twice)."""
     return _features(y, True, True, clamp_low)
+
+
+def get_zcr(y):
+    """retunegan/audio.py:98-100: ``librosa.feature.zero_crossing_rate(y, frame_length=win_length, hop_length=hop_length)[0]``."""
+    return _frame_feature(y, hp.win_length, hp.hop_length, "zcr")
+
+
+def get_c0(y):
+    """retunegan/audio.py:103-105: ``librosa.feature.rms(y=y, frame_length=win_length, hop_length=hop_length)[0]``."""
+    return _frame_feature(y, hp.win_length, hp.hop_length, "rms")
+
+
+def get_uv(zcr, dyn):
+    """retunegan/audio.py:108-113: unvoiced where ``zcr > 0.18 or dyn < 0.03`` (same dtype / container as ``zcr``)."""
+    if isinstance(zcr, torch.Tensor):
+        return ((zcr > 0.18) | (torch.as_tensor(dyn, device=zcr.device) < 0.03)).to(zcr.dtype)
+    zcr = np.asarray(zcr)
+    return ((zcr > 0.18) | (np.asarray(dyn) < 0.03)).astype(zcr.dtype)
 
 
 def mag_to_mel(x):

@@ -65,6 +65,44 @@ def align_wav(wav, r=None):
     return wav
 
 
+def _frame_feature(y, frame_length, hop_length, which):
+    """[L] -> [T]; [B, L] -> [B, T]; list of utterances -> list of [T_i].  numpy in -> float32 numpy out, torch in -> CUDA."""
+    as_np = _is_np(y) or (isinstance(y, (list, tuple)) and len(y) > 0 and _is_np(y[0]))
+    rms, zcr, frames = core.frame_stats(y, frame_length, hop_length, want_rms=which == "rms", want_zcr=which == "zcr")
+    v = rms if which == "rms" else zcr
+    if isinstance(y, (list, tuple)):
+        parts = list(torch.split(v, [int(t) for t in frames]))
+        return [p.cpu().numpy() for p in parts] if as_np else parts
+    v = v.view(len(frames), int(frames[0]))
+    if (y.ndim if _is_np(y) else y.dim()) == 1:
+        v = v[0]
+    return v.cpu().numpy() if as_np else v
+
+
+def get_c0(y):
+    """transtacos/audio.py:112-114: ``librosa.feature.rms(y, frame_length=win_length, hop_length=hop_length)[0]`` as float32."""
+    return _frame_feature(y, hp.win_length, hp.hop_length, "rms")
+
+
+def quantilize_c0(c0):
+    """transtacos/audio.py:124-128: linear bins of [c0min, c0max] -> int32 in [0, n_c0_bins - 1] (host arithmetic)."""
+    c0 = np.asarray(c0.detach().cpu() if isinstance(c0, torch.Tensor) else c0)
+    q = (c0 - hp.c0min) / (hp.c0max - hp.c0min) * hp.n_c0_bins
+    return q.clip(0, hp.n_c0_bins - 1).astype(np.int32)
+
+
+def trim_silence(wav, frame_length=512, hop_length=128):
+    """transtacos/audio.py:59-61: ``librosa.effects.trim(wav, top_db=trim_below_peak_db, frame_length, hop_length)[0]``.
+    The RMS track comes from the GPU (one launch); the threshold / first-last scan is host arithmetic on T values.
+    A list of utterances is trimmed with one launch for all of them."""
+    many = isinstance(wav, (list, tuple))
+    ws = list(wav) if many else [wav]
+    rms, _, frames = core.frame_stats(ws, frame_length, hop_length, want_zcr=False)
+    lens = [int(w.shape[-1]) for w in ws]
+    out = [w[s:e] for w, (s, e) in zip(ws, core.trim_bounds(rms, frames, lens, hop_length, hp.trim_below_peak_db))]
+    return out if many else out[0]
+
+
 def preemphasis(x):
     """x[n] - k*x[n-1], zero initial state (transtacos/audio.py:64-66; scipy promotes to float64)."""
     t = core.to_device_f32(x)
