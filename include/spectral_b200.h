@@ -131,6 +131,12 @@ int sb200_spec_to_amplitude(const float* in, int64_t n, int32_t mode, float p0, 
 int sb200_frame_stats(const float* x, const sb200_batch* batch, int32_t frame_length, int32_t hop_length, float* rms,
                       float* zcr, sb200_stream stream);
 
+/* f0[t]: librosa.yin(y, fmin, fmax, sr, frame_length, hop_length=hop_length) (win_length = frame_length / 2, trough
+ *   threshold 0.1, center=True, reflect padding) -- get_f0 at transtacos/audio.py:107-109.  Same batch convention as
+ *   sb200_frame_stats.  frame_length <= 4096. */
+int sb200_yin(const float* x, const sb200_batch* batch, int32_t sample_rate, float fmin, float fmax, int32_t frame_length,
+              int32_t hop_length, float trough_threshold, float* f0, sb200_stream stream);
+
 /* ---- pre-emphasis filters (transtacos/audio.py:64-70) ---------------------------------------------
  * preemphasis: y[n] = x[n] - k x[n-1];  inv_preemphasis: y[n] = x[n] + k y[n-1] (parallel scan). */
 int sb200_preemphasis(const float* x, const sb200_batch* batch, float k, float* y, sb200_stream stream);

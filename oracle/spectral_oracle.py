@@ -599,3 +599,75 @@ def tt_quantilize_c0(c0, c0min=4.6309418394230306e-05, c0max=0.3751049339771271,
     c0 = (np.asarray(c0) - c0min) / (c0max - c0min)
     c0 = c0 * n_c0_bins
     return c0.clip(0, n_c0_bins - 1).astype(np.int32)
+
+
+def _tiny(x):
+    return np.finfo(np.asarray(x).dtype if np.issubdtype(np.asarray(x).dtype, np.floating) else np.float32).tiny
+
+
+def yin(y, fmin, fmax, sr=22050, frame_length=2048, win_length=None, hop_length=None, trough_threshold=0.1):
+    """librosa.yin 0.8.1 (center=True, pad_mode='reflect'): FFT autocorrelation, cumulative-sum energy terms, cumulative
+    mean normalised difference, parabolic interpolation, first trough below the threshold else the global minimum.
+    Weak pin from the reference tree: transtacos/hparam.py:24-25 f0min / f0max equal sr / 301 and sr / 37, the period
+    limits this restatement derives from rf0min = 'D2', rf0max = 'D5'."""
+    y = np.asarray(y)
+    win_length = frame_length // 2 if win_length is None else win_length
+    hop_length = frame_length // 4 if hop_length is None else hop_length
+    yp = np.pad(y, frame_length // 2, mode="reflect")
+    yf = _frame(yp, frame_length, hop_length)                      # [frame_length, T]
+    min_period = max(int(np.floor(sr / fmax)), 1)
+    max_period = min(int(np.ceil(sr / fmin)), frame_length - win_length - 1)
+    a = np.fft.rfft(yf, frame_length, axis=0)
+    b = np.fft.rfft(yf[win_length:0:-1, :], frame_length, axis=0)
+    acf = np.fft.irfft(a * b, frame_length, axis=0)[win_length:]
+    acf[np.abs(acf) < 1e-6] = 0
+    energy = np.cumsum(yf ** 2, axis=0)
+    energy = energy[win_length:, :] - energy[:-win_length, :]
+    energy[np.abs(energy) < 1e-6] = 0
+    d = energy[0, :] + energy - 2 * acf
+    num = d[min_period:max_period + 1, :]
+    tau = np.arange(1, max_period + 1)[:, None]
+    cm = np.cumsum(d[1:max_period + 1, :], axis=0) / tau
+    den = cm[min_period - 1:max_period, :]
+    yn = num / (den + _tiny(den))
+    shifts = np.zeros_like(yn)
+    pa = (yn[:-2, :] + yn[2:, :] - 2 * yn[1:-1, :]) / 2
+    pb = (yn[2:, :] - yn[:-2, :]) / 2
+    shifts[1:-1, :] = -pb / (2 * pa + _tiny(pa))
+    shifts[np.abs(shifts) > 1] = 0
+    neg = -yn
+    xp = np.pad(neg, [(1, 1), (0, 0)], mode="edge")               # librosa.util.localmax(-yn, axis=0)
+    trough = (neg > xp[:-2]) & (neg >= xp[2:])
+    trough[0, :] = yn[0, :] < yn[1, :]
+    thr = np.logical_and(trough, yn < trough_threshold)
+    gmin = np.argmin(yn, axis=0)
+    per = np.argmax(thr, axis=0)
+    none = np.all(~thr, axis=0)
+    per[none] = gmin[none]
+    period = min_period + per + shifts[per, range(yn.shape[1])]
+    return sr / period
+
+
+def note_to_hz(note):
+    """librosa.note_to_hz for a single note name (A4 = 440 Hz)."""
+    pc = {'C': 0, 'D': 2, 'E': 4, 'F': 5, 'G': 7, 'A': 9, 'B': 11}[note[0].upper()]
+    i = 1
+    while i < len(note) and note[i] in '#b':
+        pc += 1 if note[i] == '#' else -1
+        i += 1
+    midi = 12 * (int(note[i:]) + 1) + pc
+    return 440.0 * 2.0 ** ((midi - 69) / 12.0)
+
+
+def tt_get_f0(y, sr=22050, win_length=1024, hop_length=256, rf0min='D2', rf0max='D5'):
+    """transtacos/audio.py:107-109."""
+    return yin(np.asarray(y, np.float32), note_to_hz(rf0min), note_to_hz(rf0max), sr, win_length, None, hop_length).astype(np.float32)
+
+
+def tt_quantilize_f0(f0, f0min=73.25581359863281, f0max=595.9459228515625):
+    """transtacos/audio.py:14-21,117-121."""
+    h2m = lambda f: 12 * (np.log2(f) - np.log2(440.0)) + 69
+    n_min = int(np.floor(h2m(f0min)))
+    n_bins = int(np.ceil(h2m(f0max))) - n_min + 1
+    q = np.asarray([h2m(f) - n_min for f in f0])
+    return q.clip(0, n_bins - 1).astype(np.int32)

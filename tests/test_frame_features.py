@@ -54,6 +54,21 @@ def test_oracle_trim_and_quantise():
     assert uv.tolist() == [0.0, 1.0, 1.0] and uv.dtype == np.float32
 
 
+def test_oracle_yin_pins_and_pure_tones():
+    # weak pin from the reference tree: transtacos/hparam.py:24-25 are the period limits of rf0min / rf0max
+    assert np.isclose(22050 / np.ceil(22050 / O.note_to_hz('D2')), 73.25581359863281)
+    assert np.isclose(22050 / np.floor(22050 / O.note_to_hz('D5')), 595.9459228515625)
+    t = np.arange(22050) / 22050.0
+    for f in (110.0, 220.0, 331.0, 440.0):
+        y = (0.3 * np.sin(2 * np.pi * f * t) + 0.1 * np.sin(4 * np.pi * f * t)).astype(np.float32)
+        f0 = O.tt_get_f0(y)
+        assert f0.shape == (1 + len(y) // 256,) and f0.dtype == np.float32
+        assert np.all(np.abs(f0[4:-4] / f - 1) < 5e-3), (f, f0[4:-4].min(), f0[4:-4].max())
+    assert np.allclose(O.tt_get_f0(np.zeros(4096, np.float32)), 22050 / 37)    # silence: d' = 0 everywhere -> first index -> shortest period
+    q = O.tt_quantilize_f0(np.array([73.26, 100.0, 440.0, 595.9]))
+    assert q.tolist() == [0, 6, 32, 37] and q.dtype == np.int32
+
+
 # ------------------------------------------------------------------------------------------------ GPU ----
 
 @pytest.fixture(scope="module")
@@ -117,3 +132,29 @@ def test_trim_silence_and_quantise(sb):
     np.testing.assert_array_equal(both[1], O.tt_trim_silence(y[:20000]))
     c0 = sb.transtacos_audio.get_c0(got[:len(got) // 256 * 256 - 1])
     np.testing.assert_array_equal(sb.transtacos_audio.quantilize_c0(c0), O.tt_quantilize_c0(c0))
+
+
+@pytest.mark.gpu
+def test_f0_yin(sb):
+    """get_f0 against the oracle restatement of librosa.yin.  The period choice is a discrete decision on fp32 (here) vs
+    fp64-FFT (librosa) difference functions, so a frame may legitimately flip between two troughs at a tie; required: every
+    frame within 1e-4 relative of the oracle on tonal input, >= 99 % of the frames on speech-like / noisy input
+    (measured on the B200: all frames, p99 of the relative deviation 1e-6)."""
+    t = np.arange(30000) / 22050.0
+    y = (0.3 * np.sin(2 * np.pi * 196.0 * t) + 0.1 * np.sin(4 * np.pi * 196.0 * t)).astype(np.float32)
+    f0 = sb.transtacos_audio.get_f0(y)
+    ref = O.tt_get_f0(y)
+    assert f0.dtype == np.float32 and f0.shape == ref.shape
+    assert np.max(np.abs(f0 / ref - 1)) < 1e-4
+    ys = [_wav(L, 60 + i) for i, L in enumerate([256 * 80 - 1, 40001, 9000])]
+    f0s = sb.transtacos_audio.get_f0(ys)
+    for y, f in zip(ys, f0s):
+        ref = O.tt_get_f0(y)
+        assert f.shape == ref.shape
+        ok = np.abs(f / ref - 1) < 1e-4
+        assert ok.mean() >= 0.99, ok.mean()
+        assert f.min() >= 22050 / 302 and f.max() <= 22050 / 36
+    Y = np.stack([_wav(8191, 70 + i) for i in range(3)])
+    fb = sb.transtacos_audio.get_f0(torch.from_numpy(Y).cuda())
+    assert fb.is_cuda and tuple(fb.shape) == (3, 32)
+    np.testing.assert_array_equal(sb.transtacos_audio.quantilize_f0(ref), O.tt_quantilize_f0(ref))

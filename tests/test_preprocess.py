@@ -149,7 +149,7 @@ def test_preprocess_small_corpus_end_to_end(tmp_path):
     old = P.DROPOUT_2SIGMA
     P.DROPOUT_2SIGMA = False        # three utterances: keep them all
     try:
-        metadata, stats, wav_dp = P.preprocess(args, f0_fn=lambda y: np.zeros(1 + len(y) // 256, np.float32))
+        metadata, stats, wav_dp = P.preprocess(args)
     finally:
         P.DROPOUT_2SIGMA = old
     assert wav_dp == str(base / "DataBaker" / "Wave") and [m[0] for m in metadata] == ["000001", "000002", "000003"]
@@ -166,7 +166,9 @@ def test_preprocess_small_corpus_end_to_end(tmp_path):
         assert mag.shape == So.shape == (1025, len(y) // 256) and mel.shape == Mo.shape and mag.flags.f_contiguous
         assert rel_fro(_amp(mag), _amp(So)) < 1e-4 and rel_fro(_amp(mel), _amp(Mo)) < 1e-4
         np.testing.assert_allclose(c0, O.tt_get_c0(y[:-1]), rtol=1e-5, atol=1e-9)
-        assert np.load(base / "preprocessed" / f"f0-{name}.npy").shape == c0.shape
+        f0 = np.load(base / "preprocessed" / f"f0-{name}.npy")
+        assert f0.shape == c0.shape and f0.dtype == np.float32
+        assert (np.abs(f0 / O.tt_get_f0(y[:-1]) - 1) < 1e-4).mean() >= 0.99
         tot += len(y)
     assert stats['total_examples'] == 3 and np.isclose(stats['total_hours'], tot / 22050 / 3600)
     assert stats['min_mag'] >= -5.6 - 1e-3                       # floor of the normalised dB scale (stats/DataBaker.stats:13)

@@ -35,6 +35,10 @@ class SpectralConfig:
     gl_power: float = 1.2
     gl_momentum: float = 0.0
     randseed: int = 114514
+    rf0min: object = 'D2'                   # transtacos/hparam.py:18-19: YIN search range (note name or Hz)
+    rf0max: object = 'D5'
+    f0min: float = 73.25581359863281        # transtacos/hparam.py:24-25: range of the quantiser (= sr / 301, sr / 37)
+    f0max: float = 595.9459228515625
     trim_below_peak_db: float = 35          # transtacos/hparam.py:15, retunegan/hparam.py:13
     c0min: float = 4.6309418394230306e-05   # transtacos/hparam.py:22-23,28 (quantilize_c0)
     c0max: float = 0.3751049339771271
@@ -79,6 +83,30 @@ class SpectralConfig:
                 kw[f.name] = v
         kw.update(overrides)
         return cls(**kw)
+
+
+_NOTE = {'C': 0, 'D': 2, 'E': 4, 'F': 5, 'G': 7, 'A': 9, 'B': 11}
+
+
+def note_to_hz(note) -> float:
+    """librosa.note_to_hz for one note name ('D2', 'C#4', 'Bb3'; A4 = 440 Hz) or a number (returned as float)."""
+    if not isinstance(note, str):
+        return float(note)
+    s = note.strip()
+    pitch = _NOTE[s[0].upper()]
+    i = 1
+    while i < len(s) and s[i] in '#b!♯♭':
+        pitch += 1 if s[i] in '#♯' else -1
+        i += 1
+    octave = int(s[i:]) if i < len(s) else 0
+    midi = 12 * (octave + 1) + pitch
+    return 440.0 * 2.0 ** ((midi - 69) / 12.0)
+
+
+def hz_to_midi(f):
+    """librosa.hz_to_midi."""
+    import numpy as np
+    return 12 * (np.log2(np.asanyarray(f)) - np.log2(440.0)) + 69
 
 
 # transtacos/hparam.py:90-91 -- 30 iterations, angle form (no momentum)

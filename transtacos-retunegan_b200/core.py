@@ -240,6 +240,42 @@ def frame_stats(ys, frame_length: int, hop_length: int, want_rms=True, want_zcr=
     return rms, zcr, frames
 
 
+def yin(ys, sample_rate: int, fmin: float, fmax: float, frame_length: int, hop_length: int, trough_threshold: float = 0.1):
+    """librosa.yin on [L] / [B, L] / a list of utterances (one launch of ``yin_kernel``): (f0 float32 CUDA [sum frames], frames)."""
+    require_cuda()
+    if isinstance(ys, (list, tuple)):
+        parts = [to_device_f32(y).reshape(-1) for y in ys]
+        if not parts:
+            raise ValueError("empty batch")
+        lens = np.array([p.numel() for p in parts], np.int64)
+        x = torch.cat(parts)
+        frames = 1 + lens // hop_length
+        tbl = np.zeros((3, len(parts) + 1), np.int64)
+        tbl[0, 1:] = np.cumsum(lens)
+        tbl[1, :-1] = lens
+        tbl[2, 1:] = np.cumsum(frames)
+        tables = torch.from_numpy(tbl).to(x.device)
+        total = int(tbl[2, -1])
+        c = Batch(len(parts), 0, 0, tables[0].data_ptr(), tables[1].data_ptr(), tables[2].data_ptr(), None, total, 0)
+    else:
+        x = to_device_f32(ys)
+        if x.dim() == 1:
+            x = x.unsqueeze(0)
+        if x.dim() != 2 or x.shape[1] < 1:
+            raise ValueError(f"expected [L] or [B, L] samples, got shape {tuple(x.shape)}")
+        x = x.contiguous()
+        B, L = x.shape
+        frames = np.full(B, 1 + L // hop_length, np.int64)
+        total = int(frames.sum())
+        tables = None
+        c = Batch(B, L, L, None, None, None, None, 0, 0)
+    f0 = torch.empty(total, device=x.device, dtype=torch.float32)
+    check(_lib.load().sb200_yin(ptr(x), C.byref(c), int(sample_rate), float(fmin), float(fmax), int(frame_length),
+                                int(hop_length), float(trough_threshold), ptr(f0), stream_ptr()), "yin")
+    del tables
+    return f0, frames
+
+
 def trim_bounds(rms: torch.Tensor, frames, lens, hop_length: int, top_db: float):
     """librosa.effects.trim on a precomputed RMS track (ref = max, amin = 1e-10): [(start, end)] sample bounds per row."""
     out, o = [], 0

@@ -217,4 +217,132 @@ __global__ void __launch_bounds__(256) frame_stats_kernel(const FrameStatsArgs a
   }
 }
 
+// YIN fundamental-frequency track (librosa 0.8.1 yin; transtacos/audio.py:107-109 get_f0), one CTA per frame:
+//   frame of frame_length samples (centred, reflect padded), W = frame_length / 2
+//   acf[tau] = sum_{j=1..W} y[j] y[j+tau],  e[tau] = sum_{j=tau+1..tau+W} y[j]^2   (both zeroed where |.| < 1e-6, as librosa does)
+//   d[tau]   = e[0] + e[tau] - 2 acf[tau]                                             (difference function)
+//   d'[i]    = d[pmin+i] / (mean_{1..pmin+i} d + tiny),  i = 0..pmax-pmin             (cumulative mean normalised difference)
+//   trough   = local minimum of d' (librosa.util.localmax of -d'; first element: d'[0] < d'[1]) with d' < trough_threshold
+//   period   = pmin + first such i (else argmin d') + parabolic shift;  f0 = sr / period
+// FP32-bound: W (pmax+1) multiply-adds per frame (155 k at the reference settings) from shared memory.
+constexpr int kYinThreads = 320;
+constexpr int kYinMaxFrame = 4096;   // samples per frame the shared-memory layout supports
+struct YinArgs {
+  const float* x;
+  BatchDev bd;
+  int frame_length, hop, pmin, pmax;
+  float sr, threshold;
+  float* f0;            // [frames]
+  long long total_frames;
+};
+
+__global__ void __launch_bounds__(kYinThreads) yin_kernel(const YinArgs a) {
+  extern __shared__ float ysm[];                 // [frame_length] samples, then [pmax + 2] d, then [n] d'
+  const int FL = a.frame_length, W = FL / 2, n = a.pmax - a.pmin + 1;
+  float* d = ysm + FL;
+  float* dn = d + a.pmax + 2;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (long long f = blockIdx.x; f < a.total_frames; f += gridDim.x) {
+    long long base, L;
+    int t;
+    if (a.bd.frame_off == nullptr) {
+      const long long b = f / a.bd.frames_per_row;
+      base = b * a.bd.stride;
+      L = a.bd.len;
+      t = static_cast<int>(f - b * a.bd.frames_per_row);
+    } else {
+      int lo = 0, hi = a.bd.B;
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(a.bd.frame_off + mid) <= f) lo = mid; else hi = mid;
+      }
+      base = __ldg(a.bd.sig_off + lo);
+      L = __ldg(a.bd.sig_len + lo);
+      t = static_cast<int>(f - __ldg(a.bd.frame_off + lo));
+    }
+    const long long i0 = static_cast<long long>(t) * a.hop - FL / 2;
+    for (int m = tid; m < FL; m += kYinThreads) {
+      long long i = i0 + m;
+      i = i < 0 ? -i : i;
+      i = i >= L ? 2 * (L - 1) - i : i;
+      i = min(max(i, 0LL), L - 1);
+      ysm[m] = __ldg(a.x + base + i);
+    }
+    __syncthreads();
+    // difference function
+    for (int tau = tid; tau <= a.pmax; tau += kYinThreads) {
+      float acf = 0.f, e = 0.f;
+      const float* yt = ysm + tau;
+#pragma unroll 8
+      for (int j = 1; j <= W; ++j) {
+        const float v = yt[j];
+        acf = fmaf(ysm[j], v, acf);
+        e = fmaf(v, v, e);
+      }
+      if (fabsf(acf) < 1e-6f) acf = 0.f;
+      if (fabsf(e) < 1e-6f) e = 0.f;
+      d[tau] = e - 2.f * acf;      // + e[0] below
+    }
+    __syncthreads();
+    {
+      const float e0 = d[0] * -1.f;   // d[0] = e[0] - 2 acf[0] = -e[0] (acf[0] = e[0], same thresholding)
+      __syncthreads();
+      for (int tau = tid; tau <= a.pmax; tau += kYinThreads) d[tau] += e0;
+    }
+    __syncthreads();
+    // cumulative sums of d[1..pmax] (warp 0: per-lane runs + shuffle scan), then d'
+    if (warp == 0) {
+      const int per = (a.pmax + 31) / 32;
+      const int lo = 1 + lane * per, hi = min(a.pmax + 1, lo + per);
+      float run = 0.f;
+      for (int k = lo; k < hi; ++k) run += d[k];
+      float incl = run;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float v = __shfl_up_sync(kFullMask, incl, o);
+        if (lane >= o) incl += v;
+      }
+      float cs = incl - run;       // sum of d[1 .. lo-1]
+      for (int k = lo; k < hi; ++k) {
+        cs += d[k];
+        const int i = k - a.pmin;
+        if (i >= 0) dn[i] = d[k] / (cs / static_cast<float>(k) + 1.17549435e-38f);
+      }
+    }
+    __syncthreads();
+    // first trough below the threshold, else the global minimum (warp 0)
+    if (warp == 0) {
+      int first = 1 << 30, amin = 0;
+      float vmin = 3.4e38f;
+      for (int i = lane; i < n; i += 32) {
+        const float v = dn[i];
+        bool trough;
+        if (i == 0) trough = n > 1 && v < dn[1];
+        else if (i == n - 1) trough = v < dn[i - 1];
+        else trough = v < dn[i - 1] && v <= dn[i + 1];
+        if (trough && v < a.threshold) first = min(first, i);
+        if (v < vmin) { vmin = v; amin = i; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        first = min(first, __shfl_xor_sync(kFullMask, first, o));
+        const float ov = __shfl_xor_sync(kFullMask, vmin, o);
+        const int oi = __shfl_xor_sync(kFullMask, amin, o);
+        if (ov < vmin || (ov == vmin && oi < amin)) { vmin = ov; amin = oi; }
+      }
+      if (lane == 0) {
+        const int i = first < (1 << 30) ? first : amin;
+        float shift = 0.f;
+        if (i >= 1 && i <= n - 2) {
+          const float pa = (dn[i - 1] + dn[i + 1] - 2.f * dn[i]) * 0.5f, pb = (dn[i + 1] - dn[i - 1]) * 0.5f;
+          shift = -pb / (2.f * pa + 1.17549435e-38f);
+          if (fabsf(shift) > 1.f) shift = 0.f;
+        }
+        a.f0[f] = a.sr / (static_cast<float>(a.pmin + i) + shift);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace sb200

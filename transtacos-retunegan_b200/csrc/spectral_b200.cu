@@ -220,6 +220,40 @@ int sb200_frame_stats(const float* x, const sb200_batch* batch, int32_t frame_le
   return check_launch("frame_stats_kernel");
 }
 
+int sb200_yin(const float* x, const sb200_batch* batch, int32_t sample_rate, float fmin, float fmax, int32_t frame_length,
+              int32_t hop_length, float trough_threshold, float* f0, sb200_stream stream) {
+  if (!x || !f0) return fail(SB200_ERR_INVALID, "yin: null argument");
+  if (frame_length < 4 || frame_length > kYinMaxFrame || hop_length < 1 || sample_rate < 1)
+    return fail(SB200_ERR_INVALID, "yin: need 4 <= frame_length <= 4096, hop_length >= 1");
+  if (!(fmin > 0.f) || !(fmax > fmin)) return fail(SB200_ERR_INVALID, "yin: need 0 < fmin < fmax");
+  YinArgs a{};
+  if (int rc = make_batch_rows(batch, &a.bd)) return rc;
+  if (a.bd.sig_off) {
+    if (!batch->frame_off) return fail(SB200_ERR_INVALID, "yin: ragged batch needs frame_off for this hop_length");
+    a.bd.frame_off = reinterpret_cast<const long long*>(batch->frame_off);
+    a.total_frames = batch->total_frames;
+  } else {
+    a.bd.frames_per_row = 1 + a.bd.len / hop_length;
+    a.total_frames = a.bd.frames_per_row * a.bd.B;
+  }
+  if (a.total_frames < 1) return fail(SB200_ERR_INVALID, "yin: no frames");
+  const int win = frame_length / 2;
+  // librosa: min_period = max(floor(sr / fmax), 1); max_period = min(ceil(sr / fmin), frame_length - win_length - 1)
+  a.pmin = std::max(static_cast<int>(std::floor(static_cast<double>(sample_rate) / fmax)), 1);
+  a.pmax = std::min(static_cast<int>(std::ceil(static_cast<double>(sample_rate) / fmin)), frame_length - win - 1);
+  if (a.pmax < a.pmin + 2) return fail(SB200_ERR_INVALID, "yin: period range too small for this frame_length");
+  a.x = x;
+  a.frame_length = frame_length;
+  a.hop = hop_length;
+  a.sr = static_cast<float>(sample_rate);
+  a.threshold = trough_threshold;
+  a.f0 = f0;
+  const size_t smem = sizeof(float) * (frame_length + a.pmax + 2 + (a.pmax - a.pmin + 1));
+  const int grid = static_cast<int>(std::min<long long>(a.total_frames, 16LL * sm_count()));
+  yin_kernel<<<grid, kYinThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  return check_launch("yin_kernel");
+}
+
 int sb200_preemphasis(const float* x, const sb200_batch* batch, float k, float* y, sb200_stream stream) {
   if (!x || !y) return fail(SB200_ERR_INVALID, "preemphasis: null argument");
   BatchDev bd;

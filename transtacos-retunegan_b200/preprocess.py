@@ -7,7 +7,7 @@ Mirrors ``transtacos/preprocess.py:16-41`` (``write_metadata``) and ``transtacos
     A.load_wav -> A.trim_silence -> A.align_wav          scipy wav read -> ONE frame_stats launch per batch -> host slices
     A.get_specs(y[:-1])  (mag, mel)                      ONE fused STFT+mel launch per batch (core.stft_features, ragged)
     A.get_c0(y[:-1])                                     ONE frame_stats launch per batch
-    A.get_f0(y[:-1])     (librosa.yin)                   ``f0_fn`` hook (YIN is not on the spectral path)
+    A.get_f0(y[:-1])     (librosa.yin)                   ONE yin launch per batch (or a caller-supplied ``f0_fn``)
     np.save mel-/mag-/f0-/c0-{name}.npy                  same files, same shapes / dtypes / memory order (see ``save_features``)
 
 Files written (consumer contract: ``transtacos/data.py:153-161`` loads ``mel-{id}.npy`` / ``mag-{id}.npy`` and transposes them,
@@ -15,7 +15,7 @@ Files written (consumer contract: ``transtacos/data.py:153-161`` loads ``mel-{id
 
     mel-{name}.npy  [n_mel, T]  float64, Fortran order   (``_normalize(...)`` of an F-ordered librosa.stft result)
     mag-{name}.npy  [n_freq, T] float64, Fortran order
-    c0-{name}.npy   [T] float32;  f0-{name}.npy [T] float32 (only with ``f0_fn``)
+    c0-{name}.npy   [T] float32;  f0-{name}.npy [T] float32
     train.txt / test.txt  ``name|prds|text`` lines;  stats.txt ``key<TAB>value``;  wav_path.txt
 
 The features are computed in float32 on the GPU (1e-4 relative to the reference's float64, tests/test_gpu_parity.py) and
@@ -97,6 +97,10 @@ def make_metadata_batch(items: Sequence[Tuple[str, Tuple[str, str], np.ndarray]]
     sc = A.db_norm_scale(hp)
     mag, mel, _ = core.stft_features(plan, batch, preemph=hp.preemphasis, mag_scale=sc, mel_scale=sc)
     c0, _, _ = core.frame_stats(cuts, hp.win_length, hp.hop_length, want_zcr=False)
+    f0_h = None
+    if f0_fn is None:
+        from .config import note_to_hz
+        f0_h = core.yin(cuts, hp.sample_rate, note_to_hz(hp.rf0min), note_to_hz(hp.rf0max), hp.win_length, hp.hop_length)[0].cpu()
     mag_h, mel_h, c0_h = mag.cpu(), mel.cpu(), c0.cpu()   # one copy each for the batch
     o = 0
     for j, i in enumerate(keep):
@@ -104,7 +108,7 @@ def make_metadata_batch(items: Sequence[Tuple[str, Tuple[str, str], np.ndarray]]
         T = int(batch.frames[j])
         len_wav = len(ys[j])
         assert len_wav == T * hp.hop_length               # datasets/databaker.py:108
-        f0 = f0_fn(cuts[j]) if f0_fn is not None else None
+        f0 = f0_fn(cuts[j]) if f0_fn is not None else f0_h[o:o + T].numpy()
         stats = save_features(out_dp, name, mag_h[o:o + T], mel_h[o:o + T], c0_h[o:o + T], f0, dtype)
         o += T
         out[i] = (name, prds, text, len(text.split(' ')), len_wav, T, stats)

@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import core
-from .config import TRANSTACOS, SpectralConfig
+from .config import TRANSTACOS, SpectralConfig, hz_to_midi, note_to_hz
 
 hp: SpectralConfig = TRANSTACOS
 eps = 1e-5
@@ -82,6 +82,28 @@ def _frame_feature(y, frame_length, hop_length, which):
 def get_c0(y):
     """transtacos/audio.py:112-114: ``librosa.feature.rms(y, frame_length=win_length, hop_length=hop_length)[0]`` as float32."""
     return _frame_feature(y, hp.win_length, hp.hop_length, "rms")
+
+
+def get_f0(y):
+    """transtacos/audio.py:107-109: ``librosa.yin(y, fmin=rf0min, fmax=rf0max, frame_length=win_length, hop_length=hop_length)``
+    as float32 ([L] -> [T]; [B, L] -> [B, T]; list -> list)."""
+    as_np = _is_np(y) or (isinstance(y, (list, tuple)) and len(y) > 0 and _is_np(y[0]))
+    f0, frames = core.yin(y, hp.sample_rate, note_to_hz(hp.rf0min), note_to_hz(hp.rf0max), hp.win_length, hp.hop_length)
+    if isinstance(y, (list, tuple)):
+        parts = list(torch.split(f0, [int(t) for t in frames]))
+        return [p.cpu().numpy() for p in parts] if as_np else parts
+    f0 = f0.view(len(frames), int(frames[0]))
+    if (y.ndim if _is_np(y) else y.dim()) == 1:
+        f0 = f0[0]
+    return f0.cpu().numpy() if as_np else f0
+
+
+def quantilize_f0(f0):
+    """transtacos/audio.py:117-121: MIDI bins ``hz_to_midi(f) - floor(hz_to_midi(f0min))`` clipped to the bin range, int32."""
+    f0 = np.asarray(f0.detach().cpu() if isinstance(f0, torch.Tensor) else f0)
+    n_min = int(np.floor(hz_to_midi(hp.f0min)))
+    n_bins = int(np.ceil(hz_to_midi(hp.f0max))) - n_min + 1
+    return (hz_to_midi(f0) - n_min).clip(0, n_bins - 1).astype(np.int32)
 
 
 def quantilize_c0(c0):
