@@ -158,3 +158,34 @@ def test_f0_yin(sb):
     fb = sb.transtacos_audio.get_f0(torch.from_numpy(Y).cuda())
     assert fb.is_cuda and tuple(fb.shape) == (3, 32)
     np.testing.assert_array_equal(sb.transtacos_audio.quantilize_f0(ref), O.tt_quantilize_f0(ref))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("split_cv,ref_wav", [(False, 'y'), (True, 'y'), (False, 'dy')])
+def test_retunegan_dataset_tuples(sb, split_cv, ref_wav):
+    """retunegan/data.py:38-122 restated on the oracle vs retunegan_data.prepare_batch (one batch, five launches)."""
+    wavs = []
+    for i, T in enumerate([40, 57, 33]):
+        wavs.append(_wav(256 * T, 80 + i))
+    got = sb.retunegan_data.prepare_batch(wavs, split_cv=split_cv, ref_wav=ref_wav)
+    for w, g in zip(wavs, got):
+        mag = O.rtg_get_mag(w[:-1])
+        mel = O.rtg_mag_to_mel(mag)
+        tm = np.pad(O.rtg_inv_mag(mag, wavlen=len(w) - 1), (0, 1))
+        if ref_wav == 'dy':
+            tp = np.pad(tm, (0, 1))
+            tm = tp[1:] - tp[:-1]
+        assert g[0].shape == mel.shape and g[1] is not None and len(g[1]) == len(w)
+        assert np.linalg.norm(g[0] - mel) / np.linalg.norm(mel) < 1e-4
+        tg = g[2] if not split_cv else g[4] + g[5]
+        assert np.linalg.norm(tg - tm) / np.linalg.norm(tm) < 1e-3                 # Griffin-Lim tolerance (BASELINE.md)
+        if split_cv:
+            zcr, dyn = O.rtg_get_zcr(tm[:-1]), O.tt_get_c0(tm[:-1])
+            uv = O.rtg_get_uv(zcr, dyn)
+            uv_ex = np.repeat(uv, 256)
+            agree = (g[6] == uv_ex).mean()                                         # thresholds on a 1e-3-accurate wav
+            assert agree > 0.98, agree
+            u = g[6][::256]
+            mel_min = g[0].min()
+            np.testing.assert_allclose(g[2], (g[0] - mel_min) * u + mel_min, rtol=1e-6, atol=1e-6)
+            np.testing.assert_allclose(g[3], (g[0] - mel_min) * (1 - u) + mel_min, rtol=1e-6, atol=1e-6)

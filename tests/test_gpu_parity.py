@@ -387,3 +387,29 @@ def test_full_size_properties_config3(sb):
     # mel == banded projection of mag
     mel2 = sb.core.mel_project(plan, mag)
     assert (mel2 - mel).abs().max() <= 1e-5 * mel.abs().max()
+
+
+@pytest.mark.parametrize("n_fft,win,hop,window", [(2048, 1024, 240, "hann"), (2048, 1024, 256, "hamming"), (1024, 512, 128, "hann"),
+                                                   (1024, 512, 120, "blackman"), (512, 256, 64, "hann")])
+def test_feature_kernel_other_configurations(sb, n_fft, win, hop, window):
+    """Every instantiation of the packed feature kernels: the warp-specialised kernel without the shared-sample fast path
+    (hop != 256), the single-role kernel (n_fft 1024 / 512), other windows, magnitude-only and mel-only launches,
+    ragged batches with edge-only utterances."""
+    class hp(O.HP):
+        pass
+    hp.n_fft, hp.win_length, hp.hop_length, hp.n_freq, hp.window_fn = n_fft, win, hop, n_fft // 2 + 1, window
+    cfg = sb.RETUNEGAN.replace(n_fft=n_fft, win_length=win, hop_length=hop, n_freq=n_fft // 2 + 1, window_fn=window)
+    A = sb.retunegan_audio
+    old = A.hp
+    A.set_hparams(cfg)
+    try:
+        ys = [O.synth_speechlike(L, 300 + i) for i, L in enumerate([9000, 4 * hop + 3, n_fft + 17, 20011])]
+        for y in ys[:2]:
+            _close(np.exp(A.get_mag(y)), np.exp(O.rtg_get_mag(y, hp=hp)))        # magnitude-only launch
+            _close(np.exp(A.get_mel(y)), np.exp(O.rtg_get_mel(y, hp=hp)))        # mel-only launch
+        mags, mels = A.get_mag_mel(ys)                                           # ragged batch, both outputs
+        for y, mg, ml in zip(ys, mags, mels):
+            _close(np.exp(mg), np.exp(O.rtg_get_mag(y, hp=hp)))
+            _close(np.exp(ml), np.exp(O.rtg_get_mel(y, hp=hp)))
+    finally:
+        A.set_hparams(old)

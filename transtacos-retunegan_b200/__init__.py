@@ -11,7 +11,7 @@ The directory name contains a hyphen; import it as ``import transtacos_retunegan
 repository root) or ``importlib.import_module("transtacos-retunegan_b200")``.
 """
 from . import config, _lib, core, sharding            # noqa: F401
-from . import transtacos_audio, retunegan_audio, loss, preprocess  # noqa: F401
+from . import transtacos_audio, retunegan_audio, loss, preprocess, retunegan_data  # noqa: F401
 from .config import SpectralConfig, TRANSTACOS, RETUNEGAN, PI   # noqa: F401
 from .loss import multi_stft_loss                      # noqa: F401
 
