@@ -111,6 +111,11 @@ int sb200_stft_features(const sb200_plan* plan, const float* x, const sb200_batc
 int sb200_mel_project(const sb200_plan* plan, const float* in, int64_t frames, sb200_scale scale, float* out,
                       sb200_stream stream);
 
+/* _mel_to_linear (transtacos/audio.py:164-175): out[t, :] = linear_basis @ mel[t, :] with
+ * linear_basis = mel_basis^T diag(1 / colsum(mel_basis mel_basis^T)); the first step of inv_mel (:100-104).
+ * mel [frames, n_mel] -> out [frames, F], frame-major. */
+int sb200_mel_to_linear(const sb200_plan* plan, const float* mel, int64_t frames, float* out, sb200_stream stream);
+
 /* Element-wise helpers of the inverse path, fused into one launch each:
  *   mode 0: out = 10^((in + max_abs)*(-min_db)/(2*max_abs) + min_db + ref) / 20) ^ power
  *           (transtacos/audio.py:80-82 spec_to_natural_scale, then S ** gl_power at :96)

@@ -671,3 +671,25 @@ def tt_quantilize_f0(f0, f0min=73.25581359863281, f0max=595.9459228515625):
     n_bins = int(np.ceil(h2m(f0max))) - n_min + 1
     q = np.asarray([h2m(f) - n_min for f in f0])
     return q.clip(0, n_bins - 1).astype(np.int32)
+
+
+def linear_basis(hp=HP):
+    """transtacos/audio.py:167-175 _get_linear_basis: m^T diag(1 / colsum(m m^T)) (float32 basis, float64 result)."""
+    m = mel_basis(hp=hp)
+    m_T = np.transpose(m)
+    p = np.matmul(m, m_T)
+    d = [1.0 / x if np.abs(x) > 1.0e-8 else x for x in np.sum(p, axis=0)]
+    return np.matmul(m_T, np.diag(d))
+
+
+def tt_mel_to_linear(mel, hp=HP):
+    """transtacos/audio.py:164-165."""
+    return np.dot(linear_basis(hp), mel)
+
+
+def tt_inv_mel(mel, hp=HP, init_phase=None, n_iter=None):
+    """transtacos/audio.py:100-104."""
+    M = tt_spec_to_natural_scale(mel, hp)
+    S = tt_mel_to_linear(M, hp)
+    wav = tt_inv_preemphasis(tt_griffin_lim(S ** hp.tt_gl_power, hp, init_phase, n_iter), hp)
+    return wav.astype(np.float32)

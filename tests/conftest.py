@@ -33,3 +33,9 @@ def rel_fro(a, b):
 def max_rel(a, b):
     a, b = _f64(a), _f64(b)
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+@pytest.fixture(scope="session")
+def golden_side():
+    """Fixtures of the widened rows, produced by tests/golden/make_golden_side.py from the reference's own source."""
+    return dict(np.load(os.path.join(ROOT, "tests", "golden", "reference_vectors_side.npz")))

@@ -69,6 +69,27 @@ def test_oracle_yin_pins_and_pure_tones():
     assert q.tolist() == [0, 6, 32, 37] and q.dtype == np.int32
 
 
+def test_oracle_side_features_match_reference_source(golden_side):
+    """The audio.py layer of the widened rows, executed from the reference's own source (make_golden_side.py)."""
+    g = golden_side
+    y = g["y_speech"]
+    lb = O.linear_basis()
+    assert lb.shape == (1025, 80) and np.abs(lb - g["tt_linear_basis"]).max() <= 1e-12 * np.abs(g["tt_linear_basis"]).max()
+    M = O.tt_spec_to_natural_scale(g["tt_mel_norm_speech"])
+    np.testing.assert_allclose(O.tt_mel_to_linear(M), g["tt_mel_to_linear_speech"], rtol=1e-12, atol=1e-300)
+    w = O.tt_inv_mel(g["tt_mel_norm_speech"], init_phase=g["tt_inv_mel_phase"])
+    assert w.dtype == np.float32 and np.linalg.norm(w - g["tt_inv_mel_speech"]) <= 1e-6 * np.linalg.norm(g["tt_inv_mel_speech"])
+    np.testing.assert_array_equal(O.tt_get_c0(y), g["tt_get_c0_speech"])
+    np.testing.assert_array_equal(O.tt_get_f0(y), g["tt_get_f0_speech"])
+    np.testing.assert_array_equal(O.rtg_get_zcr(y), g["rtg_get_zcr_speech"])
+    np.testing.assert_array_equal(O.rtg_get_uv(g["rtg_get_zcr_speech"], g["rtg_get_c0_speech"]), g["rtg_get_uv_speech"])
+    np.testing.assert_array_equal(O.tt_quantilize_c0(g["tt_get_c0_speech"]), g["tt_quantilize_c0"])
+    np.testing.assert_array_equal(O.tt_quantilize_f0(g["tt_get_f0_speech"]), g["tt_quantilize_f0"])
+    assert g["tt_n_f0"].tolist() == [37, 39]
+    np.testing.assert_array_equal(O.tt_trim_silence(g["tt_trim_in"]), g["tt_trim_silence"])
+    assert 0 < len(g["tt_trim_silence"]) < len(g["tt_trim_in"]) and len(g["tt_align_wav"]) == 1024
+
+
 # ------------------------------------------------------------------------------------------------ GPU ----
 
 @pytest.fixture(scope="module")
@@ -189,3 +210,30 @@ def test_retunegan_dataset_tuples(sb, split_cv, ref_wav):
             mel_min = g[0].min()
             np.testing.assert_allclose(g[2], (g[0] - mel_min) * u + mel_min, rtol=1e-6, atol=1e-6)
             np.testing.assert_allclose(g[3], (g[0] - mel_min) * (1 - u) + mel_min, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_side_features_golden(sb, golden_side):
+    """The CUDA path against the fixtures generated from the reference's own source."""
+    g = golden_side
+    y = g["y_speech"]
+    TA, RA = sb.transtacos_audio, sb.retunegan_audio
+    np.testing.assert_allclose(TA.get_c0(y), g["tt_get_c0_speech"], rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(RA.get_c0(y), g["rtg_get_c0_speech"], rtol=1e-5, atol=1e-9)
+    np.testing.assert_array_equal(RA.get_zcr(y), g["rtg_get_zcr_speech"])
+    np.testing.assert_array_equal(RA.get_uv(g["rtg_get_zcr_speech"], g["rtg_get_c0_speech"]), g["rtg_get_uv_speech"])
+    f0 = TA.get_f0(y)
+    assert (np.abs(f0 / g["tt_get_f0_speech"] - 1) < 1e-4).mean() >= 0.99
+    np.testing.assert_array_equal(TA.quantilize_c0(g["tt_get_c0_speech"]), g["tt_quantilize_c0"])
+    np.testing.assert_array_equal(TA.quantilize_f0(g["tt_get_f0_speech"]), g["tt_quantilize_f0"])
+    np.testing.assert_array_equal(TA.trim_silence(g["tt_trim_in"]), g["tt_trim_silence"])
+    np.testing.assert_array_equal(TA.align_wav(y[:1000]), g["tt_align_wav"])
+    # inv_mel: pseudo-inverse basis product, then the Griffin-Lim path of inv_spec
+    M = O.tt_spec_to_natural_scale(g["tt_mel_norm_speech"])
+    S = TA._mel_to_linear(M.astype(np.float32))
+    ref = g["tt_mel_to_linear_speech"]
+    assert S.shape == ref.shape == (1025, 24)
+    assert np.linalg.norm(S - ref) / np.linalg.norm(ref) < 1e-5 and np.abs(S - ref).max() < 1e-5 * np.abs(ref).max()
+    w = TA.inv_mel(g["tt_mel_norm_speech"], init_phase=g["tt_inv_mel_phase"])
+    assert w.dtype == np.float32 and w.shape == g["tt_inv_mel_speech"].shape
+    assert np.linalg.norm(w - g["tt_inv_mel_speech"]) / np.linalg.norm(g["tt_inv_mel_speech"]) < 1e-3   # Griffin-Lim tolerance

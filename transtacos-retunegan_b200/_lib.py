@@ -44,6 +44,7 @@ SIGNATURES = {
     "sb200_plan_window_host": (C.c_int, [_P, _P]),
     "sb200_stft_features": (C.c_int, [_P, _P, C.POINTER(Batch), _F, Scale, Scale, _P, _P, _P, _P]),
     "sb200_mel_project": (C.c_int, [_P, _P, _I64, Scale, _P, _P]),
+    "sb200_mel_to_linear": (C.c_int, [_P, _P, _I64, _P, _P]),
     "sb200_spec_to_amplitude": (C.c_int, [_P, _I64, _I32, _F, _F, _F, _F, _P, _P]),
     "sb200_frame_stats": (C.c_int, [_P, C.POINTER(Batch), _I32, _I32, _P, _P, _P]),
     "sb200_yin": (C.c_int, [_P, C.POINTER(Batch), _I32, _F, _F, _I32, _I32, _F, _P, _P]),

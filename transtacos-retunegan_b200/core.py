@@ -173,6 +173,14 @@ def mel_project(plan: Plan, x_fm: torch.Tensor, scale: Optional[Scale] = None) -
     return out
 
 
+def mel_to_linear(plan: Plan, mel_fm: torch.Tensor) -> torch.Tensor:
+    """[frames, n_mel] -> [frames, F]: the reference's pseudo-inverse basis product (transtacos/audio.py:164-175)."""
+    mel_fm = mel_fm.contiguous()
+    out = torch.empty((mel_fm.shape[0], plan.F), device=mel_fm.device, dtype=torch.float32)
+    check(_lib.load().sb200_mel_to_linear(plan.handle, ptr(mel_fm), mel_fm.shape[0], ptr(out), stream_ptr()), "mel_to_linear")
+    return out
+
+
 def spec_to_amplitude(x: torch.Tensor, mode: int, p0=0.0, p1=0.0, p2=0.0, power=1.0) -> torch.Tensor:
     out = torch.empty_like(x)
     check(_lib.load().sb200_spec_to_amplitude(ptr(x), x.numel(), mode, float(p0), float(p1), float(p2), float(power),

@@ -35,6 +35,22 @@ __global__ void __launch_bounds__(kFeatWarps * 32) mel_project_kernel(const Plan
   }
 }
 
+// out[t, k] = sum_m lin[k, m] mel[t, m] with the <= 2 non-zeros of row k (transtacos/audio.py:164-165 _mel_to_linear).
+// HBM-bound: 4 (n_mel + F) bytes per frame; one thread per output element, consecutive bins per warp.
+__global__ void mel_to_linear_kernel(const PlanDev p, const float* __restrict__ mel, long long frames, float* __restrict__ out) {
+  const long long n = frames * p.F;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long t = i / p.F;
+    const int k = static_cast<int>(i - t * p.F);
+    const int r0 = __ldg(p.col_r0 + k);
+    const float* row = mel + t * p.n_mel;
+    float v = __ldg(p.lin_c0 + k) * __ldg(row + r0);
+    if (r0 + 1 < p.n_mel) v = fmaf(__ldg(p.lin_c1 + k), __ldg(row + r0 + 1), v);
+    out[i] = v;
+  }
+}
+
 // mode 0: 10^(((in + p0) * (-p1) / (2 p0) + p1 + p2) / 20) ^ power ; mode 1: exp(in) ^ power ; mode 2: in ^ power (in >= 0)
 __global__ void spec_to_amplitude_kernel(const float* __restrict__ in, long long n, int mode, float p0, float p1, float p2,
                                          float power, float* __restrict__ out) {

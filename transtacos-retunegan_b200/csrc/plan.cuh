@@ -47,6 +47,10 @@ struct PlanDev {
   const int* col_r0;      // [F]
   const float* col_c0;    // [F]
   const float* col_c1;    // [F]
+  // pseudo-inverse ("linear") basis of transtacos/audio.py:167-175: lin[k, m] = basis[m, k] * dinv[m] with
+  // dinv = 1 / column sums of basis basis^T; in the column view: lin[k, r0[k]] = lin_c0[k], lin[k, r0[k]+1] = lin_c1[k]
+  const float* lin_c0;    // [F]
+  const float* lin_c1;    // [F]
 };
 
 }  // namespace sb200
@@ -302,12 +306,30 @@ inline std::string build_plan(const sb200_config& c, sb200_plan* p, int* st) {
       c1[k] = (r0[k] + 1 < c.n_mel) ? mb[static_cast<size_t>(r0[k] + 1) * F + k] : 0.f;
     }
   }
+  // _get_linear_basis: p = m m^T (float32 like np.matmul on the float32 basis), d = 1 / column sums where |x| > 1e-8
+  std::vector<float> lc0(F, 0.f), lc1(F, 0.f);
+  {
+    std::vector<double> dinv(c.n_mel, 0.0);
+    for (int j = 0; j < c.n_mel; ++j) {
+      float colsum = 0.f;
+      for (int i = 0; i < c.n_mel; ++i) {
+        float pij = 0.f;
+        for (int k = 0; k < F; ++k) pij += mb[static_cast<size_t>(i) * F + k] * mb[static_cast<size_t>(j) * F + k];
+        colsum += pij;
+      }
+      dinv[j] = std::fabs(colsum) > 1.0e-8f ? 1.0 / static_cast<double>(colsum) : static_cast<double>(colsum);
+    }
+    for (int k = 0; k < F; ++k) {
+      lc0[k] = static_cast<float>(static_cast<double>(c0[k]) * dinv[r0[k]]);
+      lc1[k] = (r0[k] + 1 < c.n_mel) ? static_cast<float>(static_cast<double>(c1[k]) * dinv[r0[k] + 1]) : 0.f;
+    }
+  }
   *st = SB200_ERR_CUDA;
   cudaError_t e;
 #define SB200_UP(vec, field) \
   if ((e = upload(p, vec, &d.field)) != cudaSuccess) return std::string("cuda upload: ") + cudaGetErrorString(e);
   SB200_UP(wf, window) SB200_UP(wout, wout) SB200_UP(wnorm, wnorm) SB200_UP(wsq, wsq) SB200_UP(wedge, wedge) SB200_UP(tw, tw) SB200_UP(ws, ws) SB200_UP(sp2, sp2) SB200_UP(spn, spn)
-  SB200_UP(melw, melw) SB200_UP(slots, mel_lo) SB200_UP(r0, col_r0) SB200_UP(c0, col_c0) SB200_UP(c1, col_c1)
+  SB200_UP(melw, melw) SB200_UP(slots, mel_lo) SB200_UP(r0, col_r0) SB200_UP(c0, col_c0) SB200_UP(c1, col_c1) SB200_UP(lc0, lin_c0) SB200_UP(lc1, lin_c1)
 #undef SB200_UP
   *st = SB200_OK;
   return "";

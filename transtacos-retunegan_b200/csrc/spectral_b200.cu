@@ -172,6 +172,12 @@ int sb200_mel_project(const sb200_plan* plan, const float* in, int64_t frames, s
   return check_launch("mel_project_kernel");
 }
 
+int sb200_mel_to_linear(const sb200_plan* plan, const float* mel, int64_t frames, float* out, sb200_stream stream) {
+  if (!plan || !mel || !out || frames < 1) return fail(SB200_ERR_INVALID, "mel_to_linear: bad argument");
+  mel_to_linear_kernel<<<grid_for(frames * plan->dev.F, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(plan->dev, mel, frames, out);
+  return check_launch("mel_to_linear_kernel");
+}
+
 int sb200_spec_to_amplitude(const float* in, int64_t n, int32_t mode, float p0, float p1, float p2, float power,
                             float* out, sb200_stream stream) {
   if (!in || !out || n < 1 || mode < 0 || mode > 2) return fail(SB200_ERR_INVALID, "spec_to_amplitude: bad argument");

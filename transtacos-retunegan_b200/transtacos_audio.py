@@ -295,3 +295,22 @@ def inv_spec(spec, init_phase=None, n_iter=None):
     ph = phase_to_frame_major(init_phase, hp.n_freq, T, S.device)
     wav = griffin_lim_amplitude(S, T, ph, hp.gl_iters if n_iter is None else n_iter, 0.0, 0, None, hp.preemphasis, hp)
     return wav.cpu().numpy().astype(np.float32) if isinstance(spec, np.ndarray) else wav
+
+
+def _mel_to_linear(mel):
+    """transtacos/audio.py:164-165: ``np.dot(_get_linear_basis(), mel)``, [n_mel, T] -> [n_freq, T]."""
+    out = core.mel_to_linear(core.get_plan(hp), _to_frame_major(mel))
+    return out.cpu().numpy().T if isinstance(mel, np.ndarray) else out.t()
+
+
+def inv_mel(mel, init_phase=None, n_iter=None):
+    """transtacos/audio.py:100-104 -- denormalise, back to linear with the pseudo-inverse basis, S**gl_power, Griffin-Lim,
+    de-emphasis ("might have no use case" upstream; it shares every kernel with ``inv_spec``)."""
+    M, T = mel.shape
+    if M != hp.n_mel:
+        raise ValueError(f"expected {hp.n_mel} mel rows, got {M}")
+    x = core.spec_to_amplitude(_to_frame_major(mel), 0, hp.max_abs_value, hp.min_level_db, hp.ref_level_db, 1.0)
+    S = core.spec_to_amplitude(core.mel_to_linear(core.get_plan(hp), x), 2, power=hp.gl_power)
+    ph = phase_to_frame_major(init_phase, hp.n_freq, T, S.device)
+    wav = griffin_lim_amplitude(S, T, ph, hp.gl_iters if n_iter is None else n_iter, 0.0, 0, None, hp.preemphasis, hp)
+    return wav.cpu().numpy().astype(np.float32) if isinstance(mel, np.ndarray) else wav
