@@ -142,6 +142,16 @@ int sb200_frame_stats(const float* x, const sb200_batch* batch, int32_t frame_le
 int sb200_yin(const float* x, const sb200_batch* batch, int32_t sample_rate, float fmin, float fmax, int32_t frame_length,
               int32_t hop_length, float trough_threshold, float* f0, sb200_stream stream);
 
+/* ---- waveform max-pool losses (retunegan/models/loss.py:66-82) ---------------------------------------
+ * mode 0: envelope_loss = mean|MaxPool(y) - MaxPool(y_g)| + mean|MaxPool(-y) - MaxPool(-y_g)|
+ * mode 1: dynamic_loss  = mean||MaxPool(y) + MaxPool(-y)| - |MaxPool(y_g) + MaxPool(-y_g)||
+ * MaxPool = nn.MaxPool1d(pool_k) (stride pool_k, no padding; retunegan/hparam.py:90 envelope_pool_k = 160).
+ * y, y_g [B, T]; loss: device scalar; grad_yg [B, T] (may be NULL): d loss / d y_g for a unit upstream gradient.
+ * workspace: sb200_pool_loss_workspace_bytes() bytes. */
+int64_t sb200_pool_loss_workspace_bytes(void);
+int sb200_pool_loss(const float* y, const float* y_g, int32_t B, int64_t T, int32_t pool_k, int32_t mode, float* loss,
+                    float* grad_yg, void* workspace, sb200_stream stream);
+
 /* ---- pre-emphasis filters (transtacos/audio.py:64-70) ---------------------------------------------
  * preemphasis: y[n] = x[n] - k x[n-1];  inv_preemphasis: y[n] = x[n] + k y[n-1] (parallel scan). */
 int sb200_preemphasis(const float* x, const sb200_batch* batch, float k, float* y, sb200_stream stream);

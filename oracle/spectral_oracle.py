@@ -693,3 +693,46 @@ def tt_inv_mel(mel, hp=HP, init_phase=None, n_iter=None):
     S = tt_mel_to_linear(M, hp)
     wav = tt_inv_preemphasis(tt_griffin_lim(S ** hp.tt_gl_power, hp, init_phase, n_iter), hp)
     return wav.astype(np.float32)
+
+
+def _maxpool1d(x, k):
+    """nn.MaxPool1d(k) on [B, T]: stride k, no padding, floor -> ([B, T // k] values, first arg-max index inside each window)."""
+    B, T = x.shape
+    n = T // k
+    w = x[:, :n * k].reshape(B, n, k)
+    return w.max(axis=2), w.argmax(axis=2)
+
+
+def rtg_envelope_loss(y, y_g, k=160):
+    """retunegan/models/loss.py:66-72 on [B, T] float arrays."""
+    y, y_g = np.asarray(y, np.float64), np.asarray(y_g, np.float64)
+    return (np.mean(np.abs(_maxpool1d(y, k)[0] - _maxpool1d(y_g, k)[0])) +
+            np.mean(np.abs(_maxpool1d(-y, k)[0] - _maxpool1d(-y_g, k)[0])))
+
+
+def rtg_dynamic_loss(y, y_g, k=160):
+    """retunegan/models/loss.py:76-82."""
+    y, y_g = np.asarray(y, np.float64), np.asarray(y_g, np.float64)
+    dyn = np.abs(_maxpool1d(y, k)[0] + _maxpool1d(-y, k)[0])
+    dyn_g = np.abs(_maxpool1d(y_g, k)[0] + _maxpool1d(-y_g, k)[0])
+    return np.mean(np.abs(dyn - dyn_g))
+
+
+def rtg_pool_loss_backward(y, y_g, mode, k=160):
+    """d loss / d y_g of envelope_loss (mode 0) / dynamic_loss (mode 1) in closed form (what torch autograd returns:
+    max-pool gradients go to the first arg-max, abs has gradient sign(x))."""
+    y, y_g = np.asarray(y, np.float64), np.asarray(y_g, np.float64)
+    B, T = y_g.shape
+    hi, _ = _maxpool1d(y, k); lo, _ = _maxpool1d(-y, k)
+    hig, ih = _maxpool1d(y_g, k); log_, il = _maxpool1d(-y_g, k)
+    n = hi.size
+    g = np.zeros((B, T))
+    bi, wi = np.meshgrid(np.arange(B), np.arange(hi.shape[1]), indexing="ij")
+    if mode == 0:
+        np.add.at(g, (bi, wi * k + ih), -np.sign(hi - hig) / n)
+        np.add.at(g, (bi, wi * k + il), np.sign(lo - log_) / n)
+    else:
+        c = -np.sign(np.abs(hi + lo) - np.abs(hig + log_)) * np.sign(hig + log_) / n
+        np.add.at(g, (bi, wi * k + ih), c)
+        np.add.at(g, (bi, wi * k + il), -c)
+    return g

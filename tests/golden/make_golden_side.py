@@ -69,6 +69,27 @@ def main():
     out["rtg_get_c0_speech"] = RT.get_c0(y)
     out["rtg_get_uv_speech"] = RT.get_uv(out["rtg_get_zcr_speech"], out["rtg_get_c0_speech"])
 
+    # waveform max-pool losses (retunegan/models/loss.py:66-82) and their autograd gradients, torch CPU
+    import torch
+    sys.modules["audio"] = RT
+    sys.modules["hparam"] = RT.hp
+    UT = G._load("utils", f"{REF}/retunegan/utils.py", f"{REF}/retunegan")
+    sys.modules["utils"] = UT
+    LS = G._load("ref_rtg_loss_side", f"{REF}/retunegan/models/loss.py", f"{REF}/retunegan")
+    B, T = 3, 8192 + 77                                     # 77 trailing samples outside every window of 160
+    rs = np.random.RandomState(114514)
+    yy = np.stack([O.synth_speechlike(T, 114514 + b) for b in range(B)]).astype(np.float32)
+    yg = np.tanh(yy * 1.1 + 0.02 * rs.randn(B, T)).astype(np.float32)
+    yg[1, 320:480] = 0.25                                   # a constant window: arg-max == arg-min == first sample
+    out["pool_y"], out["pool_yg"] = yy, yg
+    for name, fn in (("envelope", LS.envelope_loss), ("dynamic", LS.dynamic_loss)):
+        ty = torch.from_numpy(yy).unsqueeze(1)
+        tg = torch.from_numpy(yg).unsqueeze(1).requires_grad_(True)
+        loss = fn(ty, tg)
+        (g,) = torch.autograd.grad(loss, tg)
+        out[f"pool_{name}_loss"] = np.asarray(loss.item())
+        out[f"pool_{name}_grad"] = g[:, 0].numpy()
+
     path = os.path.join(HERE, "reference_vectors_side.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, f"{os.path.getsize(path) / 1e6:.2f} MB,", len(out), "arrays")

@@ -90,6 +90,16 @@ def test_oracle_side_features_match_reference_source(golden_side):
     assert 0 < len(g["tt_trim_silence"]) < len(g["tt_trim_in"]) and len(g["tt_align_wav"]) == 1024
 
 
+def test_oracle_pool_losses_match_reference_source(golden_side):
+    g = golden_side
+    y, yg = g["pool_y"], g["pool_yg"]
+    assert abs(O.rtg_envelope_loss(y, yg) - g["pool_envelope_loss"]) < 1e-6 * abs(g["pool_envelope_loss"])
+    assert abs(O.rtg_dynamic_loss(y, yg) - g["pool_dynamic_loss"]) < 1e-6 * abs(g["pool_dynamic_loss"])
+    np.testing.assert_allclose(O.rtg_pool_loss_backward(y, yg, 0), g["pool_envelope_grad"], rtol=1e-6, atol=1e-12)
+    np.testing.assert_allclose(O.rtg_pool_loss_backward(y, yg, 1), g["pool_dynamic_grad"], rtol=1e-6, atol=1e-12)
+    assert np.count_nonzero(g["pool_envelope_grad"][:, -77:]) == 0
+
+
 # ------------------------------------------------------------------------------------------------ GPU ----
 
 @pytest.fixture(scope="module")
@@ -237,3 +247,22 @@ def test_side_features_golden(sb, golden_side):
     w = TA.inv_mel(g["tt_mel_norm_speech"], init_phase=g["tt_inv_mel_phase"])
     assert w.dtype == np.float32 and w.shape == g["tt_inv_mel_speech"].shape
     assert np.linalg.norm(w - g["tt_inv_mel_speech"]) / np.linalg.norm(g["tt_inv_mel_speech"]) < 1e-3   # Griffin-Lim tolerance
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,mode", [("envelope", 0), ("dynamic", 1)])
+def test_pool_losses_golden(sb, golden_side, name, mode):
+    """envelope_loss / dynamic_loss (retunegan/models/loss.py:66-82) value and autograd gradient vs the reference's torch code."""
+    g = golden_side
+    y = torch.from_numpy(g["pool_y"]).cuda().unsqueeze(1)
+    yg = torch.from_numpy(g["pool_yg"]).cuda().unsqueeze(1).requires_grad_(True)
+    fn = sb.envelope_loss if mode == 0 else sb.dynamic_loss
+    loss = fn(y, yg)
+    (3.0 * loss).backward()
+    ref = float(g[f"pool_{name}_loss"])
+    assert abs(loss.item() - ref) < 1e-5 * abs(ref)                      # loss value tolerance (BASELINE.md)
+    grad = yg.grad[:, 0].cpu().numpy() / 3.0
+    np.testing.assert_allclose(grad, g[f"pool_{name}_grad"], rtol=1e-5, atol=1e-10)   # same arg-max positions, same signs
+    assert fn(y, yg.detach()).requires_grad is False
+    with pytest.raises(RuntimeError):
+        fn(y[..., :100], yg[..., :100])

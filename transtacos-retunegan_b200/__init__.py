@@ -13,7 +13,7 @@ repository root) or ``importlib.import_module("transtacos-retunegan_b200")``.
 from . import config, _lib, core, sharding            # noqa: F401
 from . import transtacos_audio, retunegan_audio, loss, preprocess, retunegan_data  # noqa: F401
 from .config import SpectralConfig, TRANSTACOS, RETUNEGAN, PI   # noqa: F401
-from .loss import multi_stft_loss                      # noqa: F401
+from .loss import multi_stft_loss, envelope_loss, dynamic_loss   # noqa: F401
 
 # keithito-style aliases named in BASELINE.json's north_star
 spectrogram = lambda y: transtacos_audio.get_specs(y)[0]        # noqa: E731

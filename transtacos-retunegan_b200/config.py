@@ -45,6 +45,7 @@ class SpectralConfig:
     n_c0_bins: int = 32
     multi_stft_params: Tuple[Tuple[int, int, int], ...] = ((2048, 1024, 240), (1024, 512, 120), (512, 256, 60))
     phd_input: str = "stft"
+    envelope_pool_k: int = 160              # retunegan/hparam.py:90
 
     def __post_init__(self):
         if self.window_fn not in _WINDOWS:

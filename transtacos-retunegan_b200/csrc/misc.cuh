@@ -361,4 +361,97 @@ __global__ void __launch_bounds__(kYinThreads) yin_kernel(const YinArgs a) {
   }
 }
 
+// Waveform max-pool losses of RetuneGAN (retunegan/models/loss.py:66-82, MaxPool1d(envelope_pool_k = 160), stride = kernel):
+//   hi = max over the window, lo = max(-y) = -min;
+//   envelope = mean|hi - hi_g| + mean|lo - lo_g|;   dynamic = mean| |hi + lo| - |hi_g + lo_g| |
+// One warp per window; value AND the gradient w.r.t. y_g for a unit upstream gradient in the same pass (the gradient of a max
+// pool goes to the first arg-max, as in ATen).  Partial sums per warp, summed in a fixed order by pool_loss_finalize_kernel.
+// HBM-bound: 8 B per sample read, 4 B per sample of gradient written.
+struct PoolLossArgs {
+  const float* y;
+  const float* yg;
+  int B, k, mode;           // mode 0: envelope, 1: dynamic
+  long long T, n_win;       // samples per row, windows per row (T / k)
+  float* grad;              // [B, T], zero-filled by the kernel, or null
+  float* partials;          // [gridDim.x * warps per block]
+  float inv_n;              // 1 / (B * n_win)
+};
+
+__device__ __forceinline__ void warp_argmax(float& v, int& i) {   // larger value wins, ties -> lower index
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(kFullMask, v, o);
+    const int oi = __shfl_xor_sync(kFullMask, i, o);
+    if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+  }
+}
+
+__global__ void __launch_bounds__(256) pool_loss_kernel(const PoolLossArgs a) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nwarps = (gridDim.x * static_cast<long long>(blockDim.x)) >> 5;
+  const long long total = static_cast<long long>(a.B) * a.n_win;
+  float acc = 0.f;
+  for (long long w = warp; w < total; w += nwarps) {
+    const long long b = w / a.n_win, base = b * a.T + (w - b * a.n_win) * a.k;
+    float hi = -3.4e38f, nlo = -3.4e38f, hig = -3.4e38f, nlog = -3.4e38f;   // nlo = max(-y)
+    int ihig = 0, ilog = 0, d0 = 0, d1 = 0;
+    for (int m = lane; m < a.k; m += 32) {
+      const float v = __ldg(a.y + base + m), g = __ldg(a.yg + base + m);
+      if (v > hi) hi = v;
+      if (-v > nlo) nlo = -v;
+      if (g > hig) { hig = g; ihig = m; }
+      if (-g > nlog) { nlog = -g; ilog = m; }
+      if (a.grad) a.grad[base + m] = 0.f;
+    }
+    warp_argmax(hi, d0);
+    warp_argmax(nlo, d1);
+    warp_argmax(hig, ihig);
+    warp_argmax(nlog, ilog);
+    __syncwarp();
+    auto sgn = [](float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); };
+    if (a.mode == 0) {
+      const float e0 = hi - hig, e1 = nlo - nlog;
+      acc += fabsf(e0) + fabsf(e1);
+      if (a.grad && lane == 0) {
+        a.grad[base + ihig] += -sgn(e0) * a.inv_n;      // d|hi - hi_g| / d y_g[argmax]
+        a.grad[base + ilog] += sgn(e1) * a.inv_n;       // lo_g = -y_g[argmin]
+      }
+    } else {
+      const float dyn = fabsf(hi + nlo), dg = hig + nlog, e = dyn - fabsf(dg);
+      acc += fabsf(e);
+      if (a.grad && lane == 0) {
+        const float c = -sgn(e) * sgn(dg) * a.inv_n;    // d|dyn - |dg|| / d dg
+        a.grad[base + ihig] += c;
+        a.grad[base + ilog] += -c;
+      }
+    }
+  }
+  // the tail of every row (T % k samples) is outside every window: zero gradient
+  if (a.grad) {
+    const long long tail = a.T - a.n_win * a.k;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < tail * a.B;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+      const long long b = i / tail;
+      a.grad[b * a.T + a.n_win * a.k + (i - b * tail)] = 0.f;
+    }
+  }
+  if (lane == 0) a.partials[warp] = acc;    // every lane holds the same acc (the reductions broadcast)
+}
+
+__global__ void pool_loss_finalize_kernel(const float* __restrict__ partials, int n, float inv_n, float* __restrict__ loss) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += partials[i];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(kFullMask, s, d);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) t += red[w];
+    *loss = t * inv_n;
+  }
+}
+
 }  // namespace sb200

@@ -260,6 +260,33 @@ int sb200_yin(const float* x, const sb200_batch* batch, int32_t sample_rate, flo
   return check_launch("yin_kernel");
 }
 
+static int pool_loss_grid() { return 4 * sm_count(); }
+int64_t sb200_pool_loss_workspace_bytes(void) { return static_cast<int64_t>(pool_loss_grid()) * 8 * sizeof(float) + 256; }
+
+int sb200_pool_loss(const float* y, const float* y_g, int32_t B, int64_t T, int32_t pool_k, int32_t mode, float* loss,
+                    float* grad_yg, void* workspace, sb200_stream stream) {
+  if (!y || !y_g || !loss || !workspace) return fail(SB200_ERR_INVALID, "pool_loss: null argument");
+  if (B < 1 || pool_k < 1 || T < pool_k || (mode != 0 && mode != 1))
+    return fail(SB200_ERR_INVALID, "pool_loss: need B >= 1, 1 <= pool_k <= T, mode 0 or 1");
+  PoolLossArgs a{};
+  a.y = y;
+  a.yg = y_g;
+  a.B = B;
+  a.k = pool_k;
+  a.mode = mode;
+  a.T = T;
+  a.n_win = T / pool_k;
+  a.grad = grad_yg;
+  a.partials = static_cast<float*>(workspace);
+  a.inv_n = static_cast<float>(1.0 / (static_cast<double>(B) * a.n_win));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = static_cast<int>(std::min<long long>(pool_loss_grid(), (static_cast<long long>(B) * a.n_win + 7) / 8));
+  pool_loss_kernel<<<grid, 256, 0, st>>>(a);
+  if (int rc = check_launch("pool_loss_kernel")) return rc;
+  pool_loss_finalize_kernel<<<1, 256, 0, st>>>(a.partials, grid * 8, a.inv_n, loss);
+  return check_launch("pool_loss_finalize_kernel");
+}
+
 int sb200_preemphasis(const float* x, const sb200_batch* batch, float k, float* y, sb200_stream stream) {
   if (!x || !y) return fail(SB200_ERR_INVALID, "preemphasis: null argument");
   BatchDev bd;

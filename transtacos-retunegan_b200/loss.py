@@ -146,3 +146,48 @@ def multi_stft_loss(y, y_g, ret_loss=False, ret_specs=False, ddp_reduce=False):
     elif ret_loss:
         return loss
     return (stft_r, stft_g)
+
+
+class _PoolLossFn(torch.autograd.Function):
+    """Value and d/dy_g (for a unit upstream gradient) of a waveform max-pool loss in one launch; backward scales it."""
+
+    @staticmethod
+    def forward(ctx, y, y_g, mode: int, pool_k: int):
+        lib = _lib.load()
+        dev = core.require_cuda()
+        yc = y.detach().to(device=dev, dtype=torch.float32).contiguous()
+        gc = y_g.detach().to(device=dev, dtype=torch.float32).contiguous()
+        B, T = gc.shape
+        need_grad = ctx.needs_input_grad[1]
+        loss = torch.empty((), device=dev, dtype=torch.float32)
+        grad = torch.empty((B, T), device=dev, dtype=torch.float32) if need_grad else None
+        ws = core._workspace(int(lib.sb200_pool_loss_workspace_bytes()), dev, "pool_loss")
+        _lib.check(lib.sb200_pool_loss(core.ptr(yc), core.ptr(gc), B, T, int(pool_k), int(mode), core.ptr(loss), core.ptr(grad),
+                                       core.ptr(ws), core.stream_ptr()), "pool_loss")
+        ctx.in_shape, ctx.in_dtype = y_g.shape, y_g.dtype
+        if need_grad:
+            ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        (grad,) = ctx.saved_tensors
+        return None, (grad * g_loss).to(ctx.in_dtype).reshape(ctx.in_shape), None, None
+
+
+def _pool_loss(y, y_g, mode):
+    if y.shape != y_g.shape or y.dim() not in (2, 3) or (y.dim() == 3 and y.shape[1] != 1):
+        raise ValueError(f"expected matching [B, T] / [B, 1, T] inputs, got {tuple(y.shape)} and {tuple(y_g.shape)}")
+    if y.shape[-1] < hp.envelope_pool_k:
+        raise RuntimeError("max_pool1d: output size is too small")           # what nn.MaxPool1d raises
+    return _PoolLossFn.apply(y.reshape(y.shape[0], -1), y_g.reshape(y_g.shape[0], -1), mode, hp.envelope_pool_k)
+
+
+def envelope_loss(y, y_g):
+    """retunegan/models/loss.py:66-72: ``mean|MaxPool(y) - MaxPool(y_g)| + mean|MaxPool(-y) - MaxPool(-y_g)|``."""
+    return _pool_loss(y, y_g, 0)
+
+
+def dynamic_loss(y, y_g):
+    """retunegan/models/loss.py:76-82: ``mean||MaxPool(y) + MaxPool(-y)| - |MaxPool(y_g) + MaxPool(-y_g)||``."""
+    return _pool_loss(y, y_g, 1)
