@@ -270,7 +270,7 @@ def corpus_lengths(n=10000):
     return T, 256 * T - 1
 
 
-def make_corpus(sb, torch, rank, world, n_utt=10000, chunk=256):
+def make_corpus(sb, torch, rank, world, n_utt=10000, chunk=256, d2h=False):
     """BASELINE.json configs[4]: corpus-scale preprocessing, 10k synthetic utterances sharded over the ranks (length-
     balanced, no collective).  Per utterance, as retunegan/data.py:60-76 + transtacos get_specs: dB-normalised linear + mel
     features (A3) and the Griffin-Lim reference wav (R4: ln-magnitude -> exp -> ^1.2 -> 4 iterations, momentum 0.7).
@@ -292,20 +292,45 @@ def make_corpus(sb, torch, rank, world, n_utt=10000, chunk=256):
         ys = [(0.1 * torch.randn(int(l), device="cuda", generator=g)).clamp_(-0.999, 0.999) for l in Lc]
         chunks.append((sb.core.SignalBatch(plan, ys), sb.core.FramesBatch(plan, Tc, Lc, torch.device("cuda")), None))
     fmax = max(b.total_frames for b, _, _ in chunks)
-    mag = torch.empty((fmax, F), device="cuda")
-    mel = torch.empty((fmax, N_MEL), device="cuda")
+    lmax = max(int(b.x.numel()) for b, _, _ in chunks)
+    nbuf = 2 if d2h else 1
+    mags = [torch.empty((fmax, F), device="cuda") for _ in range(nbuf)]
+    mels = [torch.empty((fmax, N_MEL), device="cuda") for _ in range(nbuf)]
     lnm = torch.empty((fmax, F), device="cuda")
     phase = torch.rand((fmax, F), device="cuda", generator=g)      # throughput mode: device RNG, drawn once
+    if d2h:   # features and reference wavs leave the device chunk by chunk (double-buffered, copy stream, pinned host ring)
+        h_mag = [torch.empty((fmax, F), pin_memory=True) for _ in range(2)]
+        h_mel = [torch.empty((fmax, N_MEL), pin_memory=True) for _ in range(2)]
+        h_wav = [torch.empty(lmax, pin_memory=True) for _ in range(2)]
+        s_out = torch.cuda.Stream()
+        ev_done = [torch.cuda.Event() for _ in range(2)]
+        ev_used = [False, False]
 
     def step(i):
         out = None
-        for batch, Tc, Lc in chunks:
+        cur = torch.cuda.current_stream()
+        for ci, (batch, Tc, Lc) in enumerate(chunks):
             n = batch.total_frames
+            b = ci % nbuf
+            if d2h and ev_used[b]:
+                cur.wait_event(ev_done[b])          # the copy of the chunk that used this buffer pair has finished
+            mag, mel = mags[b], mels[b]
             sb._lib.check(lib.sb200_stft_features(plan.handle, sb.core.ptr(batch.x), C.byref(batch.c), float(ta.hp.preemphasis),
                                                   sc_db, sc_db, sb.core.ptr(mag), sb.core.ptr(mel), None, sb.core.stream_ptr()))
             sb._lib.check(lib.sb200_stft_features(plan.handle, sb.core.ptr(batch.x), C.byref(batch.c), 0.0,
                                                   sc_ln, sb.core.RAW, sb.core.ptr(lnm), None, None, sb.core.stream_ptr()))
             out, _ = ra.inv_mag_batch(lnm[:n], Tc, Lc, init_phase=phase[:n])
+            if d2h:
+                s_out.wait_stream(cur)
+                with torch.cuda.stream(s_out):
+                    h_mag[b][:n].copy_(mag[:n], non_blocking=True)
+                    h_mel[b][:n].copy_(mel[:n], non_blocking=True)
+                    h_wav[b][:out.numel()].copy_(out, non_blocking=True)
+                    out.record_stream(s_out)
+                    ev_done[b].record(s_out)
+                ev_used[b] = True
+        if d2h:
+            cur.wait_stream(s_out)
         return out
     w.step, w.e2e = step, None
     w.units = float(L.sum()) / SR
@@ -314,7 +339,9 @@ def make_corpus(sb, torch, rank, world, n_utt=10000, chunk=256):
     w.dominant = "gl2_kernel<2048,3> (4 per chunk) + stft_feature3_kernel (2 per chunk)"
     w.launches_dominant_per_step = 1
     w.note = (f"{len(mine)} of {n_utt} utterances on this rank ({nf} frames, {w.units / 3600:.2f} h), ragged chunks of {chunk}; "
-              "features + ln-magnitude + Griffin-Lim (4 it, m 0.7, device-drawn initial phase); outputs stay in HBM")
+              "features + ln-magnitude + Griffin-Lim (4 it, m 0.7, device-drawn initial phase); " +
+              ("features and wavs copied to pinned host memory chunk by chunk (copy stream, double-buffered)" if d2h
+               else "outputs stay in HBM"))
     w.check = lambda: torch.isfinite(step(0)).all().item()
     return w
 
@@ -422,7 +449,8 @@ def main():
               "griffinlim_tt": lambda: make_griffinlim(sb, torch, 1, "tt"),
               "griffinlim_batch": lambda: make_griffinlim(sb, torch, 64, "rtg"),
               "mstft": lambda: make_mstft(sb, torch), "mstft_specs": lambda: make_mstft(sb, torch, specs=True),
-              "corpus": lambda: make_corpus(sb, torch, rank, world)}
+              "corpus": lambda: make_corpus(sb, torch, rank, world),
+              "corpus_d2h": lambda: make_corpus(sb, torch, rank, world, d2h=True)}
     w = makers[a.workload]()
     assert w.check(), "workload produced non-finite output"
 
@@ -486,7 +514,8 @@ def main():
                            ("griffinlim_rtg_64x5s_4it", makers["griffinlim_batch"], 5),
                            ("mstft_fwd_bwd_16x22050_lossonly", makers["mstft"], 50),
                            ("mstft_fwd_bwd_16x22050_specs", makers["mstft_specs"], 20),
-                           ("corpus_10000utt_specs+griffinlim", makers["corpus"], 2)):
+                           ("corpus_10000utt_specs+griffinlim", makers["corpus"], 2),
+                           ("corpus_10000utt_specs+griffinlim_d2h", makers["corpus_d2h"], 2)):
             try:
                 ww = mk()
                 d, _ = time_steps(torch, ww.step, k, 3, lambda: None)
