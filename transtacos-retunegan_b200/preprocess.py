@@ -143,30 +143,32 @@ def filter_and_aggregate(metadata: List[tuple], sample_rate: int):
     return [mt[:3] for mt in metadata], stats
 
 
+def _prosody_marks(kanji: str) -> str:
+    """One digit per character: '0' inside a word, the ``#n`` level that follows a character replaces its '0'."""
+    marks: List[str] = []
+    for ch in kanji.replace('#', ''):
+        if not ch.isdigit():
+            marks.append('0')
+        elif marks:
+            marks[-1] = ch
+        else:
+            marks.append(ch)
+    return ''.join(marks)
+
+
 def parse_label_file(fp: str) -> Dict[str, Tuple[str, str]]:
-    """DataBaker ``000001-010000.txt`` -> {name: (pinyin, prosody digits)} (datasets/databaker.py:125-160)."""
-    r = {}
+    """DataBaker ``000001-010000.txt`` -> {name: (pinyin, prosody digits)}; same result as datasets/databaker.py:125-160.
+    The file alternates ``name<TAB>text with #n prosody marks`` and ``<TAB>pinyin`` lines; reading stops at the first blank
+    header line, punctuation carries no prosody slot."""
     with open(fp, encoding='utf-8') as fh:
-        while True:
-            name_kanji = fh.readline().strip()
-            if not name_kanji:
-                break
-            name, kanji = name_kanji.split('\t')
-            pinyin = fh.readline().strip().lower()
-            kanji = PUNCT_KANJI_REGEX.sub('', kanji)
-            prodosy = []
-            for k in kanji:
-                if k == '#':
-                    continue
-                if k.isdigit():
-                    if prodosy:
-                        prodosy[-1] = k
-                    else:
-                        prodosy.append(k)
-                else:
-                    prodosy.append('0')
-            r[name] = (pinyin, ''.join(prodosy))
-    return r
+        lines = [ln.strip() for ln in fh.read().split('\n')]
+    table: Dict[str, Tuple[str, str]] = {}
+    for head, pinyin in zip(lines[0::2], lines[1::2] + ['']):
+        if not head:
+            break
+        name, kanji = head.split('\t')
+        table[name] = (pinyin.lower(), _prosody_marks(PUNCT_KANJI_REGEX.sub('', kanji)))
+    return table
 
 
 def write_metadata(metadata: List[tuple], stats: dict, wav_path: str, base_dir: str, out_dir: str = 'preprocessed',
