@@ -139,6 +139,15 @@ __device__ __forceinline__ PC gl2_update(const PC& X, float sA, float sB, float2
   return o;
 }
 
+// exp(2 pi i u), u in [0, 1): MUFU sine / cosine on the reduced argument 2 pi (u - 1/2) in [-pi, pi) (absolute error 2^-21.4,
+// CUDA programming guide), negated.  The initial phase is a random draw; 5e-7 on it is far inside the Griffin-Lim tolerance,
+// and sincospif cost as many instructions per item as a transform.
+__device__ __forceinline__ void gl2_unit_phase(float u, float* s, float* c) {
+  const float th = 6.283185307179586f * (u - 0.5f);
+  *s = -__sinf(th);
+  *c = -__cosf(th);
+}
+
 // Input spectrum of bin kb of both frames in the engine's internal form (modes 0 / 1): i^kb X, conjugated on the b side.
 template <int MODE>
 __device__ __forceinline__ PC gl2_fetch(const Gl2Args& a, long long rowA, long long rowB, bool okA, bool okB, int kb, int rot,
@@ -150,13 +159,13 @@ __device__ __forceinline__ PC gl2_fetch(const Gl2Args& a, long long rowA, long l
   } else {
     if (okA) {
       float s, c;
-      sincospif(2.f * __ldg(a.init_phase + rowA + kb), &s, &c);
+      gl2_unit_phase(__ldg(a.init_phase + rowA + kb), &s, &c);
       const float mg = __ldg(a.S + rowA + kb);
       xa = make_float2(mg * c, mg * s);
     }
     if (okB) {
       float s, c;
-      sincospif(2.f * __ldg(a.init_phase + rowB + kb), &s, &c);
+      gl2_unit_phase(__ldg(a.init_phase + rowB + kb), &s, &c);
       const float mg = __ldg(a.S + rowB + kb);
       xb = make_float2(mg * c, mg * s);
     }
@@ -176,9 +185,9 @@ __device__ __forceinline__ PC gl2_fetch_v(float sA, float sB, float2 tA, float2 
   float2 xa = tA, xb = tB;
   if constexpr (MODE == 1) {
     float s, c;
-    sincospif(2.f * tA.x, &s, &c);
+    gl2_unit_phase(tA.x, &s, &c);
     xa = make_float2(sA * c, sA * s);
-    sincospif(2.f * tB.x, &s, &c);
+    gl2_unit_phase(tB.x, &s, &c);
     xb = make_float2(sB * c, sB * s);
   }
   xa = rot_i(xa, rot);
