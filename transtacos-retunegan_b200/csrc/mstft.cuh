@@ -103,22 +103,26 @@ __global__ void __launch_bounds__(kMstftWarps * 32, 2) mstft_fwd_kernel(const Pl
     const long long row0 = (static_cast<long long>(it.b) * 2 * a.Tf + it.t0) * C::kF;
     float2 v[32];
     float mr[kMaxMelRounds][C::kQ];
-    mstft_analyse<N>(p, sm, buf, v, a.y + it.sig_base, it.L, it.t0, it.T, lane, a.spec_r,
-                     a.phd_phase ? a.spec_g : nullptr, a.spec_r, row0, chs);
-    mel_project_smem<N>(p, sm.melw, sm.mel_lo, buf, lane, [&](int q, int rd, int m, float val) {
-      mr[rd][q] = val;
-      if (m < p.n_mel && it.t0 + q < it.T) a.mel_r[(it.frame_base + it.t0 + q) * p.n_mel + m] = val;
-    });
-    __syncwarp();
-    mstft_analyse<N>(p, sm, buf, v, a.yg + it.sig_base, it.L, it.t0, it.T, lane, a.phd_phase ? nullptr : a.spec_g,
-                     nullptr, a.spec_g, row0, chs);
-    mel_project_smem<N>(p, sm.melw, sm.mel_lo, buf, lane, [&](int q, int rd, int m, float val) {
-      if (a.want_loss && m < p.n_mel && it.t0 + q < it.T) {
-        const float r = mr[rd][q];
-        acc += fabsf(r - val) + fabsf(logf(r) - logf(val));
-      }
-    });
-    __syncwarp();
+    // real, then generated signal through ONE copy of the analysis code (rolled on purpose: every warp runs this body once, so
+    // the kernel's time is the instruction fetch of its straight-line code; profiles/r01_mstft_ncu_summary.md)
+#pragma unroll 1
+    for (int side = 0; side < 2; ++side) {
+      const float* x = side ? a.yg : a.y;
+      float* ch0 = side ? (a.phd_phase ? nullptr : a.spec_g) : a.spec_r;
+      float* ch0_alias = side ? nullptr : (a.phd_phase ? a.spec_g : nullptr);
+      float* ch1 = side ? a.spec_g : a.spec_r;
+      mstft_analyse<N>(p, sm, buf, v, x + it.sig_base, it.L, it.t0, it.T, lane, ch0, ch0_alias, ch1, row0, chs);
+      mel_project_smem<N>(p, sm.melw, sm.mel_lo, buf, lane, [&](int q, int rd, int m, float val) {
+        if (side == 0) {
+          mr[rd][q] = val;
+          if (m < p.n_mel && it.t0 + q < it.T) a.mel_r[(it.frame_base + it.t0 + q) * p.n_mel + m] = val;
+        } else if (a.want_loss && m < p.n_mel && it.t0 + q < it.T) {
+          const float r = mr[rd][q];
+          acc += fabsf(r - val) + fabsf(logf(r) - logf(val));
+        }
+      });
+      __syncwarp();
+    }
     }
   }
 #pragma unroll
@@ -193,63 +197,68 @@ __global__ void __launch_bounds__(kMstftWarps * 32, 2) mstft_bwd_kernel(const Pl
     if (it.t0 < it.T) {
     float2 v[32];
     float mr[kMaxMelRounds][C::kQ];
-    if constexpr (FUSED) {
-      mstft_analyse<N>(p, sm, buf, v, a.y + it.sig_base, it.L, it.t0, it.T, lane, nullptr, nullptr, nullptr, 0, 0);
-      mel_project_smem<N>(p, sm.melw, sm.mel_lo, buf, lane, [&](int q, int rd, int, float val) { mr[rd][q] = val; });
-      __syncwarp();
-    }
-    load_frames<N, false>(v, a.yg + it.sig_base, it.L, it.t0, it.T, p.hop, 0.f, sm.win, lane);
-    fft_forward<N>(v, buf, sm.tw, lane);
     float2 Xk[kPairs], Xm[kPairs], Xs[C::kQ];
-    static_for<0, C::kQ>([&](auto qc) {
-      constexpr int q = decltype(qc)::value;
-      float2* zq = buf + q * C::kZS;
-      static_for<0, C::kPairIters>([&](auto ic) {
-        constexpr int i = decltype(ic)::value;
-        const int k = lane + 32 * i;
-        const int km = (C::kNz - k) & (C::kNz - 1);
-        float2 Ak, Am;
-        split_fwd(zq[k], zq[km], sm.ws[k], Ak, Am);
-        const float2 xk = rot_fwd(Ak, rk), xm = rot_fwd(Am, rm);
-        Xk[q * C::kPairIters + i] = xk;
-        Xm[q * C::kPairIters + i] = xm;
-        const float rek = xk.x + 1e-9f, rem = xm.x + 1e-9f;
-        zq[k].x = sqrtf(fmaf(rek, rek, xk.y * xk.y));
-        if (k != 0) zq[km].x = sqrtf(fmaf(rem, rem, xm.y * xm.y));
-      });
-      {
-        constexpr int k = C::kNz / 2;
-        float2 Ak, Am;
-        split_fwd(zq[k], zq[k], sm.ws[k], Ak, Am);
-        Xs[q] = rot_fwd(Ak, k);
-        if (lane == 0) {
-          const float rek = Xs[q].x + 1e-9f;
-          zq[k].x = sqrtf(fmaf(rek, rek, Xs[q].y * Xs[q].y));
-        }
-      }
-    });
-    __syncwarp();
-    // mel of the generated signal -> gradient of the loss w.r.t. each mel row
     float gm[kMaxMelRounds][C::kQ];
 #pragma unroll
     for (int rd = 0; rd < kMaxMelRounds; ++rd)
 #pragma unroll
       for (int q = 0; q < C::kQ; ++q) gm[rd][q] = 0.f;
-    mel_project_smem<N>(p, sm.melw, sm.mel_lo, buf, lane, [&](int q, int rd, int m, float mg) {
-      float g = 0.f;
-      if (gl != 0.f && m < p.n_mel && it.t0 + q < it.T) {
-        float r;
-        if constexpr (FUSED) {
-          r = mr[rd][q];
-          loss_acc += fabsf(r - mg) + fabsf(logf(r) - logf(mg));
-        } else {
-          r = __ldg(a.mel_r + (it.frame_base + it.t0 + q) * p.n_mel + m);
+    // FUSED: the real signal (side 0: only its mel rows are kept), then the generated one (side 1) through ONE copy of the
+    // analysis code -- rolled on purpose, see mstft_fwd_kernel.  Not fused: side 1 only.
+#pragma unroll 1
+    for (int side = FUSED ? 0 : 1; side < 2; ++side) {
+      load_frames<N, false>(v, (side ? a.yg : a.y) + it.sig_base, it.L, it.t0, it.T, p.hop, 0.f, sm.win, lane);
+      fft_forward<N>(v, buf, sm.tw, lane);
+      static_for<0, C::kQ>([&](auto qc) {
+        constexpr int q = decltype(qc)::value;
+        float2* zq = buf + q * C::kZS;
+        static_for<0, C::kPairIters>([&](auto ic) {
+          constexpr int i = decltype(ic)::value;
+          const int k = lane + 32 * i;
+          const int km = (C::kNz - k) & (C::kNz - 1);
+          float2 Ak, Am;
+          split_fwd(zq[k], zq[km], sm.ws[k], Ak, Am);
+          const float2 xk = rot_fwd(Ak, rk), xm = rot_fwd(Am, rm);
+          Xk[q * C::kPairIters + i] = xk;
+          Xm[q * C::kPairIters + i] = xm;
+          const float rek = xk.x + 1e-9f, rem = xm.x + 1e-9f;
+          zq[k].x = sqrtf(fmaf(rek, rek, xk.y * xk.y));
+          if (k != 0) zq[km].x = sqrtf(fmaf(rem, rem, xm.y * xm.y));
+        });
+        {
+          constexpr int k = C::kNz / 2;
+          float2 Ak, Am;
+          split_fwd(zq[k], zq[k], sm.ws[k], Ak, Am);
+          Xs[q] = rot_fwd(Ak, k);
+          if (lane == 0) {
+            const float rek = Xs[q].x + 1e-9f;
+            zq[k].x = sqrtf(fmaf(rek, rek, Xs[q].y * Xs[q].y));
+          }
         }
-        const float sgn = (mg > r) ? 1.f : ((mg < r) ? -1.f : 0.f);
-        g = gl * (sgn + sgn / mg);
-      }
-      gm[rd][q] = g;
-    });
+      });
+      __syncwarp();
+      // side 0: mel of the real signal; side 1: mel of the generated signal -> gradient of the loss w.r.t. each mel row
+      mel_project_smem<N>(p, sm.melw, sm.mel_lo, buf, lane, [&](int q, int rd, int m, float mg) {
+        if (side == 0) {
+          mr[rd][q] = mg;
+        } else {
+          float g = 0.f;
+          if (gl != 0.f && m < p.n_mel && it.t0 + q < it.T) {
+            float r;
+            if constexpr (FUSED) {
+              r = mr[rd][q];
+              loss_acc += fabsf(r - mg) + fabsf(logf(r) - logf(mg));
+            } else {
+              r = __ldg(a.mel_r + (it.frame_base + it.t0 + q) * p.n_mel + m);
+            }
+            const float sgn = (mg > r) ? 1.f : ((mg < r) ? -1.f : 0.f);
+            g = gl * (sgn + sgn / mg);
+          }
+          gm[rd][q] = g;
+        }
+      });
+      if (side == 0) __syncwarp();
+    }
     __syncwarp();   // all S reads done; reuse the buffer for the mel-row gradients
 #pragma unroll
     for (int rd = 0; rd < kMaxMelRounds; ++rd)
