@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(kMstftWarps * 32, 2) mstft_fwd_kernel(const Pl
     float2 v[32];
     float mr[kMaxMelRounds][C::kQ];
     // real, then generated signal through ONE copy of the analysis code (rolled on purpose: every warp runs this body once, so
-    // the kernel's time is the instruction fetch of its straight-line code; profiles/r01_mstft_ncu_summary.md)
+    // the kernel's time is the instruction fetch of its straight-line code; profiles/r01_mstft_gl2_ncu_summary.md)
 #pragma unroll 1
     for (int side = 0; side < 2; ++side) {
       const float* x = side ? a.yg : a.y;
