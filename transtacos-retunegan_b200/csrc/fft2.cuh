@@ -219,17 +219,17 @@ __device__ __forceinline__ void fft2_forward(PC (&v)[32], uint4* __restrict__ xb
   // written after a store is never hoisted above it and would cost one shared-memory round trip per column.
   const unsigned wrow = smem_u32(xbuf) + 8 * C::xoff(lane);
   constexpr int kTwBatch = 8;
-  float2 wcur[kTwBatch], wnext[kTwBatch];
+  float2 wb[2][kTwBatch];   // batch b lives in wb[b & 1] (compile-time index: no copies between batches)
   static_for<0, kTwBatch>([&](auto jc) {
     constexpr int j = decltype(jc)::value;
-    if constexpr (j >= 1 && j < C::kR2) wcur[j] = tw[(j - 1) * 32 + lane];
+    if constexpr (j >= 1 && j < C::kR2) wb[0][j] = tw[(j - 1) * 32 + lane];
   });
   static_for<0, (C::kR2 + kTwBatch - 1) / kTwBatch>([&](auto bc) {
     constexpr int b = decltype(bc)::value;
     static_for<0, kTwBatch>([&](auto jc) {
       constexpr int j = decltype(jc)::value;
       constexpr int k1n = (b + 1) * kTwBatch + j;
-      if constexpr (k1n < C::kR2) wnext[j] = tw[(k1n - 1) * 32 + lane];
+      if constexpr (k1n < C::kR2) wb[(b + 1) & 1][j] = tw[(k1n - 1) * 32 + lane];
     });
     static_for<0, kTwBatch>([&](auto jc) {
       constexpr int j = decltype(jc)::value;
@@ -241,7 +241,7 @@ __device__ __forceinline__ void fft2_forward(PC (&v)[32], uint4* __restrict__ xb
           sts_pf<C::kPlane + 8 * (p * C::kR2)>(wrow, v[p * C::kR2].im);
         });
       } else if constexpr (k1 < C::kR2) {
-        const float2 w = wcur[j];
+        const float2 w = wb[b & 1][j];
         static_for<0, C::kP>([&](auto pc_) {
           constexpr int p = decltype(pc_)::value;
           const PC& y = v[p * C::kR2 + k1];
@@ -251,10 +251,6 @@ __device__ __forceinline__ void fft2_forward(PC (&v)[32], uint4* __restrict__ xb
           sts_pf<C::kPlane + 8 * (p * C::kR2 + k1)>(wrow, im);
         });
       }
-    });
-    static_for<0, kTwBatch>([&](auto jc) {
-      constexpr int j = decltype(jc)::value;
-      wcur[j] = wnext[j];
     });
   });
   __syncwarp();
