@@ -240,8 +240,12 @@ __global__ void __launch_bounds__(256) frame_stats_kernel(const FrameStatsArgs a
 //   d'[i]    = d[pmin+i] / (mean_{1..pmin+i} d + tiny),  i = 0..pmax-pmin             (cumulative mean normalised difference)
 //   trough   = local minimum of d' (librosa.util.localmax of -d'; first element: d'[0] < d'[1]) with d' < trough_threshold
 //   period   = pmin + first such i (else argmin d') + parabolic shift;  f0 = sr / period
-// FP32-bound: W (pmax+1) multiply-adds per frame (155 k at the reference settings) from shared memory.
-constexpr int kYinThreads = 320;
+// FP32-bound: W (pmax+1) multiply-adds per frame (155 k at the reference settings) from shared memory.  A thread owns FOUR
+// consecutive lags and walks j four samples at a time: the 7 samples y[j+tau0 .. j+tau0+6] slide through registers, so a trip costs
+// one 16-byte broadcast load of y[j..j+3] plus four 4-byte loads for 16 multiply-adds.  The frame is kept twice: in natural
+// order (broadcast side) and de-interleaved by 4 (plane c holds y[4i+c]: the lane-strided side is then consecutive across the
+// threads, conflict free).  The energy terms come from a prefix sum of y^2 (as librosa's cumsum does).
+constexpr int kYinThreads = 128;
 constexpr int kYinMaxFrame = 4096;   // samples per frame the shared-memory layout supports
 struct YinArgs {
   const float* x;
@@ -252,11 +256,21 @@ struct YinArgs {
   long long total_frames;
 };
 
+__host__ __device__ inline int yin_plane_len(int frame_length) { return frame_length / 4 + 4; }
+__host__ __device__ inline size_t yin_smem_floats(int frame_length, int pmax, int pmin) {
+  // ynat [FL + 4] | planes [4][FL/4 + 4] | cs [FL + 1 (+3 pad)] | d [pmax + 2 (+ pad)] | dn [n]
+  return static_cast<size_t>(frame_length + 4) + 4 * yin_plane_len(frame_length) + (frame_length + 4) + (pmax + 8) + (pmax - pmin + 1);
+}
+
 __global__ void __launch_bounds__(kYinThreads) yin_kernel(const YinArgs a) {
-  extern __shared__ float ysm[];                 // [frame_length] samples, then [pmax + 2] d, then [n] d'
-  const int FL = a.frame_length, W = FL / 2, n = a.pmax - a.pmin + 1;
-  float* d = ysm + FL;
-  float* dn = d + a.pmax + 2;
+  extern __shared__ __align__(16) float ysm[];
+  const int FL = a.frame_length, W = FL / 2, n = a.pmax - a.pmin + 1, PL = yin_plane_len(FL);
+  float* ynat = ysm;                     // ynat[i] = y[i + 1]: y[j0 .. j0+3] with j0 = 1 (mod 4) is one aligned 16-byte load
+  float* yp = ynat + FL + 4;             // yp[c * PL + i] = y[4 i + c]
+  float* cs = yp + 4 * PL;               // cs[i] = sum_{j=1..i} y[j]^2
+  float* d = cs + FL + 4;
+  float* dn = d + a.pmax + 8;
+  __shared__ float s_warp[kYinThreads / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (long long f = blockIdx.x; f < a.total_frames; f += gridDim.x) {
     long long base, L;
@@ -277,33 +291,74 @@ __global__ void __launch_bounds__(kYinThreads) yin_kernel(const YinArgs a) {
       t = static_cast<int>(f - __ldg(a.bd.frame_off + lo));
     }
     const long long i0 = static_cast<long long>(t) * a.hop - FL / 2;
-    for (int m = tid; m < FL; m += kYinThreads) {
-      long long i = i0 + m;
-      i = i < 0 ? -i : i;
-      i = i >= L ? 2 * (L - 1) - i : i;
-      i = min(max(i, 0LL), L - 1);
-      ysm[m] = __ldg(a.x + base + i);
-    }
-    __syncthreads();
-    // difference function
-    for (int tau = tid; tau <= a.pmax; tau += kYinThreads) {
-      float acf = 0.f, e = 0.f;
-      const float* yt = ysm + tau;
-#pragma unroll 8
-      for (int j = 1; j <= W; ++j) {
-        const float v = yt[j];
-        acf = fmaf(ysm[j], v, acf);
-        e = fmaf(v, v, e);
+    for (int m = tid; m < FL + 4; m += kYinThreads) {   // 4 zero samples of padding behind the frame
+      float v = 0.f;
+      if (m < FL) {
+        long long i = i0 + m;
+        i = i < 0 ? -i : i;
+        i = i >= L ? 2 * (L - 1) - i : i;
+        i = min(max(i, 0LL), L - 1);
+        v = __ldg(a.x + base + i);
       }
-      if (fabsf(acf) < 1e-6f) acf = 0.f;
-      if (fabsf(e) < 1e-6f) e = 0.f;
-      d[tau] = e - 2.f * acf;      // + e[0] below
+      if (m >= 1) ynat[m - 1] = v;
+      yp[(m & 3) * PL + (m >> 2)] = v;
+    }
+    if (tid == 0) ynat[FL + 3] = 0.f;
+    __syncthreads();
+    // prefix sums of y[j]^2, j = 1..FL-1: per-thread runs, block scan of the run totals
+    {
+      const int per = (FL + kYinThreads - 1) / kYinThreads;
+      const int lo = 1 + tid * per, hi = min(FL, lo + per);
+      float run = 0.f;
+      for (int j = lo; j < hi; ++j) run = fmaf(ynat[j - 1], ynat[j - 1], run);
+      float incl = run;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float v = __shfl_up_sync(kFullMask, incl, o);
+        if (lane >= o) incl += v;
+      }
+      if (lane == 31) s_warp[warp] = incl;
+      __syncthreads();
+      float off = 0.f;
+      for (int w = 0; w < warp; ++w) off += s_warp[w];
+      float c = off + incl - run;
+      if (tid == 0) cs[0] = 0.f;
+      for (int j = lo; j < hi; ++j) {
+        c = fmaf(ynat[j - 1], ynat[j - 1], c);
+        cs[j] = c;
+      }
     }
     __syncthreads();
+    // difference function, four lags per thread
     {
-      const float e0 = d[0] * -1.f;   // d[0] = e[0] - 2 acf[0] = -e[0] (acf[0] = e[0], same thresholding)
-      __syncthreads();
-      for (int tau = tid; tau <= a.pmax; tau += kYinThreads) d[tau] += e0;
+      float e0 = cs[W] - cs[0];
+      if (fabsf(e0) < 1e-6f) e0 = 0.f;
+      const float4* ynat4 = reinterpret_cast<const float4*>(ynat);
+      for (int g = tid; 4 * g <= a.pmax; g += kYinThreads) {
+        float acf[4] = {0.f, 0.f, 0.f, 0.f};
+        float w0 = yp[1 * PL + g], w1 = yp[2 * PL + g], w2 = yp[3 * PL + g];   // y[tau0+1], y[tau0+2], y[tau0+3], tau0 = 4 g
+        const float* q0 = yp + g + 1;
+#pragma unroll 2
+        for (int m = 0; m < W / 4; ++m) {                 // j0 = 1 + 4 m
+          const float4 yj = ynat4[m];                     // y[j0 .. j0+3]
+          const float n0 = q0[m], n1 = q0[PL + m], n2 = q0[2 * PL + m], n3 = q0[3 * PL + m];   // y[j0+tau0+3 .. +6]
+          acf[0] = fmaf(yj.x, w0, acf[0]); acf[1] = fmaf(yj.x, w1, acf[1]); acf[2] = fmaf(yj.x, w2, acf[2]); acf[3] = fmaf(yj.x, n0, acf[3]);
+          acf[0] = fmaf(yj.y, w1, acf[0]); acf[1] = fmaf(yj.y, w2, acf[1]); acf[2] = fmaf(yj.y, n0, acf[2]); acf[3] = fmaf(yj.y, n1, acf[3]);
+          acf[0] = fmaf(yj.z, w2, acf[0]); acf[1] = fmaf(yj.z, n0, acf[1]); acf[2] = fmaf(yj.z, n1, acf[2]); acf[3] = fmaf(yj.z, n2, acf[3]);
+          acf[0] = fmaf(yj.w, n0, acf[0]); acf[1] = fmaf(yj.w, n1, acf[1]); acf[2] = fmaf(yj.w, n2, acf[2]); acf[3] = fmaf(yj.w, n3, acf[3]);
+          w0 = n1; w1 = n2; w2 = n3;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int tau = 4 * g + q;
+          if (tau <= a.pmax) {
+            float ac = acf[q], e = cs[tau + W] - cs[tau];
+            if (fabsf(ac) < 1e-6f) ac = 0.f;
+            if (fabsf(e) < 1e-6f) e = 0.f;
+            d[tau] = e0 + e - 2.f * ac;
+          }
+        }
+      }
     }
     __syncthreads();
     // cumulative sums of d[1..pmax] (warp 0: per-lane runs + shuffle scan), then d'

@@ -254,7 +254,8 @@ int sb200_yin(const float* x, const sb200_batch* batch, int32_t sample_rate, flo
   a.sr = static_cast<float>(sample_rate);
   a.threshold = trough_threshold;
   a.f0 = f0;
-  const size_t smem = sizeof(float) * (frame_length + a.pmax + 2 + (a.pmax - a.pmin + 1));
+  const size_t smem = sizeof(float) * yin_smem_floats(frame_length, a.pmax, a.pmin);
+  if (frame_length % 8) return fail(SB200_ERR_INVALID, "yin: frame_length must be a multiple of 8");
   const int grid = static_cast<int>(std::min<long long>(a.total_frames, 16LL * sm_count()));
   yin_kernel<<<grid, kYinThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
   return check_launch("yin_kernel");
