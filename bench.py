@@ -529,8 +529,8 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not a.kernel_only:
-        # bounded sample: ~30 utterances per core (10-30 CPU-seconds of the reference path in all)
-        n_utt = {"stft_mel": max(32 * cores, 64), "griffinlim": max(4 * cores, 16), "mstft": 64}[cpu_kind]
+        # bounded sample: 64 utterances per core (10-30 CPU-seconds of the reference path in all)
+        n_utt = {"stft_mel": max(64 * cores, 64), "griffinlim": max(4 * cores, 16), "mstft": 64}[cpu_kind]
         v, dt = cpu_reference_rate(cpu_kind, n_utt, L5, cores)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": f"{n_utt} x 5 s utterances, oracle restatement of the reference path, {cores} processes, {dt:.1f} s"}
