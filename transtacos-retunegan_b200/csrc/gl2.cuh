@@ -198,14 +198,20 @@ __device__ __forceinline__ PC gl2_fetch_v(float sA, float sB, float2 tA, float2 
   return r;
 }
 
-template <int N, int MODE>
-__global__ void __launch_bounds__(kGl2Warps * 32, 1) gl2_kernel(const PlanDev p, const Gl2Args a) {
+// Signal loads: read-only path when the buffers were written by an earlier LAUNCH; L2 (coherent across SMs after a grid
+// barrier) when they were written earlier in the SAME launch (persistent kernel below).
+template <bool COH, class T>
+__device__ __forceinline__ T gl2_ldsig(const T* ptr) {
+  if constexpr (COH) return __ldcg(ptr);
+  else return __ldg(ptr);
+}
+
+// One pass over all tiles (see the file header).  COH: the signal buffers may have been written earlier in this launch.
+template <int N, int MODE, bool COH>
+__device__ __forceinline__ void gl2_pass(const PlanDev& p, const Gl2Args& a, Gl2Smem<N>& sm) {
   using C = Fft2Cfg<N>;
   constexpr int FT = kGl2GroupWarps * C::kFrames;   // frames per tile
   constexpr int GT = kGl2GroupWarps * 32;           // threads per group
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  Gl2Smem<N> sm;
-  sm.init(smem_raw, p);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int group = warp / kGl2GroupWarps, wg = warp % kGl2GroupWarps, gt = threadIdx.x % GT;   // tile group, warp / thread in it
   const int hop = p.hop;
@@ -240,7 +246,7 @@ __global__ void __launch_bounds__(kGl2Warps * 32, 1) gl2_kernel(const PlanDev p,
         float4* yt4 = reinterpret_cast<float4*>(ytile);
 #pragma unroll 5
         for (int j = gt; j < span / 4; j += GT) {
-          const float4 p4 = __ldg(ya4 + j), q4 = __ldg(yb4 + j);
+          const float4 p4 = gl2_ldsig<COH>(ya4 + j), q4 = gl2_ldsig<COH>(yb4 + j);
           yt4[j] = make_float4(p4.x + q4.x, p4.y + q4.y, p4.z + q4.z, p4.w + q4.w);
         }
       } else {
@@ -251,7 +257,7 @@ __global__ void __launch_bounds__(kGl2Warps * 32, 1) gl2_kernel(const PlanDev p,
           i = i < 0 ? -i : i;
           i = i >= Ly ? 2 * (Ly - 1) - i : i;
           const int uu = min(i + N / 4, cov - 1);
-          const float val = __ldg(ya + uu) + __ldg(yb + uu);
+          const float val = gl2_ldsig<COH>(ya + uu) + gl2_ldsig<COH>(yb + uu);
           ytile[j] = (i + N / 4 < cov) ? val : 0.f;
         }
       }
@@ -561,6 +567,66 @@ __global__ void __launch_bounds__(kGl2Warps * 32, 1) gl2_kernel(const PlanDev p,
       }
     }
     gl2_group_sync(group);
+  }
+}
+
+template <int N, int MODE>
+__global__ void __launch_bounds__(kGl2Warps * 32, 1) gl2_kernel(const PlanDev p, const Gl2Args a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Gl2Smem<N> sm;
+  sm.init(smem_raw, p);
+  gl2_pass<N, MODE, false>(p, a, sm);
+}
+
+// ---- persistent Griffin-Lim: init + all iterations in ONE cooperative launch --------------------------------------------
+// For small batches (every tile group resident at once: tiles <= 2 x SMs, e.g. one 5 s utterance = 54 tiles) an iteration
+// is the latency of ONE tile, and with one launch per iteration most of that latency is fetching the kernel's ~5000
+// straight-line instructions again.  Here the CTAs stay resident, the code stays in the instruction cache, and the
+// iterations are separated by a grid barrier (arrive / spin on a global counter; the launch is cooperative, so all CTAs
+// are co-resident).  The signal written before a barrier is read after it through L2 (gl2_ldsig<true>); the per-bin state
+// (tprev) of a tile is only ever touched by the CTA that owns the tile.
+__device__ __forceinline__ void gl2_grid_barrier(unsigned* counter, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+    } while (seen < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <int N, int FORM>   // FORM 0: angle form (mode 2), 1: fast form (mode 3)
+__global__ void __launch_bounds__(kGl2Warps * 32, 1) gl2_persistent_kernel(const PlanDev p, Gl2Args a, int n_iter, float* sig,
+                                                                             long long sig_elems, unsigned* counter) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Gl2Smem<N> sm;
+  sm.init(smem_raw, p);
+  // signal buffers: [parity pair cur][a / b]
+  float* const b00 = sig;
+  float* const b01 = sig + sig_elems;
+  float* const b10 = sig + 2 * sig_elems;
+  float* const b11 = sig + 3 * sig_elems;
+  a.ya_out = b00;
+  a.yb_out = b01;
+  gl2_pass<N, 1, true>(p, a, sm);
+  unsigned target = gridDim.x;
+  gl2_grid_barrier(counter, target);
+  int cur = 0;
+#pragma unroll 1
+  for (int it = 0; it < n_iter; ++it) {
+    a.ya_in = cur ? b10 : b00;
+    a.yb_in = cur ? b11 : b01;
+    a.ya_out = cur ? b00 : b10;
+    a.yb_out = cur ? b01 : b11;
+    a.first = (it == 0);
+    gl2_pass<N, 2 + FORM, true>(p, a, sm);
+    target += gridDim.x;
+    gl2_grid_barrier(counter, target);
+    cur ^= 1;
   }
 }
 

@@ -1,4 +1,5 @@
 // C-ABI entry points: ISTFT / Griffin-Lim (include/spectral_b200.h).  Host glue + the gl2 kernels.
+#include <cstdlib>
 #include <mutex>
 
 #include "capi_common.cuh"
@@ -62,10 +63,20 @@ static void launch_gl2_mode(const sb200_plan* plan, const Gl2Args& a, int grid, 
   gl2_kernel<N, MODE><<<grid, kGl2Warps * 32, smem, st>>>(plan->dev, a);
 }
 
+// SB200_GL_PERSISTENT=0 keeps one launch per iteration for every batch size (A/B measurements)
+static bool gl2_persistent_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("SB200_GL_PERSISTENT");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 // init (mode 0: complex spectrogram, mode 1: S * exp(2 pi i u)) -> n_iter iterations -> finish [-> inv_preemphasis]
+// counter: 4 zeroable bytes of workspace for the grid barrier of the persistent kernel (null: never persistent)
 template <int N>
 static int launch_gl2(const sb200_plan* plan, Gl2Args a, int n_iter, int form, float* y, float inv_pre, float* sig,
-                      long long sig_elems, long long max_row_len, cudaStream_t st) {
+                      long long sig_elems, long long max_row_len, cudaStream_t st, unsigned* counter = nullptr) {
   using C = Fft2Cfg<N>;
   constexpr int FT = kGl2GroupWarps * C::kFrames;
   const int hop = plan->cfg.hop_length;
@@ -78,6 +89,23 @@ static int launch_gl2(const sb200_plan* plan, Gl2Args a, int n_iter, int form, f
   const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>((tiles + kGl2Groups - 1) / kGl2Groups, sm_count())));
   float* buf[2][2] = {{sig, sig + sig_elems}, {sig + 2 * sig_elems, sig + 3 * sig_elems}};
   int cur = 0;
+  // small batch, Griffin-Lim proper: one cooperative launch for init + all iterations (gl2_persistent_kernel)
+  if (!a.spec && n_iter > 0 && counter && tiles <= static_cast<long long>(kGl2Groups) * sm_count() && gl2_persistent_enabled()) {
+    void (*kern)(const PlanDev, Gl2Args, int, float*, long long, unsigned*) =
+        form == 0 ? gl2_persistent_kernel<N, 0> : gl2_persistent_kernel<N, 1>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaMemsetAsync(counter, 0, sizeof(unsigned), st);
+    PlanDev pd = plan->dev;
+    long long se = sig_elems;
+    void* args[] = {&pd, &a, &n_iter, &sig, &se, &counter};
+    const cudaError_t ce = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kern), dim3(grid), dim3(kGl2Warps * 32), args, smem, st);
+    if (ce == cudaSuccess) {
+      if (int rc = check_launch("gl2_persistent_kernel")) return rc;
+      cur = n_iter & 1;
+      goto finish;
+    }
+    cudaGetLastError();   // not co-resident / not supported: fall back to one launch per iteration
+  }
   a.ya_out = buf[0][0];
   a.yb_out = buf[0][1];
   if (a.spec) launch_gl2_mode<N, 0>(plan, a, grid, smem, st);
@@ -94,6 +122,7 @@ static int launch_gl2(const sb200_plan* plan, Gl2Args a, int n_iter, int form, f
     if (int rc = check_launch("gl2_kernel (iteration)")) return rc;
     cur ^= 1;
   }
+finish:
   Gl2FinishArgs f{a.g, buf[cur][0], buf[cur][1], y};
   dim3 ogrid(grid_for(max_row_len, 256, 4), a.g.bd.B);
   gl2_finish_kernel<N><<<ogrid, 256, 0, st>>>(plan->dev, f);
@@ -141,8 +170,12 @@ int sb200_griffinlim(const sb200_plan* plan, const float* S, const float* init_p
   float* sig = static_cast<float*>(workspace);
   a.tprev = reinterpret_cast<float2*>(sig + 4 * sig_elems);
   int rc = 0;
+  // grid-barrier counter: first 256-byte boundary behind the signal buffers and tprev (inside the workspace's 512 bytes of slack)
+  const size_t used = static_cast<size_t>(4) * sig_elems * sizeof(float) +
+                      (form == 1 ? static_cast<size_t>(total_frames) * (plan->cfg.n_fft / 2 + 1) * 8 : 0);
+  unsigned* counter = reinterpret_cast<unsigned*>(static_cast<char*>(workspace) + (used + 255) / 256 * 256);
   SB200_DISPATCH_N(plan, rc = launch_gl2<kN>(plan, a, n_iter, form, y, inv_preemph, sig, sig_elems, max_len,
-                                             static_cast<cudaStream_t>(stream)));
+                                             static_cast<cudaStream_t>(stream), counter));
   return rc;
 }
 
