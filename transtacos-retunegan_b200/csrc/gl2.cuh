@@ -49,6 +49,7 @@ struct Gl2Args {
   float2* tprev;             // [frames, F] (mode 3): previous rebuilt spectrum in the engine's internal (rotated) form
   float alpha;               // momentum / (1 + momentum)
   int first;                 // mode 3: tprev not yet written (rebuilt = 0)
+  int groups_active;         // tile groups of a CTA that take tiles (0 = all): 1 gives a small batch one tile per SM
 };
 
 // first element of utterance b in the signal buffers; an utterance owns (T - 1) * hop + win elements
@@ -223,8 +224,9 @@ __device__ __forceinline__ void gl2_pass(const PlanDev& p, const Gl2Args& a, Gl2
   const int partner = (lane & ~(C::kR2 - 1)) | ((C::kR2 - k1) & (C::kR2 - 1));
   const int rk = k1 & 3, rm = (4 - rk) & 3;                 // bin index mod 4 of the a side (k1 + R2 s) and b side (Nz - k)
   const long long n_tiles = static_cast<long long>(a.g.bd.B) * a.tiles_per_row;
-  for (long long vt = static_cast<long long>(blockIdx.x) * kGl2Groups + group; vt < n_tiles;
-       vt += static_cast<long long>(gridDim.x) * kGl2Groups) {
+  const int ga = a.groups_active > 0 ? a.groups_active : kGl2Groups;
+  for (long long vt = group < ga ? static_cast<long long>(blockIdx.x) * ga + group : n_tiles; vt < n_tiles;
+       vt += static_cast<long long>(gridDim.x) * ga) {
     const int b = static_cast<int>(vt / a.tiles_per_row), tk = static_cast<int>(vt - static_cast<long long>(b) * a.tiles_per_row);
     const GlRow row = gl_row(a.g, b, N, hop);
     const int tile_t0 = tk * FT;

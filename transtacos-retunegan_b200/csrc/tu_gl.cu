@@ -72,6 +72,14 @@ static bool gl2_persistent_enabled() {
   return on;
 }
 
+static bool gl2_one_group_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("SB200_GL_ONE_GROUP");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 // init (mode 0: complex spectrogram, mode 1: S * exp(2 pi i u)) -> n_iter iterations -> finish [-> inv_preemphasis]
 // counter: 4 zeroable bytes of workspace for the grid barrier of the persistent kernel (null: never persistent)
 template <int N>
@@ -95,16 +103,22 @@ static int launch_gl2(const sb200_plan* plan, Gl2Args a, int n_iter, int form, f
         form == 0 ? gl2_persistent_kernel<N, 0> : gl2_persistent_kernel<N, 1>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     cudaMemsetAsync(counter, 0, sizeof(unsigned), st);
+    int pgrid = grid;
+    if (tiles <= sm_count() && gl2_one_group_enabled()) {   // one tile per SM: the tile's latency is the iteration time
+      a.groups_active = 1;
+      pgrid = static_cast<int>(tiles);
+    }
     PlanDev pd = plan->dev;
     long long se = sig_elems;
     void* args[] = {&pd, &a, &n_iter, &sig, &se, &counter};
-    const cudaError_t ce = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kern), dim3(grid), dim3(kGl2Warps * 32), args, smem, st);
+    const cudaError_t ce = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kern), dim3(pgrid), dim3(kGl2Warps * 32), args, smem, st);
     if (ce == cudaSuccess) {
       if (int rc = check_launch("gl2_persistent_kernel")) return rc;
       cur = n_iter & 1;
       goto finish;
     }
     cudaGetLastError();   // not co-resident / not supported: fall back to one launch per iteration
+    a.groups_active = 0;
   }
   a.ya_out = buf[0][0];
   a.yb_out = buf[0][1];
