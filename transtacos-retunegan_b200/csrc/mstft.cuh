@@ -172,12 +172,53 @@ struct MstftBwdArgs {
   float* partials;         // FUSED: [gridDim.x * kMstftWarps] loss partial sums
 };
 
+// Shared-memory bytes of mstft_bwd_kernel: the tables and per-warp FFT buffers of the forward kernel plus, per warp, the
+// mel-row gradients [Q][128].
+template <int N>
+inline size_t mstft_bwd_smem_bytes(const PlanDev& p) {
+  return feat_smem_bytes<N>(p) + sizeof(float) * kMstftWarps * FftCfg<N>::kQ * 128;
+}
+
+// mel projection of |X + 1e-9| with the complex spectrum X in buf (natural bin order), magnitudes taken on the fly
+template <int N, class Emit>
+__device__ __forceinline__ void mel_project_cplx(const PlanDev& p, const float* __restrict__ s_melw, const int* __restrict__ s_lo,
+                                                 const float2* __restrict__ buf, int lane, Emit&& emit) {
+  using C = FftCfg<N>;
+#pragma unroll 1
+  for (int rd = 0; rd < p.mel_rounds; ++rd) {
+    const int slot = s_lo[rd * 32 + lane];
+    const int m = slot >> 16, lo = slot & 0xffff;
+    const float* wr = s_melw + p.mel_round_off[rd] + lane;
+    const int n = p.mel_round_len[rd];
+    float acc[C::kQ];
+#pragma unroll
+    for (int q = 0; q < C::kQ; ++q) acc[q] = 0.f;
+#pragma unroll 2
+    for (int it = 0; it < n; ++it) {
+      const float w = wr[it * 32];
+      const int idx = min(lo + it, C::kNz - 1);
+#pragma unroll
+      for (int q = 0; q < C::kQ; ++q) {
+        const float2 X = buf[q * C::kZS + idx];
+        const float re = X.x + 1e-9f;
+        acc[q] = fmaf(w, sqrtf(fmaf(re, re, X.y * X.y)), acc[q]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < C::kQ; ++q) emit(q, rd, m, acc[q]);
+  }
+}
+
 // FUSED = loss value and its gradient in ONE pass (loss-only training steps): analyses y, then does the backward work on
 // y_g with a unit upstream gradient while accumulating the loss -- no recomputation, no second launch per resolution.
+//
+// Every warp runs this body once per item and an item is all a warp gets at training sizes, so the kernel's time is the
+// instruction fetch of its own straight-line code (profiles/r01_mstft_gl2_ncu_summary.md: 44 % no_instruction stalls at
+// 14.6 k instructions).  The Hermitian-pair work (forward split, gradient of every bin, inverse split) therefore runs as
+// ROLLED loops over the spectrum kept in the warp's shared-memory buffer instead of unrolled over register arrays.
 template <int N, bool FUSED>
 __global__ void __launch_bounds__(kMstftWarps * 32, 2) mstft_bwd_kernel(const PlanDev p, const MstftBwdArgs a) {
   using C = FftCfg<N>;
-  constexpr int kPairs = C::kQ * C::kPairIters;   // 16
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemTables<N> sm;
   sm.carve(smem_raw, p);
@@ -185,7 +226,10 @@ __global__ void __launch_bounds__(kMstftWarps * 32, 2) mstft_bwd_kernel(const Pl
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float2* buf = sm.bufs + warp * C::kBufF2;
-  float* gmbuf = reinterpret_cast<float*>(buf);   // [Q][128] mel-row gradients, after the mel phase
+  float* gmbuf = reinterpret_cast<float*>(sm.bufs + kMstftWarps * C::kBufF2) + warp * C::kQ * 128;   // [Q][128] mel-row gradients
+  // bin Nz (Nyquist) of frame q: the pad slot behind the row where rows are padded, else behind the last row
+  auto nyq = [](int q) { return C::kZS > C::kNz ? q * C::kZS + C::kNz : C::kQ * C::kZS + q; };
+  static_assert(C::kZS > C::kNz || C::kQ * C::kZS + C::kQ <= C::kBufF2, "no room for the Nyquist bins");
   const int rk = lane & 3, rm = (4 - rk) & 3;
   const float gl = FUSED ? a.loss_scale : (a.g_loss ? __ldg(a.g_loss) * a.loss_scale : 0.f);
   float loss_acc = 0.f;
@@ -197,69 +241,67 @@ __global__ void __launch_bounds__(kMstftWarps * 32, 2) mstft_bwd_kernel(const Pl
     if (it.t0 < it.T) {
     float2 v[32];
     float mr[kMaxMelRounds][C::kQ];
-    float2 Xk[kPairs], Xm[kPairs], Xs[C::kQ];
     float gm[kMaxMelRounds][C::kQ];
 #pragma unroll
     for (int rd = 0; rd < kMaxMelRounds; ++rd)
 #pragma unroll
-      for (int q = 0; q < C::kQ; ++q) gm[rd][q] = 0.f;
+      for (int q = 0; q < C::kQ; ++q) { gm[rd][q] = 0.f; mr[rd][q] = 1.f; }
     // FUSED: the real signal (side 0: only its mel rows are kept), then the generated one (side 1) through ONE copy of the
-    // analysis code -- rolled on purpose, see mstft_fwd_kernel.  Not fused: side 1 only.
+    // analysis code.  Not fused: side 1 only.
 #pragma unroll 1
     for (int side = FUSED ? 0 : 1; side < 2; ++side) {
       load_frames<N, false>(v, (side ? a.yg : a.y) + it.sig_base, it.L, it.t0, it.T, p.hop, 0.f, sm.win, lane);
       fft_forward<N>(v, buf, sm.tw, lane);
-      static_for<0, C::kQ>([&](auto qc) {
-        constexpr int q = decltype(qc)::value;
+      // forward split in place: Z[k], Z[Nz-k] -> X[k], X[Nz-k] (bin Nz to its own slot)
+#pragma unroll 1
+      for (int q = 0; q < C::kQ; ++q) {
         float2* zq = buf + q * C::kZS;
-        static_for<0, C::kPairIters>([&](auto ic) {
-          constexpr int i = decltype(ic)::value;
+#pragma unroll 2
+        for (int i = 0; i < C::kPairIters; ++i) {
           const int k = lane + 32 * i;
           const int km = (C::kNz - k) & (C::kNz - 1);
           float2 Ak, Am;
           split_fwd(zq[k], zq[km], sm.ws[k], Ak, Am);
           const float2 xk = rot_fwd(Ak, rk), xm = rot_fwd(Am, rm);
-          Xk[q * C::kPairIters + i] = xk;
-          Xm[q * C::kPairIters + i] = xm;
-          const float rek = xk.x + 1e-9f, rem = xm.x + 1e-9f;
-          zq[k].x = sqrtf(fmaf(rek, rek, xk.y * xk.y));
-          if (k != 0) zq[km].x = sqrtf(fmaf(rem, rem, xm.y * xm.y));
-        });
-        {
+          zq[k] = xk;
+          if (k != 0) zq[km] = xm;
+          else buf[nyq(q)] = xm;
+        }
+        if (lane == 0) {
           constexpr int k = C::kNz / 2;
           float2 Ak, Am;
           split_fwd(zq[k], zq[k], sm.ws[k], Ak, Am);
-          Xs[q] = rot_fwd(Ak, k);
-          if (lane == 0) {
-            const float rek = Xs[q].x + 1e-9f;
-            zq[k].x = sqrtf(fmaf(rek, rek, Xs[q].y * Xs[q].y));
-          }
+          zq[k] = rot_fwd(Ak, k);
         }
-      });
+      }
       __syncwarp();
       // side 0: mel of the real signal; side 1: mel of the generated signal -> gradient of the loss w.r.t. each mel row
-      mel_project_smem<N>(p, sm.melw, sm.mel_lo, buf, lane, [&](int q, int rd, int m, float mg) {
-        if (side == 0) {
-          mr[rd][q] = mg;
-        } else {
-          float g = 0.f;
-          if (gl != 0.f && m < p.n_mel && it.t0 + q < it.T) {
-            float r;
-            if constexpr (FUSED) {
-              r = mr[rd][q];
-              loss_acc += fabsf(r - mg) + fabsf(logf(r) - logf(mg));
-            } else {
-              r = __ldg(a.mel_r + (it.frame_base + it.t0 + q) * p.n_mel + m);
+      mel_project_cplx<N>(p, sm.melw, sm.mel_lo, buf, lane, [&](int q, int rd, int m, float mg) {
+#pragma unroll
+        for (int r2 = 0; r2 < kMaxMelRounds; ++r2) {
+          if (r2 != rd) continue;
+          if (side == 0) {
+            mr[r2][q] = mg;
+          } else {
+            float g = 0.f;
+            if (gl != 0.f && m < p.n_mel && it.t0 + q < it.T) {
+              float r;
+              if constexpr (FUSED) {
+                r = mr[r2][q];
+                loss_acc += fabsf(r - mg) + fabsf(logf(r) - logf(mg));
+              } else {
+                r = __ldg(a.mel_r + (it.frame_base + it.t0 + q) * p.n_mel + m);
+              }
+              const float sgn = (mg > r) ? 1.f : ((mg < r) ? -1.f : 0.f);
+              g = gl * (sgn + sgn / mg);
             }
-            const float sgn = (mg > r) ? 1.f : ((mg < r) ? -1.f : 0.f);
-            g = gl * (sgn + sgn / mg);
+            gm[r2][q] = g;
           }
-          gm[rd][q] = g;
         }
       });
       if (side == 0) __syncwarp();
     }
-    __syncwarp();   // all S reads done; reuse the buffer for the mel-row gradients
+    // mel-row gradients by row (their own buffer: the spectrum stays in buf)
 #pragma unroll
     for (int rd = 0; rd < kMaxMelRounds; ++rd)
 #pragma unroll
@@ -268,7 +310,7 @@ __global__ void __launch_bounds__(kMstftWarps * 32, 2) mstft_bwd_kernel(const Pl
         if (row < 128) gmbuf[q * 128 + row] = gm[rd][q];
       }
     __syncwarp();
-    // gD on the Hermitian pairs (in registers), scaled for the adjoint: interior bins / 2, DC and Nyquist real
+    // gD of one bin, scaled for the adjoint: interior bins / 2, DC and Nyquist real
     auto grad_bin = [&](float2 X, int q, int k, float half) -> float2 {
       const long long t = it.t0 + q;
       float2 G = make_float2(0.f, 0.f);
@@ -290,40 +332,32 @@ __global__ void __launch_bounds__(kMstftWarps * 32, 2) mstft_bwd_kernel(const Pl
       }
       return G;
     };
-    static_for<0, C::kQ>([&](auto qc) {
-      constexpr int q = decltype(qc)::value;
-      static_for<0, C::kPairIters>([&](auto ic) {
-        constexpr int i = decltype(ic)::value;
-        constexpr int pi = q * C::kPairIters + i;
-        const int k = lane + 32 * i;
-        Xk[pi] = grad_bin(Xk[pi], q, k, k == 0 ? 1.f : 0.5f);
-        Xm[pi] = grad_bin(Xm[pi], q, C::kNz - k, k == 0 ? 1.f : 0.5f);
-      });
-      Xs[q] = grad_bin(Xs[q], q, C::kNz / 2, 0.5f);
-    });
-    __syncwarp();   // every lane has finished reading gmbuf before Z' overwrites it
-    static_for<0, C::kQ>([&](auto qc) {
-      constexpr int q = decltype(qc)::value;
+    // gradient of every Hermitian pair and inverse split, in place: X[k], X[Nz-k] -> Z'[k], Z'[Nz-k]
+#pragma unroll 1
+    for (int q = 0; q < C::kQ; ++q) {
       float2* zq = buf + q * C::kZS;
-      static_for<0, C::kPairIters>([&](auto ic) {
-        constexpr int i = decltype(ic)::value;
-        constexpr int pi = q * C::kPairIters + i;
+#pragma unroll 1
+      for (int i = 0; i < C::kPairIters; ++i) {
         const int k = lane + 32 * i;
-        float2 Bk = rot_inv(Xk[pi], rk), Bm = rot_inv(Xm[pi], rm);
+        const int km = (C::kNz - k) & (C::kNz - 1);
+        const float half = k == 0 ? 1.f : 0.5f;
+        const float2 Gk = grad_bin(zq[k], q, k, half);
+        const float2 Gm = grad_bin(k != 0 ? zq[km] : buf[nyq(q)], q, C::kNz - k, half);
+        float2 Bk = rot_inv(Gk, rk), Bm = rot_inv(Gm, rm);
         if (k == 0) { Bk.y = 0.f; Bm.y = 0.f; }
         float2 Zk, Zr;
         split_inv(Bk, Bm, sm.ws[k], Zk, Zr);
-        if (k != 0) zq[C::kNz - k] = Zr;
+        if (k != 0) zq[km] = Zr;
         zq[k] = Zk;
-      });
+      }
       if (lane == 0) {
         constexpr int k = C::kNz / 2;
-        const float2 B = rot_inv(Xs[q], k);
+        const float2 B = rot_inv(grad_bin(zq[k], q, k, 0.5f), k);
         float2 Zk, Zr;
         split_inv(B, B, sm.ws[k], Zk, Zr);
         zq[k] = Zk;
       }
-    });
+    }
     __syncwarp();
     fft_inverse<N>(v, buf, sm.tw, lane);
     static_for<0, C::kQ>([&](auto qc) {

@@ -105,7 +105,7 @@ static void launch_mstft_fwd(const sb200_plan* plan, const MstftFwdArgs& a, int 
 }
 template <int N>
 static void launch_mstft_bwd(const sb200_plan* plan, const MstftBwdArgs& a, int grid, cudaStream_t st, bool fused = false) {
-  const size_t smem = feat_smem_bytes<N>(plan->dev);
+  const size_t smem = mstft_bwd_smem_bytes<N>(plan->dev);
   if (fused) {
     cudaFuncSetAttribute(mstft_bwd_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     mstft_bwd_kernel<N, true><<<grid, kMstftWarps * 32, smem, st>>>(plan->dev, a);
