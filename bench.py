@@ -232,7 +232,7 @@ def make_griffinlim(sb, torch, B=1, form="rtg", rot=4):
     return w
 
 
-def make_mstft(sb, torch, B=16, T=22050, specs=False, rot=4):
+def make_mstft(sb, torch, B=16, T=22050, specs=False, rot=4, ddp=False):
     w = Workload()
     w.name = f"mstft_fwd_bwd_{B}x{T}" + ("_specs" if specs else "_lossonly")
     g = torch.Generator(device="cuda").manual_seed(77 + int(os.environ.get("RANK", 0)))
@@ -248,16 +248,17 @@ def make_mstft(sb, torch, B=16, T=22050, specs=False, rot=4):
         j = i % rot
         ygs[j].grad = None
         if specs:
-            loss, (sr, sg) = sb.multi_stft_loss(ys[j], ygs[j], ret_loss=True, ret_specs=True)
+            loss, (sr, sg) = sb.multi_stft_loss(ys[j], ygs[j], ret_loss=True, ret_specs=True, ddp_reduce=ddp)
             torch.autograd.backward([loss] + list(sg), [torch.ones_like(loss)] + ups)
         else:
-            sb.multi_stft_loss(ys[j], ygs[j], ret_loss=True).backward()
+            sb.multi_stft_loss(ys[j], ygs[j], ret_loss=True, ddp_reduce=ddp).backward()
         return ygs[j].grad
     w.step, w.e2e = step, None
     w.units = B * T / SR
     w.alg_bytes = (4.23e6 if not specs else 113e6) * (B / 16) * (T / 22050)
     w.dominant = "mstft_fwd_kernel+mstft_bwd_kernel (3 resolutions)"
-    w.note = "loss-only" if not specs else "training variant: spec stacks written, dense upstream spec grads"
+    w.note = ("loss-only" if not specs else "training variant: spec stacks written, dense upstream spec grads") + \
+        ("; the reported loss is averaged over the ranks with one NCCL all-reduce of a scalar inside the step" if ddp else "")
     w.check = lambda: torch.isfinite(step(0)).all().item()
     return w
 
@@ -448,7 +449,8 @@ def main():
     makers = {"stft_mel": lambda: make_stft_mel(sb, torch), "griffinlim": lambda: make_griffinlim(sb, torch, 1, "rtg"),
               "griffinlim_tt": lambda: make_griffinlim(sb, torch, 1, "tt"),
               "griffinlim_batch": lambda: make_griffinlim(sb, torch, 64, "rtg"),
-              "mstft": lambda: make_mstft(sb, torch), "mstft_specs": lambda: make_mstft(sb, torch, specs=True),
+              "mstft": lambda: make_mstft(sb, torch, ddp=world > 1),
+              "mstft_specs": lambda: make_mstft(sb, torch, specs=True, ddp=world > 1),
               "corpus": lambda: make_corpus(sb, torch, rank, world),
               "corpus_d2h": lambda: make_corpus(sb, torch, rank, world, d2h=True)}
     w = makers[a.workload]()
@@ -462,13 +464,13 @@ def main():
     dev_s, wall_s = time_steps(torch, w.step, a.steps, a.warmup, barrier)
     launches = sb._lib.launch_count() - l0
     window = "warmup+timed"
-    if len(sampler.samples) < 5:          # very short timed region: keep the same loop running to catch the clocks under load
-        t_end = time.perf_counter() + 1.0
-        i = 0
-        while time.perf_counter() < t_end:
+    # very short timed region: keep the same loop running ~1 s to catch the clocks under load.  The decision and the number of
+    # extra steps are agreed over the ranks (a step may contain a collective: a rank-local, time-based loop would deadlock).
+    if allmax(1.0 if len(sampler.samples) < 5 else 0.0) > 0:
+        n_cont = int(min(20000, max(1, 1.0 / max(allmax(dev_s) / a.steps, 1e-6))))
+        for i in range(n_cont):
             w.step(i)
-            i += 1
-            if i % 64 == 0:
+            if i % 64 == 63:
                 torch.cuda.synchronize()
         torch.cuda.synchronize()
         window = "warmup+timed+1s continuation of the same loop"
@@ -507,6 +509,25 @@ def main():
                "steps": K2, "api": "transtacos_audio.get_specs(cpu_tensor[64,L], out=pinned)" if a.workload == "stft_mel"
                else "retunegan_audio.inv_mag(numpy)"}
 
+    ddp_info = None
+    if world > 1 and a.workload.startswith("mstft"):
+        # under DDP the generator's gradients (RefineGAN_small, ~2.75 M parameters, retunegan/hparam.py:50)
+        # are all-reduced by DDP's buckets many layers after this loss; timed here on its own, next to the loss step
+        gbuf = torch.zeros(2_750_000, device="cuda")
+        for _ in range(5):
+            dist.all_reduce(gbuf)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(50):
+            dist.all_reduce(gbuf)
+        e1.record()
+        torch.cuda.synchronize()
+        ddp_info = {"generator_grad_allreduce_ms": allmax(e0.elapsed_time(e1) / 50), "generator_grad_bytes": gbuf.numel() * 4,
+                    "loss_allreduce": "one fp32 scalar per step, inside the timed step (multi_stft_loss(ddp_reduce=True))"}
+        del gbuf
+
     extra = {}
     if world == 1 and not a.no_extra and not a.kernel_only and a.workload == "stft_mel":
         for key, mk, k in (("griffinlim_rtg_1x5s_4it", makers["griffinlim"], 50),
@@ -540,7 +561,7 @@ def main():
             "metric": METRIC, "value": total_units * a.steps / dev_s, "unit": UNIT, "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * dev_s / a.steps, "higher_is_better": True,
             "scaling": "strong" if a.workload == "corpus" else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(config, workload=w.name, per_gpu=w.name, l2=w.note),
+            "config": dict(config, workload=w.name, per_gpu=w.name, l2=w.note, **({"ddp": ddp_info} if ddp_info else {})),
             "clocks": sampler.summary(window),
             "e2e": e2e, "gpu_launches": int(timed_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -117,6 +117,21 @@ class _MultiStftFn(torch.autograd.Function):
         return None, g_yg.to(ctx.in_dtype).reshape(ctx.in_shape), None, None, None
 
 
+class _GlobalMean(torch.autograd.Function):
+    """Value = mean of the rank-local losses (one NCCL all-reduce of a scalar), gradient = the local one: what DDP training logs
+    and back-propagates (retunegan/train.py averages nothing itself; DDP averages the generator gradients later)."""
+
+    @staticmethod
+    def forward(ctx, loss):
+        red = loss.detach() / torch.distributed.get_world_size()
+        torch.distributed.all_reduce(red, op=torch.distributed.ReduceOp.SUM)
+        return red
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
 def multi_stft_loss(y, y_g, ret_loss=False, ret_specs=False, ddp_reduce=False):
     """retunegan/models/loss.py:22-62 (same arguments and return structure)."""
     if not (ret_loss or ret_specs):
@@ -135,9 +150,7 @@ def multi_stft_loss(y, y_g, ret_loss=False, ret_specs=False, ddp_reduce=False):
         loss = outs[0]
         i = 1
         if ddp_reduce and torch.distributed.is_available() and torch.distributed.is_initialized():
-            red = loss.detach().clone()
-            torch.distributed.all_reduce(red, op=torch.distributed.ReduceOp.SUM)
-            loss = loss + (red / torch.distributed.get_world_size() - loss.detach())   # value = global mean, grad = local
+            loss = _GlobalMean.apply(loss)   # value = global mean, grad = local
     if ret_specs:
         stft_r = [s.transpose(2, 3) for s in outs[i:i + n_res]]
         stft_g = [s.transpose(2, 3) for s in outs[i + n_res:i + 2 * n_res]]
