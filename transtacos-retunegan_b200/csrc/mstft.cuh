@@ -311,14 +311,15 @@ __global__ void __launch_bounds__(kMstftWarps * 32, 2) mstft_bwd_kernel(const Pl
       }
     __syncwarp();
     // gD of one bin, scaled for the adjoint: interior bins / 2, DC and Nyquist real
-    auto grad_bin = [&](float2 X, int q, int k, float half) -> float2 {
+    // (r0, c0, c1): column view of the mel basis at bin k, loaded by the caller ahead of the branch (both bins of a pair at
+    // once: inside the conditional the two L2 round trips would be taken one after the other)
+    auto grad_bin = [&](float2 X, int q, int k, float half, int r0, float c0, float c1) -> float2 {
       const long long t = it.t0 + q;
       float2 G = make_float2(0.f, 0.f);
       if (t < it.T) {
         const float re = X.x + 1e-9f;
         const float S = sqrtf(fmaf(re, re, X.y * X.y));
-        const int r0 = __ldg(p.col_r0 + k);
-        float gS = fmaf(__ldg(p.col_c0 + k), gmbuf[q * 128 + r0], __ldg(p.col_c1 + k) * gmbuf[q * 128 + r0 + 1]);
+        float gS = fmaf(c0, gmbuf[q * 128 + r0], c1 * gmbuf[q * 128 + r0 + 1]);
         float gP = 0.f;
         if (a.g_spec) {
           const long long idx = (static_cast<long long>(it.b) * 2 * a.Tf + t) * C::kF + k;
@@ -336,13 +337,16 @@ __global__ void __launch_bounds__(kMstftWarps * 32, 2) mstft_bwd_kernel(const Pl
 #pragma unroll 1
     for (int q = 0; q < C::kQ; ++q) {
       float2* zq = buf + q * C::kZS;
-#pragma unroll 1
+#pragma unroll 2
       for (int i = 0; i < C::kPairIters; ++i) {
         const int k = lane + 32 * i;
         const int km = (C::kNz - k) & (C::kNz - 1);
         const float half = k == 0 ? 1.f : 0.5f;
-        const float2 Gk = grad_bin(zq[k], q, k, half);
-        const float2 Gm = grad_bin(k != 0 ? zq[km] : buf[nyq(q)], q, C::kNz - k, half);
+        const int r0k = __ldg(p.col_r0 + k), r0m = __ldg(p.col_r0 + C::kNz - k);
+        const float c0k = __ldg(p.col_c0 + k), c1k = __ldg(p.col_c1 + k);
+        const float c0m = __ldg(p.col_c0 + C::kNz - k), c1m = __ldg(p.col_c1 + C::kNz - k);
+        const float2 Gk = grad_bin(zq[k], q, k, half, r0k, c0k, c1k);
+        const float2 Gm = grad_bin(k != 0 ? zq[km] : buf[nyq(q)], q, C::kNz - k, half, r0m, c0m, c1m);
         float2 Bk = rot_inv(Gk, rk), Bm = rot_inv(Gm, rm);
         if (k == 0) { Bk.y = 0.f; Bm.y = 0.f; }
         float2 Zk, Zr;
@@ -352,7 +356,7 @@ __global__ void __launch_bounds__(kMstftWarps * 32, 2) mstft_bwd_kernel(const Pl
       }
       if (lane == 0) {
         constexpr int k = C::kNz / 2;
-        const float2 B = rot_inv(grad_bin(zq[k], q, k, 0.5f), k);
+        const float2 B = rot_inv(grad_bin(zq[k], q, k, 0.5f, __ldg(p.col_r0 + k), __ldg(p.col_c0 + k), __ldg(p.col_c1 + k)), k);
         float2 Zk, Zr;
         split_inv(B, B, sm.ws[k], Zk, Zr);
         zq[k] = Zk;
