@@ -266,3 +266,49 @@ def test_pool_losses_golden(sb, golden_side, name, mode):
     assert fn(y, yg.detach()).requires_grad is False
     with pytest.raises(RuntimeError):
         fn(y[..., :100], yg[..., :100])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fl,hop,fmin,fmax", [(2048, 512, 65.0, 2093.0), (512, 128, 200.0, 1500.0), (1024, 240, 73.4, 587.3)])
+def test_yin_other_framings(sb, fl, hop, fmin, fmax):
+    """sb200_yin away from the reference's framing (librosa's default 2048 / 512, a short frame, a hop that does not divide the frame)."""
+    y = _wav(30011, 91)
+    f0, frames = sb.core.yin(y, 22050, fmin, fmax, fl, hop)
+    ref = O.yin(y, fmin, fmax, 22050, fl, None, hop).astype(np.float32)
+    assert int(frames[0]) == len(ref) == 1 + len(y) // hop
+    ok = np.abs(f0.cpu().numpy() / ref - 1) < 1e-4
+    assert ok.mean() >= 0.99, ok.mean()
+    with pytest.raises(ValueError):
+        sb.core.yin(y, 22050, fmax, fmin, fl, hop)          # fmin >= fmax
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fl,hop,L", [(1024, 256, 1023), (400, 160, 16000), (512, 128, 130)])
+def test_frame_stats_other_framings(sb, fl, hop, L):
+    y = _wav(max(L, 700), 92)[:L]
+    rms, zcr, frames = sb.core.frame_stats(y, fl, hop)
+    if L > fl // 2:     # np.pad(mode='reflect') needs the signal longer than the pad
+        np.testing.assert_allclose(rms.cpu().numpy(), O.rms(y, fl, hop), rtol=1e-5, atol=1e-9)
+    np.testing.assert_array_equal(zcr.cpu().numpy(), O.zero_crossing_rate(y, fl, hop).astype(np.float32))
+    assert int(frames[0]) == 1 + L // hop
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,T,k", [(1, 1000, 100), (5, 4099, 37), (2, 160, 160)])
+def test_pool_losses_other_shapes(sb, B, T, k):
+    """Windows that are not a multiple of the warp size, a tail outside every window, a single window per row."""
+    rs = np.random.RandomState(B * 1000 + k)
+    y = (0.3 * rs.randn(B, T)).astype(np.float32)
+    yg = np.tanh(y + 0.05 * rs.randn(B, T)).astype(np.float32)
+    old = sb.loss.hp
+    sb.loss.set_hparams(sb.RETUNEGAN.replace(envelope_pool_k=k))
+    try:
+        for mode, fn, ref in ((0, sb.envelope_loss, O.rtg_envelope_loss), (1, sb.dynamic_loss, O.rtg_dynamic_loss)):
+            tg = torch.from_numpy(yg).cuda().requires_grad_(True)
+            loss = fn(torch.from_numpy(y).cuda(), tg)
+            loss.backward()
+            want = ref(y, yg, k)
+            assert abs(loss.item() - want) < 1e-5 * abs(want) + 1e-9
+            np.testing.assert_allclose(tg.grad.cpu().numpy(), O.rtg_pool_loss_backward(y, yg, mode, k), rtol=1e-5, atol=1e-10)
+    finally:
+        sb.loss.set_hparams(old)
