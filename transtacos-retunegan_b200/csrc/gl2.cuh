@@ -335,16 +335,16 @@ __device__ __forceinline__ void gl2_pass(const PlanDev& p, const Gl2Args& a, Gl2
             const int kb = C::kNz - k;
             const float2 a0 = __ldg(a.spec + rowA + k), b0 = __ldg(a.spec + rowB + k);
             const float2 a1 = __ldg(a.spec + rowA + kb), b1 = __ldg(a.spec + rowB + kb);
-            L.tAa = make_float2(a0.x * mA, a0.y * mA);
-            L.tBa = make_float2(b0.x * mB, b0.y * mB);
-            L.tAb = make_float2(a1.x * mA, a1.y * mA);
-            L.tBb = make_float2(b1.x * mB, b1.y * mB);
+            L.tAa = a0;   // raw: the masks are applied where the values are used -- a multiply here would wait for the
+            L.tBa = b0;   // load at once and undo the one-trip-ahead fetch
+            L.tAb = a1;
+            L.tBb = b1;
           } else if constexpr (MODE == 1) {   // magnitudes and initial phases: without this the loads sit behind each sincospif
             const int kb = C::kNz - k;
-            L.sAa = __ldg(a.S + rowA + k) * mA;
-            L.sBa = __ldg(a.S + rowB + k) * mB;
-            L.sAb = __ldg(a.S + rowA + kb) * mA;
-            L.sBb = __ldg(a.S + rowB + kb) * mB;
+            L.sAa = __ldg(a.S + rowA + k);    // raw: masked at the use (see above)
+            L.sBa = __ldg(a.S + rowB + k);
+            L.sAb = __ldg(a.S + rowA + kb);
+            L.sBb = __ldg(a.S + rowB + kb);
             L.tAa.x = __ldg(a.init_phase + rowA + k);
             L.tBa.x = __ldg(a.init_phase + rowB + k);
             L.tAb.x = __ldg(a.init_phase + rowA + kb);
@@ -354,10 +354,10 @@ __device__ __forceinline__ void gl2_pass(const PlanDev& p, const Gl2Args& a, Gl2
             const int km = (C::kNz - k) & (C::kNz - 1), kb = C::kNz - k;
             L.zk = zp[k];
             L.zr = zp[km];
-            L.sAa = __ldg(a.S + rowA + k) * mA;
-            L.sBa = __ldg(a.S + rowB + k) * mB;
-            L.sAb = __ldg(a.S + rowA + kb) * mA;
-            L.sBb = __ldg(a.S + rowB + kb) * mB;
+            L.sAa = __ldg(a.S + rowA + k);    // raw: masked at the use (see above)
+            L.sBa = __ldg(a.S + rowB + k);
+            L.sAb = __ldg(a.S + rowA + kb);
+            L.sBb = __ldg(a.S + rowB + kb);
             L.tAa = L.tBa = L.tAb = L.tBb = make_float2(0.f, 0.f);
             if constexpr (MODE == 3) {
               if (!a.first) {
@@ -391,11 +391,17 @@ __device__ __forceinline__ void gl2_pass(const PlanDev& p, const Gl2Args& a, Gl2
                 a.tprev[rowB + kb] = make_float2(phi(Q.re), phi(Q.im));
               }
             }
-            P = gl2_update<MODE>(P, L.sAa, L.sBa, L.tAa, L.tBa, a.alpha, a.first, k & 3, false);
-            Q = gl2_update<MODE>(Q, L.sAb, L.sBb, L.tAb, L.tBb, a.alpha, a.first, (4 - (k & 3)) & 3, true);
+            P = gl2_update<MODE>(P, L.sAa * mA, L.sBa * mB, L.tAa, L.tBa, a.alpha, a.first, k & 3, false);
+            Q = gl2_update<MODE>(Q, L.sAb * mA, L.sBb * mB, L.tAb, L.tBb, a.alpha, a.first, (4 - (k & 3)) & 3, true);
           } else {
-            P = gl2_fetch_v<MODE>(L.sAa, L.sBa, L.tAa, L.tBa, k & 3, false);
-            Q = gl2_fetch_v<MODE>(L.sAb, L.sBb, L.tAb, L.tBb, (4 - (k & 3)) & 3, true);
+            if constexpr (MODE == 0) {
+              P = gl2_fetch_v<MODE>(0.f, 0.f, make_float2(L.tAa.x * mA, L.tAa.y * mA), make_float2(L.tBa.x * mB, L.tBa.y * mB), k & 3, false);
+              Q = gl2_fetch_v<MODE>(0.f, 0.f, make_float2(L.tAb.x * mA, L.tAb.y * mA), make_float2(L.tBb.x * mB, L.tBb.y * mB),
+                                    (4 - (k & 3)) & 3, true);
+            } else {
+              P = gl2_fetch_v<MODE>(L.sAa * mA, L.sBa * mB, L.tAa, L.tBa, k & 3, false);
+              Q = gl2_fetch_v<MODE>(L.sAb * mA, L.sBb * mB, L.tAb, L.tBb, (4 - (k & 3)) & 3, true);
+            }
           }
           if (k == 0) {   // irfft ignores the imaginary parts of DC and Nyquist
             P.im = 0ull;
