@@ -526,6 +526,23 @@ __device__ __forceinline__ void gl2_pass(const PlanDev& p, const Gl2Args& a, Gl2
         });
       });
     }
+    // the next tile of this group starts by staging its signal: pull it towards L1 now (multi-launch path: the buffers were
+    // written by the previous launch and sit in L2)
+    if constexpr (MODE >= 2 && !COH) {
+      const long long nvt = vt + static_cast<long long>(gridDim.x) * ga;
+      if (nvt < n_tiles) {
+        const int nb = static_cast<int>(nvt / a.tiles_per_row), ntk = static_cast<int>(nvt - static_cast<long long>(nb) * a.tiles_per_row);
+        const GlRow nrow = gl_row(a.g, nb, N, hop);
+        if (ntk * FT < nrow.T) {
+          const long long nbase = gl2_sig_base(nrow, nb, hop, C::kWin) + static_cast<long long>(ntk) * FT * hop;
+          const int nbytes = ((FT - 1) * hop + C::kWin) * 4;
+          for (int o = gt * 128; o < nbytes; o += GT * 128) {
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(a.ya_in + nbase) + o));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(a.yb_in + nbase) + o));
+          }
+        }
+      }
+    }
     gl2_group_sync(group);
     // ---- 3. overlap-add of the tile's frames, written as this tile's span of the signal ----------------------------
     {
