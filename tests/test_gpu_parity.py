@@ -413,3 +413,39 @@ def test_feature_kernel_other_configurations(sb, n_fft, win, hop, window):
             _close(np.exp(ml), np.exp(O.rtg_get_mel(y, hp=hp)))
     finally:
         A.set_hparams(old)
+
+
+def _run_variant(env, code):
+    """Run `code` in a fresh interpreter with extra environment (the kernel-selection switches are read once per process)."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.TemporaryDirectory() as td:
+        out = os.path.join(td, "out.npz")
+        full = "import sys, numpy as np\nsys.path.insert(0, %r)\nimport transtacos_retunegan_b200 as sb\nfrom oracle import spectral_oracle as O\n" % root
+        full += code + "\nnp.savez(%r, **res)\n" % out
+        r = subprocess.run([sys.executable, "-c", full], env=dict(os.environ, **env), capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        return dict(np.load(out))
+
+
+def test_kernel_variants_agree(sb):
+    """The alternative code paths kept for A/B measurements compute the same thing: persistent / per-iteration Griffin-Lim launches
+    (bit-exact: same arithmetic per tile, the signal is only read through a different cache), one / two tile groups per SM,
+    and the single-role feature kernel against the warp-specialised one (same magnitudes; the mel sums differ in summation order)."""
+    code = ("y = O.synth_speechlike(110335, 114514)\n"
+            "S, M = sb.transtacos_audio.get_specs(y)\n"
+            "w30 = sb.transtacos_audio.inv_spec(S, init_phase=np.random.RandomState(1).rand(1025, 431))\n"
+            "w4 = sb.retunegan_audio.inv_mag(sb.retunegan_audio.get_mag(y), wavlen=110335)\n"
+            "res = dict(S=S, M=M, w30=w30, w4=w4)")
+    base = _run_variant({}, code)
+    multi = _run_variant({"SB200_GL_PERSISTENT": "0"}, code)
+    two = _run_variant({"SB200_GL_ONE_GROUP": "0"}, code)
+    for k in ("w30", "w4"):
+        np.testing.assert_array_equal(base[k], multi[k])
+        np.testing.assert_array_equal(base[k], two[k])
+    f2 = _run_variant({"SB200_FEAT_KERNEL": "2"}, code)
+    np.testing.assert_array_equal(base["S"], f2["S"])
+    np.testing.assert_allclose(base["M"], f2["M"], rtol=0, atol=2e-5)
