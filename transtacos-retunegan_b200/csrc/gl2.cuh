@@ -126,11 +126,10 @@ __device__ __forceinline__ PC gl2_update(const PC& X, float sA, float sB, float2
       o.im = pk(nA > 0.f ? plo(o.im) : sA * un.y, nB > 0.f ? phi(o.im) : sB * un.y);
     }
   } else {                     // librosa.griffinlim: c = rebuilt - alpha * tprev; angles = c / (|c| + 1e-16)
-    PC c = X;
-    if (!first) {
-      c.re = fma2s(pk(tA.x, tB.x), -alpha, X.re);
-      c.im = fma2s(pk(tA.y, tB.y), -alpha, X.im);
-    }
+    // tprev is loaded as zero on the first iteration (rebuilt = 0): the update is then exactly X, without a select
+    PC c;
+    c.re = fma2s(pk(tA.x, tB.x), -alpha, X.re);
+    c.im = fma2s(pk(tA.y, tB.y), -alpha, X.im);
     const pf n2 = norm2(c);
     // MUFU sqrt / reciprocal (~1e-7 relative): far inside the Griffin-Lim tolerance, and branch-free
     const pf sc = pk(sA * gl2_rcp(fast_sqrt(plo(n2)) + 1e-16f), sB * gl2_rcp(fast_sqrt(phi(n2)) + 1e-16f));
