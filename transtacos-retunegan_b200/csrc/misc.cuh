@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(256) frame_stats_kernel(const FrameStatsArgs a
 // one 16-byte broadcast load of y[j..j+3] plus four 4-byte loads for 16 multiply-adds.  The frame is kept twice: in natural
 // order (broadcast side) and de-interleaved by 4 (plane c holds y[4i+c]: the lane-strided side is then consecutive across the
 // threads, conflict free).  The energy terms come from a prefix sum of y^2 (as librosa's cumsum does).
-constexpr int kYinThreads = 128;
+constexpr int kYinThreads = 96;       // 76 lag groups at the reference settings: 3 warps (128 threads: 0.53 ms, 96: 0.44 ms per 64 x 5 s)
 constexpr int kYinMaxFrame = 4096;   // samples per frame the shared-memory layout supports
 struct YinArgs {
   const float* x;
