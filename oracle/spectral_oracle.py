@@ -9,6 +9,11 @@ What it restates (all paths relative to /root/reference):
   * transtacos/audio.py:64-97,130-196   (preemphasis, get_specs, inv_spec, Griffin-Lim)
   * retunegan/audio.py:19-21,116-170    (get_mag, get_mel, mag_to_mel, inv_mag, get_stft_torch)
   * retunegan/models/loss.py:22-62      (multi_stft_loss) + its closed-form backward
+  * the widened rows: transtacos/audio.py:59-61,100-128,164-175 (trim_silence, inv_mel, get_f0, get_c0,
+    quantisers, linear basis), retunegan/audio.py:98-113 (get_zcr, get_c0, get_uv), retunegan/models/loss.py:66-82
+    (envelope_loss, dynamic_loss + closed-form backward); librosa 0.8.1 ``feature.rms / feature.zero_crossing_rate /
+    effects.trim / yin`` restated (parity unpinned upstream; the audio.py / loss.py layer is pinned by
+    tests/golden/make_golden_side.py)
   * the third-party layer those files call and that is NOT vendored in the
     reference: librosa==0.8.1 (requirements.txt:1) ``stft / istft / griffinlim /
     filters.mel / feature.melspectrogram / filters.window_sumsquare``, restated
