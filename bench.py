@@ -88,13 +88,14 @@ def cpu_reference_rate(kind, n_utt, L, cores):
 
 
 def _torch_ref_mstft(y, yg):
-    """The reference's multi_stft_loss graph (retunegan/models/loss.py:22-62) in plain torch on the CPU."""
+    """The reference's multi_stft_loss graph (retunegan/models/loss.py:22-62) in plain torch, on the device of its inputs
+    (CPU for the reference arm; on the GPU it is the torch / cuFFT comparator of SURVEY.md 8d)."""
     import torch
     from oracle import spectral_oracle as O
     loss = 0
     for n_fft, win, hop in O.HP.multi_stft_params:
-        w = torch.hann_window(win)
-        mb = torch.from_numpy(O.mel_basis(n_fft))
+        w = torch.hann_window(win, device=y.device)
+        mb = torch.from_numpy(O.mel_basis(n_fft)).to(y.device)
 
         def f(x):
             D = torch.stft(x, n_fft, hop, win, window=w, center=True, pad_mode="reflect", return_complex=True)
@@ -546,6 +547,21 @@ def main():
                 del ww
             except Exception as ex:   # secondary numbers must never break the contract line
                 extra[key] = {"error": repr(ex)[:200]}
+        try:   # the reference's own torch formulation on the same GPU (cuFFT + ~60 small kernels): comparator only
+            yt = (0.1 * torch.randn(16, 22050, device="cuda")).clamp_(-0.999, 0.999)
+            ygt = torch.tanh(yt + 0.01 * torch.randn_like(yt)).requires_grad_(True)
+
+            def torch_step(i):
+                ygt.grad = None
+                _torch_ref_mstft(yt, ygt).backward()
+                return ygt.grad
+            d, _ = time_steps(torch, torch_step, 30, 5, lambda: None)
+            extra["mstft_fwd_bwd_16x22050_lossonly_torch_cufft"] = {
+                "value": 16 * 22050 / SR * 30 / d, "unit": UNIT, "ms_per_step": 1e3 * d / 30,
+                "note": "comparator: the reference's multi_stft_loss graph through torch.stft (cuFFT) + autograd on the same GPU; "
+                        "not this repo's code path"}
+        except Exception as ex:
+            extra["mstft_fwd_bwd_16x22050_lossonly_torch_cufft"] = {"error": repr(ex)[:200]}
     sampler.stop_flag = True
 
     cpu_baseline = None
