@@ -562,6 +562,26 @@ def main():
                         "not this repo's code path"}
         except Exception as ex:
             extra["mstft_fwd_bwd_16x22050_lossonly_torch_cufft"] = {"error": repr(ex)[:200]}
+        try:   # get_specs (transtacos/audio.py:73-77) written with torch ops on the same GPU: cuFFT + dense mel GEMM comparator
+            from oracle import spectral_oracle as O
+            yb = (0.1 * torch.randn(64, L5, device="cuda")).clamp_(-0.999, 0.999)
+            wnd = torch.hann_window(WIN, device="cuda")
+            mbt = torch.from_numpy(O.mel_basis(N_FFT)).cuda()
+
+            def torch_specs(i):
+                x = torch.cat([yb[:, :1], yb[:, 1:] - 0.97 * yb[:, :-1]], dim=1)
+                D = torch.stft(x, N_FFT, HOP, WIN, window=wnd, center=True, pad_mode="reflect", return_complex=True).abs()
+                S = 8.0 * ((20.0 * torch.log10(D.clamp_min(1e-5)) - 20.0 + 100.0) / 100.0) - 4.0
+                M = 8.0 * ((20.0 * torch.log10((mbt @ D).clamp_min(1e-5)) - 20.0 + 100.0) / 100.0) - 4.0
+                return S, M
+            d, _ = time_steps(torch, torch_specs, 30, 5, lambda: None)
+            extra["stft_mel_64x5s_torch_cufft"] = {
+                "value": 64 * L5 / SR * 30 / d, "unit": UNIT, "ms_per_step": 1e3 * d / 30,
+                "note": "comparator: get_specs written with torch ops (torch.stft / cuFFT, dense mel GEMM, elementwise) on the same GPU; "
+                        "not this repo's code path"}
+            del yb
+        except Exception as ex:
+            extra["stft_mel_64x5s_torch_cufft"] = {"error": repr(ex)[:200]}
     sampler.stop_flag = True
 
     cpu_baseline = None
