@@ -387,7 +387,7 @@ class HostFeaturePipeline:
     ``get_specs`` / ``get_mag`` use for 2-D host input, and what bench.py times as the end-to-end number.
     """
 
-    def __init__(self, plan: Plan, L: int, chunk: int = 8, depth: int = 3):
+    def __init__(self, plan: Plan, L: int, chunk: int = 16, depth: int = 3):
         self.plan, self.L, self.chunk, self.depth = plan, int(L), int(chunk), int(depth)
         dev = require_cuda()
         self.T = 1 + self.L // plan.hop_length
@@ -409,8 +409,17 @@ class HostFeaturePipeline:
         plan, T = self.plan, self.T
         cur = torch.cuda.current_stream()
         self.s_in.wait_stream(cur)
-        for c, b0 in enumerate(range(0, B, self.chunk)):
-            n = min(self.chunk, B - b0)
+        # ramp-up schedule: a quarter and a half chunk first (the copy-back, which bounds the pipeline, starts early), full
+        # chunks afterwards (few launches / cross-stream waits)
+        sched, b0 = [], 0
+        for n in (max(1, self.chunk // 4), max(1, self.chunk // 2)):
+            if b0 < B:
+                sched.append((b0, min(n, B - b0)))
+                b0 += sched[-1][1]
+        while b0 < B:
+            sched.append((b0, min(self.chunk, B - b0)))
+            b0 += sched[-1][1]
+        for c, (b0, n) in enumerate(sched):
             s = c % self.depth
             with torch.cuda.stream(self.s_in):
                 if self.used[s]:
@@ -442,7 +451,7 @@ class HostFeaturePipeline:
 _pipelines = {}
 
 
-def host_feature_pipeline(plan: Plan, L: int, chunk: int = 8) -> HostFeaturePipeline:
+def host_feature_pipeline(plan: Plan, L: int, chunk: int = 16) -> HostFeaturePipeline:
     key = (plan.key, plan.device_index, int(L), int(chunk))
     p = _pipelines.get(key)
     if p is None:

@@ -149,7 +149,7 @@ def _host_batch(y):
 
 
 def features_host(cfg: SpectralConfig, y_host: torch.Tensor, preemph, mag_scale, mel_scale, want_mag=True,
-                  want_mel=True, out=None, chunk=8):
+                  want_mel=True, out=None, chunk=16):
     """Host-resident [B, L] batch -> host features through the chunked copy/compute pipeline.
     ``out=(mag [B*T, F], mel [B*T, n_mel])`` lets the caller supply (pinned) destinations; returns CPU tensors."""
     plan = core.get_plan(cfg)
