@@ -425,6 +425,7 @@ def main():
     import transtacos_retunegan_b200 as sb
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
+    numa_bound = sb.sharding.bind_to_gpu_numa(local) if world > 1 else False   # before any pinned allocation
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -597,7 +598,8 @@ def main():
             "metric": METRIC, "value": total_units * a.steps / dev_s, "unit": UNIT, "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * dev_s / a.steps, "higher_is_better": True,
             "scaling": "strong" if a.workload == "corpus" else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(config, workload=w.name, per_gpu=w.name, l2=w.note, **({"ddp": ddp_info} if ddp_info else {})),
+            "config": dict(config, workload=w.name, per_gpu=w.name, l2=w.note, **({"ddp": ddp_info} if ddp_info else {}),
+                           **({"numa_bound": bool(numa_bound)} if world > 1 else {})),
             "clocks": sampler.summary(window),
             "e2e": e2e, "gpu_launches": int(timed_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -52,3 +52,25 @@ def reduce_mean_scalar(x: torch.Tensor) -> torch.Tensor:
     y = x.detach().clone()
     torch.distributed.all_reduce(y, op=torch.distributed.ReduceOp.SUM)
     return y / world
+
+
+def bind_to_gpu_numa(local_rank: int) -> bool:
+    """Pin this process to the CPUs that are local to its GPU (NVML's ideal CPU affinity) BEFORE it allocates pinned host
+    memory: first-touch then places the staging buffers on the GPU's NUMA node, so that the ranks of one box do not
+    share one socket's memory controllers for their host<->device copies.  Returns False (and changes nothing) when
+    NVML or the affinity call is unavailable."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(local_rank))
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1}
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return False
+        os.sched_setaffinity(0, allowed)
+        return True
+    except Exception:
+        return False
