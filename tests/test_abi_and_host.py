@@ -127,3 +127,15 @@ def test_shard_utterances_balanced_and_deterministic(sb):
     assert [len(s) for s in sb.sharding.shard_utterances([1, 1], 4)] == [1, 1, 0, 0]
     with pytest.raises(ValueError):
         sb.sharding.shard_utterances([1], 0)
+
+
+def test_numa_binding_is_a_no_op_without_nvml():
+    """sharding.bind_to_gpu_numa never raises: without a GPU / NVML it reports False and leaves the affinity alone."""
+    import os
+    import transtacos_retunegan_b200 as sb
+    before = os.sched_getaffinity(0)
+    ok = sb.sharding.bind_to_gpu_numa(0)
+    assert ok in (True, False)
+    if not ok:
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)
