@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """bench.py -- spectrogram-seconds per second of the spectral hot path on N B200s (one JSON line on rank 0).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload stft_mel|griffinlim|griffinlim_batch|mstft]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload stft_mel|griffinlim|griffinlim_batch|mstft|corpus ...]
                     [--impl reference] [--no-extra]
 
 Default workload = BASELINE.json configs[2]: batched STFT + mel feature extraction (TransTacoS get_specs:
@@ -12,6 +12,13 @@ host<->device copies inside the timed region.  Utterances shard across ranks wit
 scaling: every rank owns 64 utterances).  `--impl reference` times the CPU oracle restatement of the reference's
 librosa/numpy path (the reference itself cannot be installed: librosa / TF are absent and there is no network) on
 all host cores, the way the reference parallelises it (process pool over utterances, databaker.py:31).
+
+`extra` (every N, not only N = 1) carries the other BASELINE.json configs on the same box in the same run, each timed
+between barriers as the max over ranks, with its own clocks, HBM and FP32-pipe roofline fractions: Griffin-Lim (single
+utterance both forms, 64-utterance batch, weak), the multi-resolution STFT loss forward + backward (loss-only and training
+variant; under torchrun with the loss all-reduce inside the step and DDP's 11 MB gradient all-reduce timed beside it) and the
+10 000-utterance corpus (STRONG scaling: the corpus is sharded over the ranks, per-rank load max / min reported).
+Before anything is timed one row of every workload's output is compared with the CPU oracle (the checker, not timed).
 """
 import argparse
 import json
@@ -138,7 +145,7 @@ class ClockSampler(threading.Thread):
                             self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.01)
+            time.sleep(0.003)
 
     def summary(self, window):
         if not self.samples:
@@ -159,6 +166,8 @@ class Workload:
     launches_dominant_per_step = 1
     h2d = d2h = 0
     note = ""
+    flops = 0.0            # algorithmic FP32 FLOPs per step per rank
+    load = None            # corpus: audio seconds of this rank's shard
 
 
 def make_stft_mel(sb, torch, B=64, rot=6):
@@ -197,7 +206,22 @@ def make_stft_mel(sb, torch, B=64, rot=6):
     w.d2h = B * T5 * (F + N_MEL) * 4
     w.note = (f"{rot} rotating input/output sets ({rot * (w.alg_bytes) / 1e6:.0f} MB) > 126 MB L2 between reuses; "
               "TransTacoS epilogue (pre-emphasis 0.97, dB-normalise)")
-    w.check = lambda: (torch.isfinite(mags[0]).all().item() and torch.isfinite(mels[0]).all().item())
+    w.flops = B * T5 * 66e3                                       # ~66 kFLOP per frame
+
+    def check():
+        """rows 0 and B-1 of the exact timed launch against the oracle (tolerance of the parity tests: 1e-4 relative)."""
+        from oracle import spectral_oracle as O
+        step(0)
+        torch.cuda.synchronize()
+        for b in (0, B - 1):
+            So, Mo = O.tt_get_specs(ys[0][b].cpu().numpy())
+            S = mags[0].view(B, T5, F)[b].t().cpu().numpy()
+            M = mels[0].view(B, T5, N_MEL)[b].t().cpu().numpy()
+            e1, e2 = np.linalg.norm(S - So) / np.linalg.norm(So), np.linalg.norm(M - Mo) / np.linalg.norm(Mo)
+            if not (e1 < 1e-4 and e2 < 1e-4):
+                return False, f"row {b}: rel-Frobenius mag {e1:.2e} mel {e2:.2e}"
+        return True, "rows 0 and B-1 of the timed launch vs oracle tt_get_specs: rel-Frobenius < 1e-4"
+    w.check = check
     return w
 
 
@@ -229,7 +253,22 @@ def make_griffinlim(sb, torch, B=1, form="rtg", rot=4):
     w.launches_dominant_per_step = n_iter
     w.h2d, w.d2h = F * T5 * 4, L5 * 4
     w.note = f"{'fast form, momentum 0.7' if frm else 'angle form'}; {n_iter} iterations + initial/final ISTFT; state L2/HBM resident"
-    w.check = lambda: torch.isfinite(step(0)).all().item()
+    w.flops = B * T5 * 134e3 * (n_iter + 0.5)                    # ~134 kFLOP per frame and iteration
+
+    def check():
+        """row 0 of the timed call against the oracle, same initial phase: waveform rel-L2 <= 1e-3 (parity-test tolerance)."""
+        from oracle import spectral_oracle as O
+        out = step(0).view(B, -1)[0].cpu().numpy()
+        S0 = Ss[0].view(B, T5, F)[0].t().cpu().numpy().astype(np.float64)
+        p0 = ph.view(B, T5, F)[0].t().cpu().numpy().astype(np.float64)
+        if form == "rtg":
+            ref = O.griffinlim(S0, n_iter=n_iter, hop_length=HOP, win_length=WIN, length=L5, momentum=mom,
+                               init_angles=np.exp(2j * np.pi * p0))
+        else:
+            ref = O.tt_griffin_lim(S0, init_phase=p0, n_iter=n_iter)
+        e = np.linalg.norm(out - ref) / np.linalg.norm(ref)
+        return bool(e < 1e-3), f"row 0 vs oracle Griffin-Lim ({n_iter} it), waveform rel-L2 {e:.2e}"
+    w.check = check
     return w
 
 
@@ -260,7 +299,22 @@ def make_mstft(sb, torch, B=16, T=22050, specs=False, rot=4, ddp=False):
     w.dominant = "mstft_fwd_kernel+mstft_bwd_kernel (3 resolutions)"
     w.note = ("loss-only" if not specs else "training variant: spec stacks written, dense upstream spec grads") + \
         ("; the reported loss is averaged over the ranks with one NCCL all-reduce of a scalar inside the step" if ddp else "")
-    w.check = lambda: torch.isfinite(step(0)).all().item()
+    w.flops = (0.49e9 + 0.25e9) * (B / 16) * (T / 22050)
+
+    def check():
+        """loss value and d loss / d y_g of the timed batch against the oracle (1e-5 / 1e-4, the parity-test tolerances)."""
+        from oracle import spectral_oracle as O
+        ygs[0].grad = None
+        loss = sb.multi_stft_loss(ys[0], ygs[0], ret_loss=True)
+        loss.backward()
+        yn, gn = ys[0].cpu().numpy(), ygs[0].detach().cpu().numpy()
+        lo = O.rtg_multi_stft_loss(yn, gn, ret_loss=True)
+        go = O.rtg_multi_stft_loss_backward(yn, gn)
+        e1 = abs(loss.item() - lo) / abs(lo)
+        e2 = np.linalg.norm(ygs[0].grad[:, 0].cpu().numpy() - go) / np.linalg.norm(go)
+        ygs[0].grad = None
+        return bool(e1 < 1e-5 and e2 < 1e-4), f"loss rel {e1:.1e}, grad rel-L2 {e2:.1e} vs oracle"
+    w.check = check
     return w
 
 
@@ -344,7 +398,26 @@ def make_corpus(sb, torch, rank, world, n_utt=10000, chunk=256, d2h=False):
               "features + ln-magnitude + Griffin-Lim (4 it, m 0.7, device-drawn initial phase); " +
               ("features and wavs copied to pinned host memory chunk by chunk (copy stream, double-buffered)" if d2h
                else "outputs stay in HBM"))
-    w.check = lambda: torch.isfinite(step(0)).all().item()
+    w.flops = nf * (2 * 66e3 + 134e3 * 4.5)
+    w.load = float(L.sum()) / SR
+
+    def check():
+        """first utterance of the first ragged chunk: features against the oracle."""
+        from oracle import spectral_oracle as O
+        ok = bool(torch.isfinite(step(0)).all().item())
+        torch.cuda.synchronize()
+        batch = chunks[0][0]
+        l0, t0 = int(batch.lens[0]), int(batch.frames[0])
+        y0 = batch.x[:l0].cpu().numpy()
+        cur = torch.cuda.current_stream()
+        sb._lib.check(lib.sb200_stft_features(plan.handle, sb.core.ptr(batch.x), C.byref(batch.c), float(ta.hp.preemphasis),
+                                              sc_db, sc_db, sb.core.ptr(mags[0]), sb.core.ptr(mels[0]), None, sb.core.stream_ptr()))
+        cur.synchronize()
+        So, Mo = O.tt_get_specs(y0)
+        e1 = np.linalg.norm(mags[0][:t0].t().cpu().numpy() - So) / np.linalg.norm(So)
+        e2 = np.linalg.norm(mels[0][:t0].t().cpu().numpy() - Mo) / np.linalg.norm(Mo)
+        return bool(ok and e1 < 1e-4 and e2 < 1e-4), f"utterance 0 of the ragged chunk vs oracle: mag {e1:.1e} mel {e2:.1e}; wavs finite"
+    w.check = check
     return w
 
 
@@ -368,6 +441,41 @@ def time_steps(torch, fn, steps, warmup, barrier):
     return e0.elapsed_time(e1) / 1e3, wall
 
 
+def link_probe(torch, h2d_bytes, d2h_bytes, barrier, allmax, reps=6):
+    """The host-link ceiling of the end-to-end step, measured with NO kernels: the step's own H2D and D2H byte counts moved
+    between pinned host memory and HBM on two streams at once, every rank at the same time (max over ranks).  Returns
+    the time such a step needs on the link alone plus the one-direction bandwidths."""
+    dev_in = torch.empty(h2d_bytes, dtype=torch.uint8, device="cuda")
+    dev_out = torch.empty(d2h_bytes, dtype=torch.uint8, device="cuda")
+    host_in = torch.empty(h2d_bytes, dtype=torch.uint8).pin_memory()
+    host_out = torch.empty(d2h_bytes, dtype=torch.uint8).pin_memory()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def run(do_in, do_out):
+        torch.cuda.synchronize()
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            if do_in:
+                with torch.cuda.stream(s1):
+                    dev_in.copy_(host_in, non_blocking=True)
+            if do_out:
+                with torch.cuda.stream(s2):
+                    host_out.copy_(dev_out, non_blocking=True)
+        torch.cuda.synchronize()
+        return allmax(time.perf_counter() - t0) / reps
+    run(True, True)
+    t_in, t_out, t_both = run(True, False), run(False, True), run(True, True)
+    return {"h2d_gbs": h2d_bytes / t_in / 1e9, "d2h_gbs": d2h_bytes / t_out / 1e9,
+            "both_ms": 1e3 * t_both, "link_gbs": (h2d_bytes + d2h_bytes) / t_both / 1e9}
+
+
+def fp32_peak_tflops(sm_mhz):
+    """Non-tensor FP32 peak: 148 SMs x 128 FMA lanes x 2 FLOP at the maximum SM clock."""
+    return 148 * 128 * 2 * (sm_mhz or 1965.0) * 1e6 / 1e12
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -375,7 +483,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="stft_mel", choices=["stft_mel", "griffinlim", "griffinlim_tt",
-                                                               "griffinlim_batch", "mstft", "mstft_specs", "corpus"])
+                                                               "griffinlim_batch", "mstft", "mstft_specs", "corpus", "corpus_d2h"])
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--kernel-only", action="store_true", help="profiling runs: skip e2e, extra workloads and the CPU baseline")
     a = ap.parse_args()
@@ -384,11 +492,12 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     cores = len(os.sched_getaffinity(0))
     cpu_kind = {"stft_mel": "stft_mel", "griffinlim": "griffinlim", "griffinlim_tt": "griffinlim",
-                "griffinlim_batch": "griffinlim", "mstft": "mstft", "mstft_specs": "mstft", "corpus": "griffinlim"}[a.workload]
+                "griffinlim_batch": "griffinlim", "mstft": "mstft", "mstft_specs": "mstft", "corpus": "griffinlim",
+                "corpus_d2h": "griffinlim"}[a.workload]
     workload_name = {"stft_mel": "stft_mel_64x5s", "griffinlim": "griffinlim_rtg_1x5s_4it",
                      "griffinlim_tt": "griffinlim_tt_1x5s_30it", "griffinlim_batch": "griffinlim_rtg_64x5s_4it",
                      "mstft": "mstft_fwd_bwd_16x22050_lossonly", "mstft_specs": "mstft_fwd_bwd_16x22050_specs",
-                     "corpus": "corpus_10000utt_specs+griffinlim"}[a.workload]
+                     "corpus": "corpus_10000utt_specs+griffinlim", "corpus_d2h": "corpus_10000utt_specs+griffinlim"}[a.workload]
 
     config = {"workload": workload_name, "per_gpu": workload_name, "sample_rate": SR, "n_fft": N_FFT, "hop": HOP, "win": WIN,
               "n_mel": N_MEL, "sharding": "utterances per rank, no data-path collective"}
@@ -396,10 +505,11 @@ def main():
     if a.impl == "reference":
         # The reference's own CPU implementation of the path (oracle port: librosa / TF are not installable) on
         # all host cores, parallelised as the reference does (process pool over utterances).  A step is a bounded sample of
-        # the workload: 8 utterances per core (~0.3 s); at most 20 steps so the run ends within minutes.
+        # the workload (the workload's own 64 utterances for stft_mel, rounded up to a whole number per core); at most 20
+        # steps so the run ends within minutes.
         if rank != 0:
             return
-        n_utt = {"stft_mel": max(8 * cores, 64), "griffinlim": max(2 * cores, 16), "mstft": 64}[cpu_kind]
+        n_utt = {"stft_mel": cores * ((64 + cores - 1) // cores), "griffinlim": max(2 * cores, 16), "mstft": 64}[cpu_kind]
         cpu_reference_rate(cpu_kind, max(cores, 16), L5, cores)          # warm-up step (imports, page-in)
         vals, t_tot = [], 0.0
         for _ in range(max(1, min(a.steps, 20))):
@@ -436,17 +546,20 @@ def main():
         if dist is not None:
             dist.all_reduce(sync_t)
 
-    def allsum(x):
+    def allred(x, op=None):
         t = torch.tensor([x], device="cuda", dtype=torch.float64)
         if dist is not None:
-            dist.all_reduce(t)
+            dist.all_reduce(t, op=op or dist.ReduceOp.SUM)
         return float(t.item())
 
+    def allsum(x):
+        return allred(x)
+
     def allmax(x):
-        t = torch.tensor([x], device="cuda", dtype=torch.float64)
-        if dist is not None:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return allred(x, dist.ReduceOp.MAX if dist is not None else None)
+
+    def allmin(x):
+        return allred(x, dist.ReduceOp.MIN if dist is not None else None)
 
     makers = {"stft_mel": lambda: make_stft_mel(sb, torch), "griffinlim": lambda: make_griffinlim(sb, torch, 1, "rtg"),
               "griffinlim_tt": lambda: make_griffinlim(sb, torch, 1, "tt"),
@@ -455,46 +568,66 @@ def main():
               "mstft_specs": lambda: make_mstft(sb, torch, specs=True, ddp=world > 1),
               "corpus": lambda: make_corpus(sb, torch, rank, world),
               "corpus_d2h": lambda: make_corpus(sb, torch, rank, world, d2h=True)}
-    w = makers[a.workload]()
-    assert w.check(), "workload produced non-finite output"
-
     sampler = ClockSampler(local)
     sampler.start()
-    # warm-up happens inside time_steps; sample clocks from the start of warm-up to the end of the timed region
-    sampler.active = True
-    l0 = sb._lib.launch_count()
-    dev_s, wall_s = time_steps(torch, w.step, a.steps, a.warmup, barrier)
-    launches = sb._lib.launch_count() - l0
-    window = "warmup+timed"
-    # very short timed region: keep the same loop running ~1 s to catch the clocks under load.  The decision and the number of
-    # extra steps are agreed over the ranks (a step may contain a collective: a rank-local, time-based loop would deadlock).
-    if allmax(1.0 if len(sampler.samples) < 5 else 0.0) > 0:
-        n_cont = int(min(20000, max(1, 1.0 / max(allmax(dev_s) / a.steps, 1e-6))))
-        for i in range(n_cont):
-            w.step(i)
-            if i % 64 == 63:
-                torch.cuda.synchronize()
-        torch.cuda.synchronize()
-        window = "warmup+timed+1s continuation of the same loop"
-    sampler.active = False
-    dev_s = allmax(dev_s)
-    total_units = allsum(w.units)          # audio seconds per step over all ranks (corpus shards differ slightly)
-    timed_launches = launches * a.steps // (a.steps + a.warmup)
-
-    # dominant kernel duration, live: for single-kernel steps it is the step; otherwise re-time it alone is not possible
-    # from Python, so the per-launch duration is the device time of the step divided by its dominant launches (upper bound).
-    kern_s = dev_s / a.steps / w.launches_dominant_per_step
     peak, peak_src = peaks()
+    fp32_peak = fp32_peak_tflops(sampler.sm_max)
+
+    def checked(mk):
+        """Build a workload and compare one row of its output with the oracle (rank 0; never timed).  Agreed over the ranks:
+        a step may contain a collective, so either every rank runs it or none does."""
+        w, ok, msg = None, True, ""
+        try:
+            w = mk()
+            if rank == 0:
+                ok, msg = w.check()
+        except Exception as ex:
+            ok, msg = False, repr(ex)[:300]
+        if allmin(1.0 if ok else 0.0) < 1.0:
+            raise RuntimeError(f"workload check failed on some rank (rank {rank}: {msg or 'ok'})")
+        return w, msg
+
+    def measure(w, steps, warmup, min_seconds=0.0):
+        """Timed region of one workload: device time between barriers, max over ranks; clocks sampled over the same loop."""
+        sampler.samples, sampler.reasons = [], set()
+        sampler.active = True
+        l0 = sb._lib.launch_count()
+        dev_s, wall_s = time_steps(torch, w.step, steps, warmup, barrier)
+        launches = sb._lib.launch_count() - l0
+        window = "warmup+timed"
+        # short timed region: keep the same loop running to catch the clocks under load.  The decision and the number of
+        # extra steps are agreed over the ranks (a step may contain a collective: a rank-local loop would deadlock).
+        dev_s = allmax(dev_s)
+        if allmax(1.0 if len(sampler.samples) < 5 else 0.0) > 0 or dev_s < min_seconds:
+            n_cont = int(min(20000, max(1, max(min_seconds, 0.5) / max(dev_s / steps, 1e-6))))
+            for i in range(n_cont):
+                w.step(i)
+                if i % 64 == 63:
+                    torch.cuda.synchronize()
+            torch.cuda.synchronize()
+            window = "warmup+timed+continuation of the same loop"
+        sampler.active = False
+        return dev_s, wall_s, launches * steps // (steps + warmup), sampler.summary(window)
+
+    w, check_msg = checked(makers[a.workload])
+    dev_s, wall_s, timed_launches, clocks = measure(w, a.steps, a.warmup, 1.0)
+    total_units = allsum(w.units)          # audio seconds per step over all ranks (corpus shards differ slightly)
+
+    # dominant kernel duration, live: for single-kernel steps it is the step; otherwise the per-launch duration is the device
+    # time of the step divided by its dominant launches (upper bound).
+    kern_s = dev_s / a.steps / w.launches_dominant_per_step
     achieved = w.alg_bytes / kern_s / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(a.workload)
+            tj = json.load(open(tp))
+            traffic = tj.get(a.workload)
+            traffic_src = "static: " + tj.get("_source", "profiles/traffic.json (ncu --set full capture, not measured in this run)")
         except Exception:
             traffic = None
 
-    # end to end through the public API with host buffers
+    # end to end through the public API with host buffers; the link ceiling of the same byte counts is probed beside it
     e2e = None
     if w.e2e is not None and not a.kernel_only:
         K2 = max(3, min(a.steps, 20))
@@ -508,11 +641,20 @@ def main():
         torch.cuda.synchronize()
         e2e_s = allmax(time.perf_counter() - t0)
         e2e = {"value": world * w.units * K2 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": w.h2d, "d2h_bytes_per_step": w.d2h,
-               "steps": K2, "api": "transtacos_audio.get_specs(cpu_tensor[64,L], out=pinned)" if a.workload == "stft_mel"
+               "steps": K2, "ms_per_step": 1e3 * e2e_s / K2,
+               "api": "transtacos_audio.get_specs(cpu_tensor[64,L], out=pinned)" if a.workload == "stft_mel"
                else "retunegan_audio.inv_mag(numpy)"}
+        try:
+            lp = link_probe(torch, int(w.h2d), int(w.d2h), barrier, allmax)
+            e2e.update({"link_gbs": lp["link_gbs"], "link_ms_per_step": lp["both_ms"],
+                        "frac_of_link": lp["both_ms"] / (1e3 * e2e_s / K2), "link_h2d_gbs": lp["h2d_gbs"],
+                        "link_d2h_gbs": lp["d2h_gbs"],
+                        "link_note": "the step's own H2D + D2H bytes between pinned host memory and HBM on two streams, no kernels, "
+                                     "all ranks at once, max over ranks; frac_of_link = that time / the end-to-end step time"})
+        except Exception as ex:
+            e2e["link_error"] = repr(ex)[:200]
 
-    ddp_info = None
-    if world > 1 and a.workload.startswith("mstft"):
+    def ddp_probe():
         # under DDP the generator's gradients (RefineGAN_small, ~2.75 M parameters, retunegan/hparam.py:50)
         # are all-reduced by DDP's buckets many layers after this loss; timed here on its own, next to the loss step
         gbuf = torch.zeros(2_750_000, device="cuda")
@@ -526,63 +668,80 @@ def main():
             dist.all_reduce(gbuf)
         e1.record()
         torch.cuda.synchronize()
-        ddp_info = {"generator_grad_allreduce_ms": allmax(e0.elapsed_time(e1) / 50), "generator_grad_bytes": gbuf.numel() * 4,
-                    "loss_allreduce": "one fp32 scalar per step, inside the timed step (multi_stft_loss(ddp_reduce=True))"}
-        del gbuf
+        return {"generator_grad_allreduce_ms": allmax(e0.elapsed_time(e1) / 50), "generator_grad_bytes": gbuf.numel() * 4,
+                "loss_allreduce": "one fp32 scalar per step, inside the timed step (multi_stft_loss(ddp_reduce=True))"}
+
+    ddp_info = ddp_probe() if (world > 1 and a.workload.startswith("mstft")) else None
 
     extra = {}
-    if world == 1 and not a.no_extra and not a.kernel_only and a.workload == "stft_mel":
-        for key, mk, k in (("griffinlim_rtg_1x5s_4it", makers["griffinlim"], 50),
-                           ("griffinlim_tt_1x5s_30it", makers["griffinlim_tt"], 10),
-                           ("griffinlim_rtg_64x5s_4it", makers["griffinlim_batch"], 5),
-                           ("mstft_fwd_bwd_16x22050_lossonly", makers["mstft"], 50),
-                           ("mstft_fwd_bwd_16x22050_specs", makers["mstft_specs"], 20),
-                           ("corpus_10000utt_specs+griffinlim", makers["corpus"], 2),
-                           ("corpus_10000utt_specs+griffinlim_d2h", makers["corpus_d2h"], 2)):
+    if not a.no_extra and not a.kernel_only and a.workload == "stft_mel":
+        ddp_cached = None
+        for key, mkey, kmin in (("griffinlim_rtg_1x5s_4it", "griffinlim", 50),
+                                ("griffinlim_tt_1x5s_30it", "griffinlim_tt", 10),
+                                ("griffinlim_rtg_64x5s_4it", "griffinlim_batch", 5),
+                                ("mstft_fwd_bwd_16x22050_lossonly", "mstft", 50),
+                                ("mstft_fwd_bwd_16x22050_specs", "mstft_specs", 20),
+                                ("corpus_10000utt_specs+griffinlim", "corpus", 2),
+                                ("corpus_10000utt_specs+griffinlim_d2h", "corpus_d2h", 2)):
             try:
-                ww = mk()
-                d, _ = time_steps(torch, ww.step, k, 3, lambda: None)
-                extra[key] = {"value": ww.units * k / d, "unit": UNIT, "ms_per_step": 1e3 * d / k,
-                              "roofline_frac_hbm": ww.alg_bytes * ww.launches_dominant_per_step / (d / k) / 1e9 / peak,
-                              "note": ww.note}
-                del ww
+                ww, msg = checked(makers[mkey])
             except Exception as ex:   # secondary numbers must never break the contract line
-                extra[key] = {"error": repr(ex)[:200]}
-        try:   # the reference's own torch formulation on the same GPU (cuFFT + ~60 small kernels): comparator only
-            yt = (0.1 * torch.randn(16, 22050, device="cuda")).clamp_(-0.999, 0.999)
-            ygt = torch.tanh(yt + 0.01 * torch.randn_like(yt)).requires_grad_(True)
+                extra[key] = {"error": repr(ex)[:300]}
+                continue
+            d1, _ = time_steps(torch, ww.step, 1, 3, barrier)          # calibration: steps for >= 0.3 s of device time
+            k = int(min(2000, max(kmin, 0.3 / max(allmax(d1), 1e-6))))
+            d, _, nl, ck = measure(ww, k, 3)
+            units = allsum(ww.units)
+            strong = mkey.startswith("corpus")
+            ent = {"value": units * k / d, "unit": UNIT, "ms_per_step": 1e3 * d / k, "steps": k, "n_gpus": world,
+                   "scaling": "strong" if strong else "weak", "gpu_launches_per_step": nl // k,
+                   "roofline_frac_hbm": ww.alg_bytes * ww.launches_dominant_per_step / (d / k) / 1e9 / peak,
+                   "roofline_frac_fp32": ww.flops / (d / k) / 1e12 / fp32_peak,
+                   "clocks": ck, "parity_check": msg, "note": ww.note}
+            if strong:
+                ent["load_audio_s_max"], ent["load_audio_s_min"] = allmax(ww.load), allmin(ww.load)
+            if mkey.startswith("mstft") and world > 1:
+                ddp_cached = ddp_cached or ddp_probe()
+                ent["ddp"] = ddp_cached
+            extra[key] = ent
+            del ww
+            torch.cuda.empty_cache()
+        if rank == 0 and world == 1:
+            try:   # the reference's own torch formulation on the same GPU (cuFFT + ~60 small kernels): comparator only
+                yt = (0.1 * torch.randn(16, 22050, device="cuda")).clamp_(-0.999, 0.999)
+                ygt = torch.tanh(yt + 0.01 * torch.randn_like(yt)).requires_grad_(True)
 
-            def torch_step(i):
-                ygt.grad = None
-                _torch_ref_mstft(yt, ygt).backward()
-                return ygt.grad
-            d, _ = time_steps(torch, torch_step, 30, 5, lambda: None)
-            extra["mstft_fwd_bwd_16x22050_lossonly_torch_cufft"] = {
-                "value": 16 * 22050 / SR * 30 / d, "unit": UNIT, "ms_per_step": 1e3 * d / 30,
-                "note": "comparator: the reference's multi_stft_loss graph through torch.stft (cuFFT) + autograd on the same GPU; "
-                        "not this repo's code path"}
-        except Exception as ex:
-            extra["mstft_fwd_bwd_16x22050_lossonly_torch_cufft"] = {"error": repr(ex)[:200]}
-        try:   # get_specs (transtacos/audio.py:73-77) written with torch ops on the same GPU: cuFFT + dense mel GEMM comparator
-            from oracle import spectral_oracle as O
-            yb = (0.1 * torch.randn(64, L5, device="cuda")).clamp_(-0.999, 0.999)
-            wnd = torch.hann_window(WIN, device="cuda")
-            mbt = torch.from_numpy(O.mel_basis(N_FFT)).cuda()
+                def torch_step(i):
+                    ygt.grad = None
+                    _torch_ref_mstft(yt, ygt).backward()
+                    return ygt.grad
+                d, _ = time_steps(torch, torch_step, 30, 5, lambda: None)
+                extra["mstft_fwd_bwd_16x22050_lossonly_torch_cufft"] = {
+                    "value": 16 * 22050 / SR * 30 / d, "unit": UNIT, "ms_per_step": 1e3 * d / 30,
+                    "note": "comparator: the reference's multi_stft_loss graph through torch.stft (cuFFT) + autograd on the same GPU; "
+                            "not this repo's code path"}
+            except Exception as ex:
+                extra["mstft_fwd_bwd_16x22050_lossonly_torch_cufft"] = {"error": repr(ex)[:200]}
+            try:   # get_specs (transtacos/audio.py:73-77) written with torch ops on the same GPU: cuFFT + dense mel GEMM comparator
+                from oracle import spectral_oracle as O
+                yb = (0.1 * torch.randn(64, L5, device="cuda")).clamp_(-0.999, 0.999)
+                wnd = torch.hann_window(WIN, device="cuda")
+                mbt = torch.from_numpy(O.mel_basis(N_FFT)).cuda()
 
-            def torch_specs(i):
-                x = torch.cat([yb[:, :1], yb[:, 1:] - 0.97 * yb[:, :-1]], dim=1)
-                D = torch.stft(x, N_FFT, HOP, WIN, window=wnd, center=True, pad_mode="reflect", return_complex=True).abs()
-                S = 8.0 * ((20.0 * torch.log10(D.clamp_min(1e-5)) - 20.0 + 100.0) / 100.0) - 4.0
-                M = 8.0 * ((20.0 * torch.log10((mbt @ D).clamp_min(1e-5)) - 20.0 + 100.0) / 100.0) - 4.0
-                return S, M
-            d, _ = time_steps(torch, torch_specs, 30, 5, lambda: None)
-            extra["stft_mel_64x5s_torch_cufft"] = {
-                "value": 64 * L5 / SR * 30 / d, "unit": UNIT, "ms_per_step": 1e3 * d / 30,
-                "note": "comparator: get_specs written with torch ops (torch.stft / cuFFT, dense mel GEMM, elementwise) on the same GPU; "
-                        "not this repo's code path"}
-            del yb
-        except Exception as ex:
-            extra["stft_mel_64x5s_torch_cufft"] = {"error": repr(ex)[:200]}
+                def torch_specs(i):
+                    x = torch.cat([yb[:, :1], yb[:, 1:] - 0.97 * yb[:, :-1]], dim=1)
+                    D = torch.stft(x, N_FFT, HOP, WIN, window=wnd, center=True, pad_mode="reflect", return_complex=True).abs()
+                    S = 8.0 * ((20.0 * torch.log10(D.clamp_min(1e-5)) - 20.0 + 100.0) / 100.0) - 4.0
+                    M = 8.0 * ((20.0 * torch.log10((mbt @ D).clamp_min(1e-5)) - 20.0 + 100.0) / 100.0) - 4.0
+                    return S, M
+                d, _ = time_steps(torch, torch_specs, 30, 5, lambda: None)
+                extra["stft_mel_64x5s_torch_cufft"] = {
+                    "value": 64 * L5 / SR * 30 / d, "unit": UNIT, "ms_per_step": 1e3 * d / 30,
+                    "note": "comparator: get_specs written with torch ops (torch.stft / cuFFT, dense mel GEMM, elementwise) on the same GPU; "
+                            "not this repo's code path"}
+                del yb
+            except Exception as ex:
+                extra["stft_mel_64x5s_torch_cufft"] = {"error": repr(ex)[:200]}
     sampler.stop_flag = True
 
     cpu_baseline = None
@@ -594,17 +753,23 @@ def main():
                         "sample": f"{n_utt} x 5 s utterances, oracle restatement of the reference path, {cores} processes, {dt:.1f} s"}
 
     if rank == 0:
+        strong = a.workload.startswith("corpus")
         out = {
             "metric": METRIC, "value": total_units * a.steps / dev_s, "unit": UNIT, "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * dev_s / a.steps, "higher_is_better": True,
-            "scaling": "strong" if a.workload == "corpus" else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(config, workload=w.name, per_gpu=w.name, l2=w.note, **({"ddp": ddp_info} if ddp_info else {}),
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(config, workload=w.name, per_gpu=w.name, l2=w.note, parity_check=check_msg,
+                           **({"ddp": ddp_info} if ddp_info else {}),
                            **({"numa_bound": bool(numa_bound)} if world > 1 else {})),
-            "clocks": sampler.summary(window),
+            "clocks": clocks,
             "e2e": e2e, "gpu_launches": int(timed_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": w.dominant, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": w.alg_bytes, "kernel_us": kern_s * 1e6},
+                         "traffic": traffic, "traffic_source": traffic_src, "kernel": w.dominant, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": w.alg_bytes, "kernel_us": kern_s * 1e6,
+                         "fp32": {"achieved_tflops": w.flops / (dev_s / a.steps) / 1e12, "peak_tflops": fp32_peak,
+                                  "frac": w.flops / (dev_s / a.steps) / 1e12 / fp32_peak,
+                                  "note": "algorithmic FP32 FLOPs of the step (SURVEY.md 8d) / step time / (148 SMs x 128 lanes x 2 x max SM "
+                                          "clock); the measured FMA-pipe utilisation is in profiles/"}},
             "cpu_baseline": cpu_baseline, "wall_s": wall_s,
         }
         if extra:

@@ -39,3 +39,16 @@ def max_rel(a, b):
 def golden_side():
     """Fixtures of the widened rows, produced by tests/golden/make_golden_side.py from the reference's own source."""
     return dict(np.load(os.path.join(ROOT, "tests", "golden", "reference_vectors_side.npz")))
+
+
+@pytest.fixture(scope="session")
+def golden_real():
+    """Fixtures on the recordings the reference ships (img/gt_hfg.wav, img/y_tmpl.wav), produced by
+    tests/golden/make_golden_real.py from the reference's own source.  Spectrogram outputs hold every 16th frame."""
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", "reference_vectors_real.npz")))
+    g["y_gt_hfg"] = g["wav_gt_hfg_int16"].astype(np.float32) / 32768.0
+    g["y_y_tmpl"] = g["wav_y_tmpl"]
+    for k in ("gt_hfg", "y_tmpl"):
+        y = g[f"y_{k}"]
+        g[f"y_{k}"] = y[:(len(y) // 256) * 256 - 1]           # aligned to the hop, then y[:-1] (retunegan/data.py:60-62)
+    return g

@@ -68,7 +68,9 @@ def test_mel_basis_matches_oracle(sb):
         np.testing.assert_array_equal(plan.mel_basis(), O.mel_filterbank(22050, n_fft, 80, 125, 7600))
         np.testing.assert_allclose(plan.window(), O.get_window("hann", win).astype(np.float32), atol=1e-7)
     cfg = sb.RETUNEGAN.replace(mel_scale="htk")
-    np.testing.assert_array_equal(sb.core.get_plan(cfg).mel_basis(), O.mel_filterbank(22050, 2048, 80, 125, 7600, htk=True))
+    np.testing.assert_array_equal(sb.core.get_plan(cfg, htk=True).mel_basis(), O.mel_filterbank(22050, 2048, 80, 125, 7600, htk=True))
+    # hp.mel_scale reaches get_mel only (retunegan/audio.py:126); mel_basis / mag_to_mel / get_stft_torch / the loss stay Slaney
+    np.testing.assert_array_equal(sb.core.get_plan(cfg).mel_basis(), O.mel_filterbank(22050, 2048, 80, 125, 7600))
 
 
 # ------------------------------------------------------------------ TransTacoS get_specs ------
@@ -76,8 +78,8 @@ def test_mel_basis_matches_oracle(sb):
 @pytest.mark.parametrize("tag", ["speech", "noise"])
 def test_get_specs_golden(sb, golden, tag):
     S, M = sb.transtacos_audio.get_specs(golden[f"y_{tag}"])
-    assert S.dtype == np.float32 and S.shape == (1025, 24) and M.shape == (80, 24)
-    assert sb.transtacos_audio.get_specs(golden[f"y_{tag}"], out_dtype=np.float64)[0].dtype == np.float64   # reference dtype
+    assert S.dtype == np.float64 and S.shape == (1025, 24) and M.shape == (80, 24)                          # reference dtype
+    assert sb.transtacos_audio.get_specs(golden[f"y_{tag}"], out_dtype=np.float32)[0].dtype == np.float32   # compute dtype
     assert not S.flags.c_contiguous      # frame-major memory, like librosa's order='F'
     _close_db(S, golden[f"tt_get_specs_S_{tag}"])
     _close_db(M, golden[f"tt_get_specs_M_{tag}"])
@@ -449,3 +451,138 @@ def test_kernel_variants_agree(sb):
     f2 = _run_variant({"SB200_FEAT_KERNEL": "2"}, code)
     np.testing.assert_array_equal(base["S"], f2["S"])
     np.testing.assert_allclose(base["M"], f2["M"], rtol=0, atol=2e-5)
+
+
+# ------------------------------------------------------------------ the benchmarked launches ------------
+
+def test_benchmarked_feature_launch_vs_oracle(sb):
+    """The exact launch bench.py times (BASELINE.json configs[2]): uniform [64, 110335] device batch, TransTacoS epilogue
+    (stft_feature3_kernel<2048, PRE=true, HS=4>, pre-emphasis 0.97, dB-normalise), called through the C ABI the way
+    bench.py calls it.  Rows 0 / 17 / 63 against the oracle; every row of the batch bit-equal to its own single launch."""
+    import ctypes as C
+    B, L, T, F, M = 64, 431 * 256 - 1, 431, 1025, 80
+    ta = sb.transtacos_audio
+    g = torch.Generator(device="cuda").manual_seed(114514)
+    y = (0.1 * torch.randn(B, L, device="cuda", generator=g)).clamp_(-0.999, 0.999)
+    plan = sb.core.get_plan(ta.hp)
+    batch = sb.core.SignalBatch(plan, y)
+    mag = torch.empty((B * T, F), device="cuda")
+    mel = torch.empty((B * T, M), device="cuda")
+    sc = ta.db_norm_scale(ta.hp)
+    sb._lib.check(sb._lib.load().sb200_stft_features(plan.handle, sb.core.ptr(batch.x), C.byref(batch.c), float(ta.hp.preemphasis),
+                                                     sc, sc, sb.core.ptr(mag), sb.core.ptr(mel), None, sb.core.stream_ptr()))
+    torch.cuda.synchronize()
+    for b in (0, 17, 63):
+        So, Mo = O.tt_get_specs(y[b].cpu().numpy())
+        _close_db(mag.view(B, T, F)[b].t().cpu().numpy(), So)
+        _close_db(mel.view(B, T, M)[b].t().cpu().numpy(), Mo)
+    for b in (0, 1, 17, 62, 63):      # odd rows start at odd sample offsets (L is odd): the misaligned gather path
+        S1, M1 = ta.get_specs(y[b])
+        assert torch.equal(S1.t(), mag.view(B, T, F)[b]) and torch.equal(M1.t(), mel.view(B, T, M)[b])
+
+
+@pytest.mark.parametrize("specs", [False, True])
+def test_benchmarked_mstft_launch_vs_oracle(sb, specs):
+    """BASELINE.json configs[3]: y, y_g [16, 1, 22050] (1 s segments, frames 92 / 184 / 368), loss-only and the training
+    variant (spec stacks + dense upstream spec gradients), against the oracle's loss and closed-form gradient."""
+    B, T = 16, 22050
+    g = torch.Generator(device="cuda").manual_seed(77)
+    y = (0.1 * torch.randn(B, 1, T, device="cuda", generator=g)).clamp_(-0.999, 0.999)
+    yg = torch.tanh(y + 0.01 * torch.randn(B, 1, T, device="cuda", generator=g)).requires_grad_(True)
+    yn, gn = y.cpu().numpy(), yg.detach().cpu().numpy()
+    lo = O.rtg_multi_stft_loss(yn, gn, ret_loss=True)
+    if not specs:
+        loss = sb.multi_stft_loss(y, yg, ret_loss=True)
+        loss.backward()
+        go = O.rtg_multi_stft_loss_backward(yn, gn)
+        tol = 1e-4
+    else:
+        loss, (sr, sg) = sb.multi_stft_loss(y, yg, ret_loss=True, ret_specs=True)
+        assert [tuple(s.shape) for s in sg] == [(16, 2, 1025, 92), (16, 2, 513, 184), (16, 2, 257, 368)]
+        rs = np.random.RandomState(3)
+        ups = [rs.randn(*s.shape).astype(np.float32) * 1e-3 for s in sg]
+        torch.autograd.backward([loss] + list(sg), [torch.ones_like(loss)] + [torch.from_numpy(u).cuda() for u in ups])
+        # oracle gradient on the first two rows only (the closed form is per row; 16 rows of float64 take a while)
+        go = O.rtg_multi_stft_loss_backward(yn[:2], gn[:2], g_loss=2.0 / B, g_specs_g=[u[:2] for u in ups])
+        tol = 1e-3      # spec-stack gradients are ill conditioned at weak bins (see the golden training-gradient test)
+    assert abs(loss.item() - lo) <= 1e-5 * abs(lo), (loss.item(), lo)
+    got = yg.grad[:, 0].cpu().numpy()[:go.shape[0]]
+    assert rel_fro(got, go) <= tol, rel_fro(got, go)
+
+
+# ------------------------------------------------------------------ the recordings the reference ships ----
+
+@pytest.mark.parametrize("tag", ["gt_hfg", "y_tmpl"])
+def test_real_recordings_features(sb, golden_real, tag):
+    """img/gt_hfg.wav / img/y_tmpl.wav: CUDA path vs outputs of the reference's own source (make_golden_real.py)."""
+    y = golden_real[f"y_{tag}"]
+    S, M = sb.transtacos_audio.get_specs(y)
+    _close_db(S[:, ::16], golden_real[f"tt_S_{tag}"])
+    _close_db(M, golden_real[f"tt_M_{tag}"])
+    mag, mel = sb.retunegan_audio.get_mag_mel(y)
+    _close(np.exp(mag[:, ::16]), np.exp(golden_real[f"rtg_mag_{tag}"]))
+    _close(np.exp(mel), np.exp(golden_real[f"rtg_mel_{tag}"]))
+
+
+def test_real_recording_griffinlim_and_loss(sb, golden_real):
+    y = golden_real["y_gt_hfg"]
+    w = sb.retunegan_audio.inv_mag(sb.retunegan_audio.get_mag(y), wavlen=len(y))
+    assert w.dtype == np.float32 and len(w) == len(y)
+    seg = golden_real["rtg_inv_mag_gt_hfg_seg"]
+    assert rel_fro(w[16384:32768], seg) <= 1e-3
+    assert abs(np.linalg.norm(w.astype(np.float64)) / float(golden_real["rtg_inv_mag_gt_hfg_norm"]) - 1) <= 1e-3
+    yr = torch.from_numpy(golden_real["loss_y_real"]).cuda().unsqueeze(1)
+    yg = torch.from_numpy(golden_real["loss_yg_real"]).cuda().unsqueeze(1).requires_grad_(True)
+    loss = sb.multi_stft_loss(yr, yg, ret_loss=True)
+    ref = float(golden_real["loss_real_value_f64"])
+    assert abs(loss.item() - ref) <= 1e-5 * abs(ref)
+    loss.backward()
+    assert rel_fro(yg.grad[:, 0].cpu().numpy(), golden_real["loss_real_grad_f64"]) <= 1e-4
+
+
+# ------------------------------------------------------------------ threads and streams -------------------
+
+def test_concurrent_threads_and_streams_equal_serial(sb):
+    """The call pattern of the Flask servers (retunegan/server.py:33-62, transtacos/server.py:59-101): request threads calling
+    the numpy-facing API at the same time, here additionally on their own CUDA streams.  Every result must be bit-equal to
+    the same call made alone (per-thread / per-stream workspaces incl. the persistent Griffin-Lim kernel's barrier counter,
+    locked host pipeline, published phase cache)."""
+    import threading
+    ra, ta = sb.retunegan_audio, sb.transtacos_audio
+    lens = [256 * 431 - 1, 256 * 57 - 1, 256 * 200 - 1, 256 * 33 - 1]
+    ys = [O.synth_speechlike(L, 900 + i) for i, L in enumerate(lens)]
+    yb = np.stack([O.synth_noise(256 * 60 - 1, 950 + i) for i in range(6)])
+    y_loss = torch.from_numpy(np.stack([O.synth_noise(8192, 970 + i) for i in range(4)])).cuda()
+
+    def job(i):
+        mag = ra.get_mag(ys[i])
+        wav = ra.inv_mag(mag, wavlen=lens[i])                                  # 4 iterations, seeded phase
+        S, M = ta.get_specs(ys[i], out_dtype=np.float32)
+        w30 = ta.inv_spec(S[:, :40], init_phase=np.random.RandomState(i).rand(1025, 40), n_iter=6)
+        Sb, Mb = ta.get_specs(yb + 0.001 * i, out_dtype=np.float32)            # host batch: the chunked copy pipeline
+        yg = torch.tanh(y_loss * (1.0 + 0.1 * i)).requires_grad_(True)
+        loss = sb.multi_stft_loss(y_loss, yg, ret_loss=True)
+        loss.backward()
+        return [mag, wav, S, M, w30, np.ascontiguousarray(Sb), np.ascontiguousarray(Mb), np.asarray(loss.item()),
+                yg.grad.cpu().numpy()]
+    serial = [job(i) for i in range(4)]
+    results, errors = [None] * 4, []
+
+    def worker(i):
+        try:
+            s = torch.cuda.Stream()
+            with torch.cuda.stream(s):
+                for _ in range(3):
+                    results[i] = job(i)
+            s.synchronize()
+        except Exception as ex:   # surfaced in the main thread
+            errors.append(repr(ex))
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for i in range(4):
+        for a, b in zip(serial[i], results[i]):
+            np.testing.assert_array_equal(a, b)

@@ -62,12 +62,16 @@ class SpectralConfig:
     def window_id(self) -> int:
         return _WINDOWS[self.window_fn]
 
-    def plan_key(self, n_fft=None, win_length=None, hop_length=None):
+    def plan_key(self, n_fft=None, win_length=None, hop_length=None, htk=False):
+        """Key of the plan tables.  ``htk``: mel scale of the filterbank.  The reference honours ``hp.mel_scale`` ONLY in
+        ``get_mel`` (retunegan/audio.py:126 ``htk=hp.mel_scale=='htk'``); ``mel_basis`` / ``mag_to_mel`` (audio.py:20-21) and
+        ``get_stft_torch`` / ``multi_stft_loss`` (audio.py:158) always build the Slaney basis, so the flag is explicit and
+        defaults to Slaney."""
         n_fft = self.n_fft if n_fft is None else int(n_fft)
         win_length = self.win_length if win_length is None else int(win_length)
         hop_length = self.hop_length if hop_length is None else int(hop_length)
         return (self.sample_rate, n_fft, win_length, hop_length, self.n_mel, float(self.fmin), float(self.fmax),
-                int(self.mel_scale == "htk"), self.window_id)
+                int(bool(htk)), self.window_id)
 
     def replace(self, **kw) -> "SpectralConfig":
         return dataclasses.replace(self, **kw)

@@ -62,11 +62,11 @@ class Plan:
         return out
 
 
-def get_plan(cfg: SpectralConfig, n_fft=None, win_length=None, hop_length=None) -> Plan:
+def get_plan(cfg: SpectralConfig, n_fft=None, win_length=None, hop_length=None, htk=False) -> Plan:
     """Plan cache keyed by configuration AND device (the reference pins its caches to the first device seen,
-    retunegan/audio.py:153-159)."""
+    retunegan/audio.py:153-159).  ``htk=True`` only from ``get_mel`` (the one place the reference reads ``hp.mel_scale``)."""
     dev = require_cuda()
-    key = cfg.plan_key(n_fft, win_length, hop_length)
+    key = cfg.plan_key(n_fft, win_length, hop_length, htk)
     ck = (key, dev.index)
     p = _plans.get(ck)
     if p is None:
@@ -256,6 +256,8 @@ def yin(ys, sample_rate: int, fmin: float, fmax: float, frame_length: int, hop_l
         if not parts:
             raise ValueError("empty batch")
         lens = np.array([p.numel() for p in parts], np.int64)
+        if lens.min() < frame_length // 2 + 1:
+            raise ValueError("signal shorter than frame_length/2 + 1 samples: reflect padding undefined")
         x = torch.cat(parts)
         frames = 1 + lens // hop_length
         tbl = np.zeros((3, len(parts) + 1), np.int64)
@@ -271,6 +273,8 @@ def yin(ys, sample_rate: int, fmin: float, fmax: float, frame_length: int, hop_l
             x = x.unsqueeze(0)
         if x.dim() != 2 or x.shape[1] < 1:
             raise ValueError(f"expected [L] or [B, L] samples, got shape {tuple(x.shape)}")
+        if x.shape[1] < frame_length // 2 + 1:
+            raise ValueError("signal shorter than frame_length/2 + 1 samples: reflect padding undefined")
         x = x.contiguous()
         B, L = x.shape
         frames = np.full(B, 1 + L // hop_length, np.int64)
@@ -339,16 +343,23 @@ class FramesBatch:
             self.out_off = tbl[0].copy()
 
 
-_ws_cache = {}
+_tls = threading.local()
 
 
 def _workspace(nbytes: int, device, tag: str) -> torch.Tensor:
-    """Grow-only per-device scratch buffer (caller-allocated workspace of the C ABI)."""
-    key = (device.index, tag)
-    buf = _ws_cache.get(key)
+    """Grow-only scratch buffer (the caller-allocated workspace of the C ABI), private to the calling THREAD and to the
+    CUDA STREAM the call is enqueued on.  A workspace holds state that lives across the kernels of one call (Griffin-Lim
+    signal buffers and the grid-barrier counter of the persistent kernel, mstft gradient frames and partial sums): two
+    host threads interleaving their enqueues on one stream, or two streams running at once, must never share it.  Flask
+    request threads (retunegan/server.py:33-62, transtacos/server.py:59-101) each get their own; it dies with the thread."""
+    cache = getattr(_tls, "ws", None)
+    if cache is None:
+        cache = _tls.ws = {}
+    key = (device.index, int(torch.cuda.current_stream(device).cuda_stream), tag)
+    buf = cache.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(int(nbytes), device=device, dtype=torch.uint8)
-        _ws_cache[key] = buf
+        cache[key] = buf
     return buf
 
 
@@ -387,26 +398,49 @@ class HostFeaturePipeline:
     ``get_specs`` / ``get_mag`` use for 2-D host input, and what bench.py times as the end-to-end number.
     """
 
-    def __init__(self, plan: Plan, L: int, chunk: int = 16, depth: int = 3):
-        self.plan, self.L, self.chunk, self.depth = plan, int(L), int(chunk), int(depth)
-        dev = require_cuda()
-        self.T = 1 + self.L // plan.hop_length
-        self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
-        self.x = [torch.empty((chunk, self.L), device=dev, dtype=torch.float32) for _ in range(depth)]
-        self.mag = [torch.empty((chunk * self.T, plan.F), device=dev, dtype=torch.float32) for _ in range(depth)]
-        self.mel = [torch.empty((chunk * self.T, plan.n_mel), device=dev, dtype=torch.float32) for _ in range(depth)]
+    def __init__(self, plan: Plan, chunk: int = 16, depth: int = 3):
+        self.plan, self.chunk, self.depth = plan, int(chunk), int(depth)
+        self.dev = require_cuda()
+        self.L = 0                      # capacity of the slots in samples per row; grow-only
+        self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(self.dev) for _ in range(3))
+        self.x, self.mag, self.mel = [], [], []
         self.ev_in = [torch.cuda.Event() for _ in range(depth)]
         self.ev_run = [torch.cuda.Event() for _ in range(depth)]
         self.ev_out = [torch.cuda.Event() for _ in range(depth)]
         self.used = [False] * depth
+        self.lock = threading.Lock()    # one batch at a time per device: the slots, streams and events are shared state
+
+    def _reserve(self, L: int) -> None:
+        """Slots sized for the longest row seen so far (a corpus / DataLoader changes the padded length every step: one set
+        of buffers, streams and events serves every length, nothing is kept per length)."""
+        if L <= self.L:
+            return
+        torch.cuda.synchronize(self.dev)            # nothing of the old slots is in flight any more
+        plan, chunk, dev = self.plan, self.chunk, self.dev
+        T = 1 + L // plan.hop_length
+        self.x = self.mag = self.mel = None         # free before allocating the larger set
+        self.x = [torch.empty(chunk * L, device=dev, dtype=torch.float32) for _ in range(self.depth)]
+        self.mag = [torch.empty(chunk * T * plan.F, device=dev, dtype=torch.float32) for _ in range(self.depth)]
+        self.mel = [torch.empty(chunk * T * plan.n_mel, device=dev, dtype=torch.float32) for _ in range(self.depth)]
+        self.used = [False] * self.depth
+        self.L = L
 
     def run(self, y_host: torch.Tensor, mag_host: Optional[torch.Tensor], mel_host: Optional[torch.Tensor],
             preemph: float, mag_scale: Scale, mel_scale: Scale) -> None:
         """y_host [B, L] float32 CPU; mag_host [B*T, F] / mel_host [B*T, n_mel] float32 CPU (None = not wanted).
-        Returns after all copies have completed."""
+        Returns after all copies have completed.  Thread-safe (serialised per device)."""
+        with self.lock:
+            self._run(y_host, mag_host, mel_host, preemph, mag_scale, mel_scale)
+
+    def _run(self, y_host, mag_host, mel_host, preemph, mag_scale, mel_scale) -> None:
         lib = _lib.load()
-        B = y_host.shape[0]
-        plan, T = self.plan, self.T
+        B, L = y_host.shape
+        self._reserve(int(L))
+        plan = self.plan
+        T = 1 + L // plan.hop_length
+        xs = [b[:self.chunk * L].view(self.chunk, L) for b in self.x]
+        mags = [b[:self.chunk * T * plan.F].view(self.chunk * T, plan.F) for b in self.mag]
+        mels = [b[:self.chunk * T * plan.n_mel].view(self.chunk * T, plan.n_mel) for b in self.mel]
         cur = torch.cuda.current_stream()
         self.s_in.wait_stream(cur)
         # ramp-up schedule: a quarter and a half chunk first (the copy-back, which bounds the pipeline, starts early), full
@@ -424,24 +458,24 @@ class HostFeaturePipeline:
             with torch.cuda.stream(self.s_in):
                 if self.used[s]:
                     self.s_in.wait_event(self.ev_run[s])          # slot's previous launch has consumed x[s]
-                self.x[s][:n].copy_(y_host[b0:b0 + n], non_blocking=True)
+                xs[s][:n].copy_(y_host[b0:b0 + n], non_blocking=True)
                 self.ev_in[s].record(self.s_in)
             with torch.cuda.stream(self.s_run):
                 self.s_run.wait_event(self.ev_in[s])
                 if self.used[s]:
                     self.s_run.wait_event(self.ev_out[s])         # slot's previous outputs have left the device
-                bc = Batch(n, self.L, self.L, None, None, None, None, 0, 0)
-                check(lib.sb200_stft_features(plan.handle, ptr(self.x[s]), C.byref(bc), float(preemph), mag_scale,
-                                              mel_scale, ptr(self.mag[s]) if mag_host is not None else None,
-                                              ptr(self.mel[s]) if mel_host is not None else None, None,
+                bc = Batch(n, L, L, None, None, None, None, 0, 0)
+                check(lib.sb200_stft_features(plan.handle, ptr(xs[s]), C.byref(bc), float(preemph), mag_scale,
+                                              mel_scale, ptr(mags[s]) if mag_host is not None else None,
+                                              ptr(mels[s]) if mel_host is not None else None, None,
                                               C.c_void_p(self.s_run.cuda_stream)), "stft_features")
                 self.ev_run[s].record(self.s_run)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(self.ev_run[s])
                 if mag_host is not None:
-                    mag_host[b0 * T:(b0 + n) * T].copy_(self.mag[s][:n * T], non_blocking=True)
+                    mag_host[b0 * T:(b0 + n) * T].copy_(mags[s][:n * T], non_blocking=True)
                 if mel_host is not None:
-                    mel_host[b0 * T:(b0 + n) * T].copy_(self.mel[s][:n * T], non_blocking=True)
+                    mel_host[b0 * T:(b0 + n) * T].copy_(mels[s][:n * T], non_blocking=True)
                 self.ev_out[s].record(self.s_out)
             self.used[s] = True
         self.s_out.synchronize()
@@ -449,12 +483,15 @@ class HostFeaturePipeline:
 
 
 _pipelines = {}
+_pipelines_lock = threading.Lock()
 
 
-def host_feature_pipeline(plan: Plan, L: int, chunk: int = 16) -> HostFeaturePipeline:
-    key = (plan.key, plan.device_index, int(L), int(chunk))
-    p = _pipelines.get(key)
-    if p is None:
-        p = HostFeaturePipeline(plan, L, chunk)
-        _pipelines[key] = p
+def host_feature_pipeline(plan: Plan, chunk: int = 16) -> HostFeaturePipeline:
+    """One pipeline per (plan, device, chunk size); its slots grow to the longest row seen (no entry per length)."""
+    key = (plan.key, plan.device_index, int(chunk))
+    with _pipelines_lock:
+        p = _pipelines.get(key)
+        if p is None:
+            p = HostFeaturePipeline(plan, chunk)
+            _pipelines[key] = p
     return p

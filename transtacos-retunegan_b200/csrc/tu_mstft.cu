@@ -28,6 +28,10 @@ struct MstftSide {
   cudaEvent_t fork, join[kMaxRes - 1];
   bool ok = false;
 };
+// The side streams and the fork / join events are one set per device: the whole enqueue of a call holds this mutex, so
+// two host threads (or two caller streams) never interleave their event records / waits (an event is re-recorded only
+// after every wait on its previous record has been enqueued).
+static std::mutex g_mstft_enqueue_mu;
 static MstftSide* mstft_side() {
   static std::mutex mu;
   static MstftSide side[64];
@@ -132,6 +136,7 @@ int sb200_mstft_forward(const sb200_plan* const* plans, int32_t n_res, const flo
                         void* saved, void* workspace, sb200_stream stream) {
   if (int rc = mstft_check(plans, n_res, B, T)) return rc;
   if (!y || !y_g || !saved || !workspace) return fail(SB200_ERR_INVALID, "mstft_forward: null argument");
+  std::lock_guard<std::mutex> enqueue_lock(g_mstft_enqueue_mu);
   if (!loss && !specs_r && !specs_g) return fail(SB200_ERR_INVALID, "mstft_forward: neither loss nor specs requested (loss.py:62 raises)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   char* ws = static_cast<char*>(workspace);
@@ -175,6 +180,7 @@ int sb200_mstft_backward(const sb200_plan* const* plans, int32_t n_res, const fl
                          float* g_yg, void* workspace, sb200_stream stream) {
   if (int rc = mstft_check(plans, n_res, B, T)) return rc;
   if (!y_g || !saved || !g_yg || !workspace) return fail(SB200_ERR_INVALID, "mstft_backward: null argument");
+  std::lock_guard<std::mutex> enqueue_lock(g_mstft_enqueue_mu);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   char* ws = static_cast<char*>(workspace);
   GradOlaArgs o{};
@@ -218,6 +224,7 @@ int sb200_mstft_loss_and_grad(const sb200_plan* const* plans, int32_t n_res, con
                               int64_t T, float* loss, float* grad_yg, void* workspace, sb200_stream stream) {
   if (int rc = mstft_check(plans, n_res, B, T)) return rc;
   if (!y || !y_g || !loss || !grad_yg || !workspace) return fail(SB200_ERR_INVALID, "mstft_loss_and_grad: null argument");
+  std::lock_guard<std::mutex> enqueue_lock(g_mstft_enqueue_mu);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   char* ws = static_cast<char*>(workspace);
   const int64_t part0 = mstft_ws_gfb_off(plans, n_res, B, T);

@@ -26,6 +26,7 @@ length (``sharding.shard_utterances``) with no data-path collective; rank 0 gath
 from __future__ import annotations
 
 import os
+import warnings
 import random
 from collections import defaultdict
 from re import compile as Regex
@@ -89,10 +90,26 @@ def make_metadata_batch(items: Sequence[Tuple[str, Tuple[str, str], np.ndarray]]
     out: List[Optional[tuple]] = [None] * len(items)
     if not keep:
         return out
-    ys = A.trim_silence(ys)                              # one launch for the batch
-    ys = [A.align_wav(y) for y in ys]
-    cuts = [y[:-1] for y in ys]                          # datasets/databaker.py:102
     plan = core.get_plan(hp)
+    min_len = plan.n_fft // 4 + 2                        # reflect padding of the centred window needs n_fft/4 + 1 samples of y[:-1]
+    ok = [j for j, y in enumerate(ys) if len(y) >= 2]
+    trimmed = dict(zip(ok, A.trim_silence([ys[j] for j in ok]))) if ok else {}   # one launch for the batch
+    good = []
+    for j in range(len(ys)):
+        y = A.align_wav(trimmed[j]) if j in trimmed else None
+        if y is None or len(y) < min_len:
+            # the reference handles clips one by one (librosa reflect-pads anything >= 2 samples, with a warning); a clip
+            # shorter than the window support carries no usable frame: skip it instead of failing the whole batch
+            warnings.warn(f"preprocess: utterance {items[keep[j]][0]!r} is too short after trimming "
+                          f"({0 if y is None else len(y)} samples); skipped")
+            continue
+        ys[j] = y
+        good.append(j)
+    keep = [keep[j] for j in good]
+    ys = [ys[j] for j in good]
+    if not keep:
+        return out
+    cuts = [y[:-1] for y in ys]                          # datasets/databaker.py:102
     batch = core.SignalBatch(plan, cuts)
     sc = A.db_norm_scale(hp)
     mag, mel, _ = core.stft_features(plan, batch, preemph=hp.preemphasis, mag_scale=sc, mel_scale=sc)

@@ -11,7 +11,9 @@ frame-major memory.  Lists / ``[B, L]`` batches are additions over the reference
 """
 from __future__ import annotations
 
+import collections
 import math
+import threading
 
 import numpy as np
 import torch
@@ -22,13 +24,21 @@ from .transtacos_audio import _frame_feature, _is_np, _split_fm, _to_frame_major
 
 hp: SpectralConfig = RETUNEGAN
 eps = 1e-5
-_phase_cache = {}
+# Seeded initial phase (librosa.griffinlim random_state=int).  rand(F, T) is the first F*T values of ONE MT19937 stream, so a
+# single device-resident prefix of that stream serves every T (grow-only, <= a few MB); the [T, F] frame-major layouts made
+# from it are kept in a small LRU (a ragged corpus sees hundreds of distinct T: nothing is kept per length beyond that).
+_phase_lock = threading.Lock()
+_phase_stream = {}                       # (seed, device) -> float32 CUDA prefix of RandomState(seed).rand(n)
+_phase_cache = collections.OrderedDict()  # (seed, F, T, device) -> float32 CUDA [T, F]
+_PHASE_LRU = 16
 
 
 def set_hparams(cfg) -> None:
     global hp
     hp = cfg if isinstance(cfg, SpectralConfig) else SpectralConfig.from_hparam(cfg)
-    _phase_cache.clear()
+    with _phase_lock:
+        _phase_cache.clear()
+        _phase_stream.clear()
 
 
 def __getattr__(name):
@@ -44,7 +54,8 @@ def ln_scale(clamp_low: bool) -> core.Scale:
 
 def _features(y, want_mag, want_mel, clamp_low):
     as_np = _is_np(y)
-    plan = core.get_plan(hp)
+    # hp.mel_scale is honoured by get_mel only (retunegan/audio.py:126); the magnitudes do not depend on the mel tables
+    plan = core.get_plan(hp, htk=(want_mel and hp.mel_scale == "htk"))
     batch = core.SignalBatch(plan, y)
     sc = ln_scale(clamp_low)
     mag, mel, _ = core.stft_features(plan, batch, 0.0, sc, sc, want_mag, want_mel)
@@ -97,11 +108,25 @@ def mag_to_mel(x):
 def _seeded_phase(F: int, T: int) -> torch.Tensor:
     """librosa.griffinlim(random_state=int) draws RandomState(seed).rand(F, T) afresh on every call, so every
     utterance of a given length starts from the same phase: cache it on the device."""
-    key = (hp.randseed, F, T, torch.cuda.current_device())
-    ph = _phase_cache.get(key)
-    if ph is None:
-        ph = _to_frame_major(np.random.RandomState(hp.randseed).rand(F, T))
+    dev = torch.cuda.current_device()
+    key = (hp.randseed, F, T, dev)
+    cur = torch.cuda.current_stream()
+    with _phase_lock:
+        ph = _phase_cache.get(key)
+        if ph is not None:
+            _phase_cache.move_to_end(key)
+            ph.record_stream(cur)      # may have been built on another thread's stream; keep its memory until this use is done
+            return ph
+        u = _phase_stream.get((hp.randseed, dev))
+        if u is None or u.numel() < F * T:
+            n = max(F * T, F * 600)            # corpus utterances have <= 524 frames (stats/DataBaker.stats:6-11)
+            u = core.to_device_f32(np.random.RandomState(hp.randseed).rand(n))
+            _phase_stream[(hp.randseed, dev)] = u
+        ph = u[:F * T].view(F, T).t().contiguous()      # element (f, t) = draw f*T + t (C-order rand(F, T)), frame-major
+        cur.synchronize()              # published to other threads / streams only once it is complete
         _phase_cache[key] = ph
+        while len(_phase_cache) > _PHASE_LRU:
+            _phase_cache.popitem(last=False)
     return ph
 
 

@@ -165,17 +165,18 @@ def features_host(cfg: SpectralConfig, y_host: torch.Tensor, preemph, mag_scale,
             mag = torch.empty((B * T, plan.F), dtype=torch.float32)
         if want_mel:
             mel = torch.empty((B * T, plan.n_mel), dtype=torch.float32)
-    core.host_feature_pipeline(plan, L, chunk).run(y_host, mag, mel, preemph, mag_scale, mel_scale)
+    core.host_feature_pipeline(plan, chunk).run(y_host, mag, mel, preemph, mag_scale, mel_scale)
     return mag, mel, T
 
 
 def get_specs(y, out_dtype=None, out=None):
     """(normalised dB magnitude [F,T], normalised dB mel [M,T]) -- transtacos/audio.py:73-77.
 
-    Host input (numpy / CPU tensor) -> host output; ``out_dtype`` defaults to float32, the precision the kernels
-    compute in (the reference returns float64 only because scipy's lfilter promotes; pass np.float64 to get
-    that dtype).  CUDA tensor in -> CUDA float32 views out.  ``[B, L]`` host batches stream through pinned-copy /
-    launch / copy-back overlap; ``out=(mag [B*T, F], mel [B*T, M])`` supplies (pinned) CPU destination tensors.
+    numpy in -> numpy out in float64, the dtype the reference returns (scipy's lfilter promotes, transtacos/audio.py:66;
+    the features are np.save'd as float64, datasets/databaker.py:113-114).  The kernels compute in float32:
+    ``out_dtype=np.float32`` skips the widening.  torch in -> float32 torch views out (CPU tensor in -> CPU out, CUDA in ->
+    CUDA out).  ``[B, L]`` host batches stream through pinned-copy / launch / copy-back overlap; ``out=(mag [B*T, F],
+    mel [B*T, M])`` supplies (pinned) float32 CPU destination tensors, which are then what is returned (no widening).
     """
     sc = db_norm_scale(hp)
     yh = _host_batch(y)
@@ -185,7 +186,7 @@ def get_specs(y, out_dtype=None, out=None):
         mag, mel, T = features_host(hp, yh, hp.preemphasis, sc, sc, out=out)
         B = yh.shape[0]
         if isinstance(y, np.ndarray):
-            dt = np.float32 if out_dtype is None else out_dtype
+            dt = (np.float32 if out is not None else np.float64) if out_dtype is None else out_dtype
             S = mag.numpy().astype(dt, copy=False).reshape(B, T, -1).transpose(0, 2, 1)
             M = mel.numpy().astype(dt, copy=False).reshape(B, T, -1).transpose(0, 2, 1)
             return S, M
@@ -195,7 +196,7 @@ def get_specs(y, out_dtype=None, out=None):
     batch = core.SignalBatch(plan, y)
     mag, mel, _ = core.stft_features(plan, batch, preemph=hp.preemphasis, mag_scale=sc, mel_scale=sc)
     single = not isinstance(y, (list, tuple)) and getattr(y, "ndim", 1) == 1
-    dt = (np.float32 if out_dtype is None else out_dtype) if as_np else None
+    dt = (np.float64 if out_dtype is None else out_dtype) if as_np else None
     S = _split_fm(mag, batch.frames, plan.F, as_np, dt, single)
     M = _split_fm(mel, batch.frames, plan.n_mel, as_np, dt, single)
     if not single and not isinstance(y, (list, tuple)):      # uniform [B, L] CUDA batch -> [B, F, T] views
