@@ -55,7 +55,8 @@ typedef struct {
 /* Batch of independent utterances.  Uniform: off == NULL, every row has `len` samples at stride
  * `stride` and n_frames = 1 + len/hop.  Ragged: device tables (int64) sig_off[B] (first sample of row b),
  * sig_len[B], frame_off[B+1] (prefix sum of frames; row b owns output frames [frame_off[b], frame_off[b+1])),
- * item_off[B+1] (prefix sum of ceil(frames_b / frames_per_pass), see sb200_plan_frames_per_pass). */
+ * item_off[B+1] (prefix sum of ceil(frames_b / frames_per_pass), see sb200_plan_frames_per_pass).
+ * The sample buffer need not be aligned; when x is 16-byte aligned the hot feature kernel stages samples with bulk-tensor (TMA) copies. */
 typedef struct {
   int32_t B;
   int64_t len, stride;       /* uniform */
@@ -65,6 +66,8 @@ typedef struct {
   const int64_t* item_off;
   int64_t total_frames;      /* ragged: frame_off[B]; uniform: ignored */
   int64_t total_items;       /* ragged: item_off[B];  uniform: ignored */
+  int64_t total_samples;     /* ragged: samples the flat buffer holds from x (>= sig_off[b] + sig_len[b] for every b), or 0 =
+                                unknown (then the feature kernel gathers with plain loads instead of bulk-tensor copies); uniform: ignored */
 } sb200_batch;
 
 /* Output transform of a magnitude-like value v:  raw v, or a*log2(max(floor, v)) + b.

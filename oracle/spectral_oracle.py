@@ -451,17 +451,24 @@ def rtg_multi_stft_loss(y, y_g, ret_loss=False, ret_specs=False, hp=HP, dtype=np
     raise RuntimeError("multi_stft_loss: neither ret_loss nor ret_specs")  # loss.py:62 bare raise
 
 
-def rtg_multi_stft_loss_backward(y, y_g, g_loss=1.0, g_specs_g=None, hp=HP):
+def rtg_multi_stft_loss_backward(y, y_g, g_loss=1.0, g_specs_g=None, hp=HP, tie_rel=None):
     """Closed-form d/dy_g of multi_stft_loss (the autograd graph of retunegan/train.py:192).
 
     SURVEY.md §8a row L2.  ``g_specs_g``: optional list of upstream grads [B,2,F,T'] for
     the generated-side stacks (ln S_g, P_g/PI), one per resolution.  Returns g_yg [B,T] f64.
+
+    ``tie_rel``: the L1 terms contribute sign(M_g - M), which is discontinuous where a generated mel cell ties with the real
+    one; any float32 evaluation (this repo's kernels and the reference's own torch float32 graph alike) may land on the other
+    side of a tie that is closer than its rounding error.  With ``tie_rel`` set, cells with |M_g - M| <= tie_rel * M
+    contribute nothing, and the function returns ``(g, n_ties)``: ``g_full - g`` is then exactly the part of the gradient
+    that hinges on those near-ties (the tests bound the float32 disagreement by tol * |g| + 2 * |g_full - g|).
     """
     y, y_g = np.asarray(y, np.float64), np.asarray(y_g, np.float64)
     if y.ndim == 3:
         y, y_g = y[:, 0], y_g[:, 0]
     B, T = y_g.shape
     g = np.zeros((B, T))
+    n_ties = 0
     nres = len(hp.multi_stft_params)
     for ri, (n_fft, win, hop) in enumerate(hp.multi_stft_params):
         _, M, _, _ = rtg_get_stft(y, n_fft, win, hop, hp, np.float64)
@@ -469,6 +476,10 @@ def rtg_multi_stft_loss_backward(y, y_g, g_loss=1.0, g_specs_g=None, hp=HP):
         basis = mel_basis(n_fft, hp).astype(np.float64)
         cnt = M.size
         gM = g_loss * (np.sign(Mg - M) + np.sign(np.log(Mg) - np.log(M)) / Mg) / (nres * cnt)
+        if tie_rel is not None:
+            tie = np.abs(Mg - M) <= tie_rel * M
+            n_ties += int(tie.sum())
+            gM = np.where(tie, 0.0, gM)
         gS = np.einsum("mf,bmt->bft", basis, gM)
         gD = np.zeros_like(Dg)
         if g_specs_g is not None and g_specs_g[ri] is not None:
@@ -497,7 +508,7 @@ def rtg_multi_stft_loss_backward(y, y_g, g_loss=1.0, g_specs_g=None, hp=HP):
             np.add.at(gb, h - i, gp[i])
             np.add.at(gb, T - 2 - i, gp[h + T + i])
             g[b] += gb
-    return g
+    return g if tie_rel is None else (g, n_ties)
 
 
 def spectral_convergence(S_target, y, hp=HP):

@@ -1,0 +1,69 @@
+// Minimal producer / consumer hand-off through two mbarriers (full / empty), written the same way as feat3.cuh
+// (inline PTX: mbarrier.init by one thread + fence.mbarrier_init + __syncthreads, 32-lane arrive, try_wait.parity loop).
+// Used to find out what compute-sanitizer's synccheck / racecheck report for the bare pattern:
+//   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -o mbar_minimal mbar_minimal.cu
+//   compute-sanitizer --tool synccheck ./mbar_minimal ; compute-sanitizer --tool racecheck ./mbar_minimal
+#include <cstdio>
+#include <cuda_runtime.h>
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(unsigned addr, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned addr) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned addr, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}" ::"r"(addr), "r"(parity)
+      : "memory");
+}
+
+template <bool DYNAMIC>
+__global__ void handoff(float* out, int rounds) {
+  extern __shared__ __align__(16) unsigned char dyn[];
+  __shared__ __align__(16) unsigned char stat[32 * 4 + 16];
+  unsigned char* raw = DYNAMIC ? dyn : stat;
+  float* buf = reinterpret_cast<float*>(raw);
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(raw + 32 * 4);
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(bar), 32);
+    mbar_init(smem_u32(bar + 1), 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const unsigned full = smem_u32(bar), empty = smem_u32(bar + 1);
+  const int lane = threadIdx.x & 31;
+  float acc = 0.f;
+  for (int r = 0; r < rounds; ++r) {
+    if (threadIdx.x < 32) {
+      mbar_wait(empty, (r & 1) ^ 1);
+      buf[lane] = static_cast<float>(r * 32 + lane);
+      mbar_arrive(full);
+    } else {
+      mbar_wait(full, r & 1);
+      acc += buf[31 - lane];
+      mbar_arrive(empty);
+    }
+  }
+  if (threadIdx.x >= 32) out[lane] = acc;
+}
+
+int main() {
+  float* out;
+  cudaMalloc(&out, 32 * sizeof(float));
+  handoff<true><<<1, 64, 32 * 4 + 16>>>(out, 8);
+  cudaError_t e1 = cudaDeviceSynchronize();
+  handoff<false><<<1, 64>>>(out, 8);
+  cudaError_t e2 = cudaDeviceSynchronize();
+  float h[32];
+  cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
+  printf("dynamic smem: %s, static smem: %s, out[0] = %g (expect %g)\n", cudaGetErrorString(e1), cudaGetErrorString(e2), h[0],
+         8 * 31.f + 32.f * 28);
+  return 0;
+}

@@ -22,7 +22,7 @@ class Config(C.Structure):
 class Batch(C.Structure):
     _fields_ = [("B", C.c_int32), ("len", C.c_int64), ("stride", C.c_int64), ("sig_off", C.c_void_p),
                 ("sig_len", C.c_void_p), ("frame_off", C.c_void_p), ("item_off", C.c_void_p),
-                ("total_frames", C.c_int64), ("total_items", C.c_int64)]
+                ("total_frames", C.c_int64), ("total_items", C.c_int64), ("total_samples", C.c_int64)]
 
 
 class Scale(C.Structure):

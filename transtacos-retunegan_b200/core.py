@@ -126,7 +126,8 @@ class SignalBatch:
             self.total_frames = int(tbl[2, -1])
             self.tables = torch.from_numpy(tbl).to(self.x.device)
             self.c = Batch(self.B, 0, 0, self.tables[0].data_ptr(), self.tables[1].data_ptr(),
-                           self.tables[2].data_ptr(), self.tables[3].data_ptr(), self.total_frames, int(tbl[3, -1]))
+                           self.tables[2].data_ptr(), self.tables[3].data_ptr(), self.total_frames, int(tbl[3, -1]),
+                           int(self.x.numel()))
             self.uniform = False
         else:
             x = to_device_f32(ys)

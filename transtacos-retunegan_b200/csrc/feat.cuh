@@ -18,6 +18,7 @@ struct BatchDev {
   const long long* frame_off;
   const long long* item_off;
   long long total_items;
+  long long total_samples;   // ragged: samples in the flat buffer (0 = unknown)
   long long items_per_row;   // uniform
   long long frames_per_row;  // uniform
 };
@@ -191,13 +192,17 @@ __device__ __forceinline__ void mel_project_smem(const PlanDev& p, const float* 
 
 // Sum of the frames covering offset coordinate pp (= padded position - n_fft/4) of one utterance whose
 // frames are stored as fb[frame][win] (overlap-add written as a gather: deterministic, no atomics).
+// L2 = true: the frames were written earlier in the SAME launch by other CTAs (behind a grid barrier): read them through L2
+// (ld.global.cg), never through the non-coherent L1 / read-only path.
+template <bool L2 = false>
 __device__ __forceinline__ float ola_gather(const float* __restrict__ fb, int n_frames, int hop, int win, long long pp) {
   int tp = static_cast<int>(min(static_cast<long long>(n_frames - 1), pp / hop));
   float acc = 0.f;
   for (; tp >= 0; --tp) {
     const long long off = pp - static_cast<long long>(tp) * hop;
     if (off >= win) break;
-    acc += fb[static_cast<long long>(tp) * win + off];
+    const float* q = fb + static_cast<long long>(tp) * win + off;
+    acc += L2 ? __ldcg(q) : *q;
   }
   return acc;
 }

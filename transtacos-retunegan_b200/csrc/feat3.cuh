@@ -9,6 +9,8 @@
 // and moves on to the next item's FFT while the epilogue warp takes logs, stores and runs the mel filterbank.
 // Registers are re-partitioned with setmaxnreg (analysis 200, epilogue 56 per thread; 128 at launch).
 #pragma once
+#include <cuda.h>   // CUtensorMap (type only: the encoder is reached through cudaGetDriverEntryPoint, no libcuda link)
+
 #include "feat2.cuh"
 
 namespace sb200 {
@@ -29,15 +31,51 @@ __device__ __forceinline__ void mbar_init(unsigned addr, unsigned count) {
 __device__ __forceinline__ void mbar_arrive(unsigned addr) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(addr) : "memory");
 }
+// try_wait suspends the thread until the phase completes or a time limit expires; the explicit (large) suspend-time hint keeps
+// a waiting warp from waking up every few hundred cycles to re-issue the instruction (ncu: ~190 re-issues per item and epilogue
+// warp without it -- issue slots taken from the analysis warps).
 __device__ __forceinline__ void mbar_wait(unsigned addr, unsigned parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "WAIT_LOOP:\n\t"
+#ifndef SB200_TRYWAIT_NO_HINT
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+#else
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+#endif
       "@p bra DONE;\n\t"
       "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t}" ::"r"(addr), "r"(parity)
+      "DONE:\n\t}" ::"r"(addr), "r"(parity), "r"(0x989680u)
       : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned addr, unsigned bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(addr), "r"(bytes) : "memory");
+}
+// One bulk-tensor (TMA) copy of a 2-D box global -> shared, completion counted in bytes on an mbarrier (SASS: UTMALDG).
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map, int c0, int c1, unsigned bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+
+// Staging of an interior item's raw samples (hop 256, n_fft 2048).  A bulk-tensor copy must START on a 16-byte boundary of global
+// memory (measured: tools/sanitizer/tma_align.cu traps with "illegal instruction" at element offset 1), but the rows of a [B, L]
+// batch with odd L start anywhere.  The flat signal buffer is therefore described to the TMA unit as the 2-D tensor
+// t[j][c] = x[64 j + c] (overlapping rows: row stride 256 B, row length = the whole buffer), and the box {64 columns, 21 rows}
+// at (c0, 0) is the 1344 CONTIGUOUS samples x[c0 .. c0 + 1343]; c0 = (first sample of the pair's first frame - 4) rounded down
+// to a multiple of 4.  Sample i of the pair then sits at float index lead + i of the staging area, lead = 4 .. 7, and
+// x[p0 - 1], which the pre-emphasis FIR needs, at lead - 1.
+constexpr int kStageBoxCols = 64, kStageBoxRows = 21;
+constexpr int kStageFloats = kStageBoxCols * kStageBoxRows;     // 1344 >= 7 + 1280
+constexpr unsigned kStageBytes = kStageFloats * 4;
+
+// SB200_SANITIZER_NAMED_BARRIERS (tools/variants.py, sanitizer runs only): the same hand-off additionally bracketed by a named
+// barrier per warp pair (bar.sync id, 64: "empty" then "full", both warps run the same sequence).  compute-sanitizer's racecheck
+// models bar.sync but not an mbarrier arrive / try_wait pair written in inline PTX, so the product build shows the accesses on
+// either side of the mbarriers as hazards; with this variant it reports none, i.e. they are exactly the mbarrier-ordered pairs.
+__device__ __forceinline__ void pair_bar_sync(int w) {
+#ifdef SB200_SANITIZER_NAMED_BARRIERS
+  asm volatile("bar.sync %0, 64;" ::"r"(w + 1) : "memory");
+#endif
 }
 
 template <int N>
@@ -50,11 +88,11 @@ struct Smem3 {
   float2* sp2;              // [17*32]
   float* melw;              // [melw_count]
   int* mel_lo;              // [32*rounds]
-  unsigned long long* bar;  // [2*pairs]: full[w], empty[w]
+  unsigned long long* bar;  // [3*pairs]: full[w], empty[w], staged[w] (bulk-tensor copy of the next item's samples landed)
   __host__ __device__ static size_t bytes(int melw_count, int mel_rounds) {
     return static_cast<size_t>(kFeat3Pairs) * (C::kXBytes + kFeat3PbufElems * sizeof(pf)) + sizeof(float) * C::kWin +
            sizeof(float2) * (C::kTwCount + 17 * 32) + sizeof(float) * melw_count + sizeof(int) * 32 * mel_rounds +
-           sizeof(unsigned long long) * 2 * kFeat3Pairs;
+           sizeof(unsigned long long) * 3 * kFeat3Pairs;
   }
   __device__ __forceinline__ void carve(unsigned char* raw, const PlanDev& p) {
     xbufs = reinterpret_cast<uint4*>(raw);
@@ -151,9 +189,56 @@ __device__ __forceinline__ void gather_item3(PC (&v)[32], const Item& it, const 
   }
 }
 
+// Pass-A registers of an interior item whose samples a bulk-tensor copy has staged in shared memory: sample i of the pair at
+// stage[lead + i].  Same arithmetic as the global-load path of gather_item3 (bit-identical results); the FIR's previous sample
+// is read from the staging area too (no shuffle, no carry).  ODD = lead is odd: the 8-byte aligned pair then holds
+// (previous, even) and the odd sample comes from the 4-byte load; else (even, odd) and the previous sample does.
+template <int N, bool PRE, int HS, bool ODD>
+__device__ __forceinline__ void gather_staged3(PC (&v)[32], const float* __restrict__ q /* stage + (lead & ~1) + 2 lane */,
+                                               float pre, const float* __restrict__ s_win, int lane) {
+  using C = Fft2Cfg<N>;
+  constexpr int kSlots = C::kR + HS;
+  float lo[kSlots], hi[kSlots];
+  static_for<0, kSlots>([&](auto rc) {
+    constexpr int r = decltype(rc)::value;
+    const float2 t = *reinterpret_cast<const float2*>(q + 64 * r);
+    if constexpr (!ODD) {
+      lo[r] = t.x;
+      hi[r] = t.y;
+      if constexpr (PRE) {
+        const float pv = q[64 * r - 1];
+        hi[r] = fmaf(-pre, t.x, t.y);
+        lo[r] = fmaf(-pre, pv, t.x);
+      }
+    } else {
+      const float h = q[64 * r + 2];
+      lo[r] = t.y;
+      hi[r] = h;
+      if constexpr (PRE) {
+        hi[r] = fmaf(-pre, t.y, h);
+        lo[r] = fmaf(-pre, t.x, t.y);
+      }
+    }
+  });
+  static_for<0, C::kR>([&](auto rc) {
+    constexpr int r = decltype(rc)::value;
+    const float2 w = *reinterpret_cast<const float2*>(s_win + 2 * lane + 64 * r);
+    constexpr int idx = brev(r, C::kLogR2);
+    v[idx].re = pk(lo[r] * w.x, lo[r + HS] * w.x);
+    v[idx].im = pk(hi[r] * w.y, hi[r + HS] * w.y);
+    v[idx + 1] = v[idx];
+  });
+}
+
+// What the analysis warps need to know about the bulk-tensor staging (TMA == true only).
+struct StageArgs {
+  long long total;   // samples the flat buffer holds from x: a staged box must end inside it (else the item takes the edge path)
+};
+
 // ---- analysis warp: gather + window + FFT + Hermitian split; |A|^2 of every bin goes to the pair's power buffer ----
-template <int N, bool PRE, int HS>
-__device__ __forceinline__ void feat3_analysis(const PlanDev& p, const FeatArgs& a, Smem3<N>& sm, int w, int lane) {
+template <int N, bool PRE, int HS, bool TMA>
+__device__ __forceinline__ void feat3_analysis(const PlanDev& p, const FeatArgs& a, Smem3<N>& sm, int w, int lane,
+                                               const CUtensorMap* tmap, const StageArgs sa_) {
   using C = Fft2Cfg<N>;
   uint4* xbuf = sm.xbufs + w * C::kXElems;
   pf* pbuf = sm.pbufs + w * kFeat3PbufElems;
@@ -168,14 +253,55 @@ __device__ __forceinline__ void feat3_analysis(const PlanDev& p, const FeatArgs&
   const long long warps_total = static_cast<long long>(gridDim.x) * kFeat3Pairs;
   long long item = static_cast<long long>(blockIdx.x) * kFeat3Pairs + w;
   unsigned round = 0;
+  // TMA: while pass B and the split of item n run, ONE elected lane has the TMA unit copy the samples of item n + 1 (an
+  // interior frame pair: 1280 contiguous samples and the few before them) into this warp's exchange buffer, which is idle from
+  // the transposed read of item n to the transposed write of item n + 1; the copy completes on an mbarrier (bytes).  The
+  // gather then costs 56 shared-memory loads and no global-load latency on the critical warp.
+  const unsigned staged_bar = smem_u32(sm.bar + 2 * kFeat3Pairs + w);
+  unsigned staged_phase = 0;
+  bool staged = false;
+  auto stage_start = [&](const Item& ni) -> long long {   // first sample of the box, or -1 if the item is not staged
+    const long long p0 = static_cast<long long>(ni.t0) * p.hop - N / 4;
+    const long long g0 = (ni.sig_base + p0 - 4) & ~3LL;
+    const bool interior = (ni.t0 + 1 < ni.T) && p0 >= 1 && p0 + p.hop + C::kWin <= ni.L && ni.sig_base + p0 >= 4 &&
+                          g0 + kStageFloats <= sa_.total;
+    return interior ? g0 : -1;
+  };
+  auto stage_next = [&](long long nxt) -> bool {
+    if (nxt >= a.bd.total_items) return false;
+    const long long g0 = stage_start(decode_item(a.bd, nxt, C::kFrames));
+    if (g0 >= 0 && lane == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the warp's generic-proxy reads of the buffer come first
+      mbar_expect_tx(staged_bar, kStageBytes);
+      tma_load_2d(smem_u32(xbuf), tmap, static_cast<int>(g0), 0, staged_bar);
+    }
+    return g0 >= 0;
+  };
+  if constexpr (TMA) staged = stage_next(item);
   for (; item < a.bd.total_items; item += warps_total, ++round) {
     // No register prefetch across items: ptxas spills whatever stays live over the loop edge when the register budget comes
-    // from setmaxnreg; the other three warps of the scheduler cover the load latency.  (Measured and dropped: an L2 prefetch
-    // of the next item from the epilogue warp, +1 us; a second copy of the loop body for the edge path, +3.7 us.)
+    // from setmaxnreg.  (Measured and dropped: an L2 prefetch of the next item from the epilogue warp, +1 us; a second copy
+    // of the loop body for the edge path, +3.7 us; cp.async staging, +7 us.)
     const Item it = decode_item(a.bd, item, C::kFrames);
     PC v[32];
-    gather_item3<N, PRE, HS>(v, it, a.x, p.hop, a.pre, sm.win, reinterpret_cast<float*>(xbuf), lane);
-    fft2_forward<N>(v, xbuf, sm.tw, lane);
+    if constexpr (TMA) {
+      if (staged) {
+        const long long p0 = static_cast<long long>(it.t0) * p.hop - N / 4;
+        const int lead = static_cast<int>(it.sig_base + p0 - stage_start(it));   // 4 .. 7
+        const float* q = reinterpret_cast<const float*>(xbuf) + (lead & ~1) + 2 * lane;
+        mbar_wait(staged_bar, staged_phase);
+        staged_phase ^= 1;
+        if (lead & 1) gather_staged3<N, PRE, HS, true>(v, q, a.pre, sm.win, lane);
+        else gather_staged3<N, PRE, HS, false>(v, q, a.pre, sm.win, lane);
+        __syncwarp();   // every lane has its samples before the transpose overwrites the staging area
+      } else {          // edge items (reflect padding, odd tail): per-frame path
+        gather_item3<N, PRE, 0>(v, it, a.x, p.hop, a.pre, sm.win, reinterpret_cast<float*>(xbuf), lane);
+      }
+      fft2_forward_h<N, true>(v, xbuf, sm.tw, lane, [&] { staged = stage_next(item + warps_total); });
+    } else {
+      gather_item3<N, PRE, HS>(v, it, a.x, p.hop, a.pre, sm.win, reinterpret_cast<float*>(xbuf), lane);
+      fft2_forward<N>(v, xbuf, sm.tw, lane);
+    }
     // lane (pl, k1) now holds Z[k1 + R2*k2] of frames t0 + 2 pl, t0 + 2 pl + 1
     // all split twiddles up front: a table load written after a store to the power buffer cannot be hoisted above it
     float2 spv[17];
@@ -184,6 +310,7 @@ __device__ __forceinline__ void feat3_analysis(const PlanDev& p, const FeatArgs&
       spv[s] = sp[s * 32];
     });
     mbar_wait(empty, (round & 1) ^ 1);   // the epilogue warp is done with the previous item's powers
+    pair_bar_sync(w);
     {
       // self pair of column 0 (bin Nz/2) first: the exchange below overwrites v[16]
       PC ak, am;
@@ -201,6 +328,7 @@ __device__ __forceinline__ void feat3_analysis(const PlanDev& p, const FeatArgs&
       else sb[-C::kR2 * s] = norm2(am);
     });
     mbar_arrive(full);
+    pair_bar_sync(w);
   }
 }
 
@@ -219,7 +347,9 @@ __device__ __forceinline__ void feat3_epilogue(const PlanDev& p, const FeatArgs&
   unsigned round = 0;
   for (long long item = static_cast<long long>(blockIdx.x) * kFeat3Pairs + w; item < a.bd.total_items; item += warps_total, ++round) {
     const Item it = decode_item(a.bd, item, C::kFrames);
+    pair_bar_sync(w);
     mbar_wait(full, round & 1);
+    pair_bar_sync(w);
 #pragma unroll
     for (int q = 0; q < C::kP; ++q) {
       const int fA = it.t0 + 2 * q;
@@ -308,20 +438,32 @@ __device__ __forceinline__ void feat3_epilogue(const PlanDev& p, const FeatArgs&
   }
 }
 
-template <int N, bool PRE, int HS>
-__global__ void __launch_bounds__(kFeat3Threads, 1) stft_feature3_kernel(const PlanDev p, const FeatArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+template <int N, bool PRE, int HS, bool TMA>
+__global__ void __launch_bounds__(kFeat3Threads, 1) stft_feature3_kernel(const PlanDev p, const FeatArgs a,
+                                                                          const __grid_constant__ CUtensorMap tmap,
+                                                                          const StageArgs sa) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];   // bulk-tensor copies land in 128-byte aligned shared memory
   Smem3<N> sm;
   sm.carve(smem_raw, p);
   sm.fill(p, a.mel != nullptr);
-  if (threadIdx.x < 2 * kFeat3Pairs) mbar_init(smem_u32(sm.bar + threadIdx.x), 32);
+  if (threadIdx.x < 3 * kFeat3Pairs) {   // full / empty: 32 lane arrivals; staged: the one expect_tx arrival of the issuing lane
+    mbar_init(smem_u32(sm.bar + threadIdx.x), threadIdx.x < 2 * kFeat3Pairs ? 32 : 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // SB200_NO_SETMAXNREG (sanitizer variant, tools/variants.py): no register re-partitioning, the whole kernel is compiled for
+  // the 128 registers per thread of the launch (the analysis role spills).  compute-sanitizer patches the kernel with code of its
+  // own that needs registers too: with setmaxnreg in the kernel its synccheck / racecheck lose track of the mbarriers.
   if (warp < kFeat3Pairs) {
+#ifndef SB200_NO_SETMAXNREG
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kFeat3AnalysisRegs));
-    feat3_analysis<N, PRE, HS>(p, a, sm, warp, lane);
+#endif
+    feat3_analysis<N, PRE, HS, TMA>(p, a, sm, warp, lane, &tmap, sa);
   } else {
+#ifndef SB200_NO_SETMAXNREG
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kFeat3EpilogueRegs));
+#endif
     feat3_epilogue<N>(p, a, sm, warp - kFeat3Pairs, lane);
   }
 }

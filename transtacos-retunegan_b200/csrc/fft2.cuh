@@ -206,9 +206,13 @@ struct Fft2Cfg {
 // On entry v[p*R2 + brev(r)] = v[p*R2 + brev(r) + 1] = z_p[lane + 32 r], r < R (brev over log2(R2) bits).
 // On exit lane j = p*R2 + k1 holds Z_p[k1 + R2*k2] in v[k2], k2 = 0..31.  xbuf: this warp's exchange buffer.
 // tw: smem table tw[(k1-1)*32 + lane] = w_Nz^{k1*lane}.
-template <int N>
-__device__ __forceinline__ void fft2_forward(PC (&v)[32], uint4* __restrict__ xbuf, const float2* __restrict__ tw,
-                                             int lane) {
+// xbuf_free(): called once every lane has read its transposed column, i.e. as soon as the exchange buffer may be reused
+// (feat3.cuh issues the bulk-tensor copy of the NEXT item's samples into it there, under pass B and the split).
+// EARLY = true: the warp synchronises right after the transposed read and calls xbuf_free() before pass B; false: pass B first
+// (its leading butterflies overlap the tail of the loads), synchronisation at the end, no hook.
+template <int N, bool EARLY, class Hook>
+__device__ __forceinline__ void fft2_forward_h(PC (&v)[32], uint4* __restrict__ xbuf, const float2* __restrict__ tw,
+                                               int lane, Hook&& xbuf_free) {
   using C = Fft2Cfg<N>;
   static_for<0, C::kP>([&](auto pc_) {
     constexpr int p = decltype(pc_)::value;
@@ -261,8 +265,19 @@ __device__ __forceinline__ void fft2_forward(PC (&v)[32], uint4* __restrict__ xb
     v[brev(n1, 5)].re = lds_pf<8 * C::xoff(n1)>(rcol);
     v[brev(n1, 5)].im = lds_pf<C::kPlane + 8 * C::xoff(n1)>(rcol);
   });
-  dit<32, 0, false, 2>(v);
-  __syncwarp();   // exchange buffer free again
+  if constexpr (EARLY) {
+    __syncwarp();   // exchange buffer free again
+    xbuf_free();
+    dit<32, 0, false, 2>(v);
+  } else {
+    dit<32, 0, false, 2>(v);
+    __syncwarp();   // exchange buffer free again
+  }
+}
+template <int N>
+__device__ __forceinline__ void fft2_forward(PC (&v)[32], uint4* __restrict__ xbuf, const float2* __restrict__ tw,
+                                             int lane) {
+  fft2_forward_h<N, false>(v, xbuf, tw, lane, [] {});
 }
 
 // ---- Hermitian split on packed data -------------------------------------------------------------------------

@@ -82,10 +82,11 @@ __device__ __forceinline__ void mstft_analyse(const PlanDev& p, const SmemTables
   __syncwarp();
 }
 
+// vb / nvb: index of this CTA among the CTAs working on this resolution and their number (the per-resolution kernel passes
+// blockIdx.x / gridDim.x; the all-resolution kernel deals its CTAs to the resolutions round-robin).
 template <int N>
-__global__ void __launch_bounds__(kMstftWarps * 32, 2) mstft_fwd_kernel(const PlanDev p, const MstftFwdArgs a) {
+__device__ __forceinline__ void mstft_fwd_body(const PlanDev& p, const MstftFwdArgs& a, unsigned char* smem_raw, int vb, int nvb) {
   using C = FftCfg<N>;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemTables<N> sm;
   sm.carve(smem_raw, p);
   sm.fill(p, p.window, true);
@@ -95,8 +96,8 @@ __global__ void __launch_bounds__(kMstftWarps * 32, 2) mstft_fwd_kernel(const Pl
   float acc = 0.f;
   const long long chs = static_cast<long long>(a.Tf) * C::kF;
   // an item is 2Q frames (packed-engine granularity); this engine takes it as two independent Q-frame passes
-  for (long long sub = static_cast<long long>(blockIdx.x) * kMstftWarps + warp; sub < 2 * a.bd.total_items;
-       sub += static_cast<long long>(gridDim.x) * kMstftWarps) {
+  for (long long sub = static_cast<long long>(vb) * kMstftWarps + warp; sub < 2 * a.bd.total_items;
+       sub += static_cast<long long>(nvb) * kMstftWarps) {
     Item it = decode_item(a.bd, sub >> 1, 2 * C::kQ);
     it.t0 += static_cast<int>(sub & 1) * C::kQ;
     if (it.t0 < it.T) {
@@ -127,7 +128,13 @@ __global__ void __launch_bounds__(kMstftWarps * 32, 2) mstft_fwd_kernel(const Pl
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(kFullMask, acc, d);
-  if (lane == 0) a.partials[blockIdx.x * kMstftWarps + warp] = acc;
+  if (lane == 0) a.partials[vb * kMstftWarps + warp] = acc;
+}
+
+template <int N>
+__global__ void __launch_bounds__(kMstftWarps * 32, 2) mstft_fwd_kernel(const PlanDev p, const MstftFwdArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  mstft_fwd_body<N>(p, a, smem_raw, blockIdx.x, gridDim.x);
 }
 
 struct MstftFinArgs {
@@ -137,13 +144,13 @@ struct MstftFinArgs {
   float inv_count[kMaxRes];   // 1 / (B * n_mel * Tf)
   float* loss;
 };
-// loss = 1/n_res * sum_res (sum of partials) / count   (F.l1_loss reduction='mean', loss.py:51-54)
-__global__ void mstft_finalize_kernel(const MstftFinArgs a) {
+// loss = 1/n_res * sum_res (sum of partials) / count   (F.l1_loss reduction='mean', loss.py:51-54); one CTA, fixed order
+__device__ __forceinline__ void mstft_finalize_body(const MstftFinArgs& a) {
   __shared__ float red[32];
   float total = 0.f;
   for (int r = 0; r < a.n_res; ++r) {
     float s = 0.f;
-    for (int i = threadIdx.x; i < a.n_partials[r]; i += blockDim.x) s += a.partials[r][i];
+    for (int i = threadIdx.x; i < a.n_partials[r]; i += blockDim.x) s += __ldcg(a.partials[r] + i);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(kFullMask, s, d);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -157,6 +164,7 @@ __global__ void mstft_finalize_kernel(const MstftFinArgs a) {
   }
   if (threadIdx.x == 0) *a.loss = total / a.n_res;
 }
+__global__ void mstft_finalize_kernel(const MstftFinArgs a) { mstft_finalize_body(a); }
 
 struct MstftBwdArgs {
   const float* yg;
@@ -217,9 +225,8 @@ __device__ __forceinline__ void mel_project_cplx(const PlanDev& p, const float* 
 // 14.6 k instructions).  The Hermitian-pair work (forward split, gradient of every bin, inverse split) therefore runs as
 // ROLLED loops over the spectrum kept in the warp's shared-memory buffer instead of unrolled over register arrays.
 template <int N, bool FUSED>
-__global__ void __launch_bounds__(kMstftWarps * 32, 2) mstft_bwd_kernel(const PlanDev p, const MstftBwdArgs a) {
+__device__ __forceinline__ void mstft_bwd_body(const PlanDev& p, const MstftBwdArgs& a, unsigned char* smem_raw, int vb, int nvb) {
   using C = FftCfg<N>;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemTables<N> sm;
   sm.carve(smem_raw, p);
   sm.fill(p, p.window, true);
@@ -234,8 +241,8 @@ __global__ void __launch_bounds__(kMstftWarps * 32, 2) mstft_bwd_kernel(const Pl
   const float gl = FUSED ? a.loss_scale : (a.g_loss ? __ldg(a.g_loss) * a.loss_scale : 0.f);
   float loss_acc = 0.f;
   const long long chs = static_cast<long long>(a.Tf) * C::kF;
-  for (long long sub = static_cast<long long>(blockIdx.x) * kMstftWarps + warp; sub < 2 * a.bd.total_items;
-       sub += static_cast<long long>(gridDim.x) * kMstftWarps) {
+  for (long long sub = static_cast<long long>(vb) * kMstftWarps + warp; sub < 2 * a.bd.total_items;
+       sub += static_cast<long long>(nvb) * kMstftWarps) {
     Item it = decode_item(a.bd, sub >> 1, 2 * C::kQ);
     it.t0 += static_cast<int>(sub & 1) * C::kQ;
     if (it.t0 < it.T) {
@@ -383,8 +390,14 @@ __global__ void __launch_bounds__(kMstftWarps * 32, 2) mstft_bwd_kernel(const Pl
   if constexpr (FUSED) {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) loss_acc += __shfl_xor_sync(kFullMask, loss_acc, d);
-    if (lane == 0) a.partials[blockIdx.x * kMstftWarps + warp] = loss_acc;
+    if (lane == 0) a.partials[vb * kMstftWarps + warp] = loss_acc;
   }
+}
+
+template <int N, bool FUSED>
+__global__ void __launch_bounds__(kMstftWarps * 32, 2) mstft_bwd_kernel(const PlanDev p, const MstftBwdArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  mstft_bwd_body<N, FUSED>(p, a, smem_raw, blockIdx.x, gridDim.x);
 }
 
 // g_yg[b, j] = sum_res ( gp[h + j] + [1 <= j <= h] gp[h - j] + [T-2-h < j <= T-2] gp[h + 2T - 2 - j] ),
@@ -397,24 +410,113 @@ struct GradOlaArgs {
   long long T;
   float* g;
 };
+template <bool L2>
+__device__ __forceinline__ float grad_ola_sample(const GradOlaArgs& a, int b, long long j) {
+  float acc = 0.f;
+  for (int r = 0; r < a.n_res; ++r) {
+    const int N = a.n_fft[r], h = N / 2, win = N / 2, hop = a.hop[r], Tf = a.Tf[r];
+    const float* fb = a.gfb[r] + static_cast<long long>(b) * Tf * win;
+    // padded position P -> offset coordinate P - N/4; positions outside every window contribute 0
+    auto gp = [&](long long P) -> float {
+      const long long pp = P - N / 4;
+      return pp >= 0 ? ola_gather<L2>(fb, Tf, hop, win, pp) : 0.f;
+    };
+    acc += gp(h + j);
+    if (j >= 1 && j <= h) acc += gp(h - j);
+    if (j > a.T - 2 - h && j <= a.T - 2) acc += gp(h + 2 * a.T - 2 - j);
+  }
+  return acc;
+}
 __global__ void grad_ola_kernel(const GradOlaArgs a) {
   const int b = blockIdx.y;
   for (long long j = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; j < a.T;
-       j += static_cast<long long>(gridDim.x) * blockDim.x) {
-    float acc = 0.f;
-    for (int r = 0; r < a.n_res; ++r) {
-      const int N = a.n_fft[r], h = N / 2, win = N / 2, hop = a.hop[r], Tf = a.Tf[r];
-      const float* fb = a.gfb[r] + static_cast<long long>(b) * Tf * win;
-      // padded position P -> offset coordinate P - N/4; positions outside every window contribute 0
-      auto gp = [&](long long P) -> float {
-        const long long pp = P - N / 4;
-        return pp >= 0 ? ola_gather(fb, Tf, hop, win, pp) : 0.f;
-      };
-      acc += gp(h + j);
-      if (j >= 1 && j <= h) acc += gp(h - j);
-      if (j > a.T - 2 - h && j <= a.T - 2) acc += gp(h + 2 * a.T - 2 - j);
-    }
-    a.g[static_cast<long long>(b) * a.T + j] = acc;
+       j += static_cast<long long>(gridDim.x) * blockDim.x)
+    a.g[static_cast<long long>(b) * a.T + j] = grad_ola_sample<false>(a, b, j);
+}
+
+// ---- all resolutions in ONE launch ------------------------------------------------------------------------------------------
+// The per-resolution kernels above are each well under one wave of the GPU (184 CTAs at the training size) and were run on three
+// streams, followed by the reduction and the overlap-add as two more launches: 552 CTAs over 296 resident slots plus fork / join
+// events and two small kernels per step.  Here ONE grid of resident CTAs (<= 2 per SM) deals its CTAs to the resolutions round-robin
+// (CTA c works on resolution c % n_res: one set of tables, one code body per CTA), every CTA loops over the items of its
+// resolution, and the tail runs in the same launch: the loss reduction by the last CTA to finish (threadfence reduction, no
+// spinning), the gradient overlap-add by ALL CTAs after a grid barrier (cooperative launch: the CTAs are co-resident).
+struct MstftAllFwdArgs {
+  int n_res;
+  PlanDev plan[kMaxRes];
+  MstftFwdArgs f[kMaxRes];
+  MstftFinArgs fin;        // fin.loss == nullptr: no reduction
+  unsigned* counter;       // zeroed before the launch
+};
+struct MstftAllBwdArgs {
+  int n_res;
+  PlanDev plan[kMaxRes];
+  MstftBwdArgs b[kMaxRes];
+  MstftFinArgs fin;        // FUSED only
+  GradOlaArgs ola;
+  unsigned* counter;       // [2]: finished-CTA count (loss reduction), grid barrier; zeroed before the launch
+};
+
+__device__ __forceinline__ void mstft_split_grid(int n_res, int* r, int* vb, int* nvb) {
+  *r = static_cast<int>(blockIdx.x) % n_res;
+  *vb = static_cast<int>(blockIdx.x) / n_res;
+  *nvb = (static_cast<int>(gridDim.x) - *r + n_res - 1) / n_res;
+}
+// true in exactly one CTA: the last one to get here (everything the others wrote before is visible to it)
+__device__ __forceinline__ bool mstft_last_cta(unsigned* counter) {
+  __shared__ unsigned last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    __threadfence();
+  }
+  __syncthreads();
+  return last != 0;
+}
+
+__global__ void __launch_bounds__(kMstftWarps * 32, 2) mstft_all_fwd_kernel(const __grid_constant__ MstftAllFwdArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int r, vb, nvb;
+  mstft_split_grid(A.n_res, &r, &vb, &nvb);
+  switch (A.plan[r].n_fft) {
+    case 2048: mstft_fwd_body<2048>(A.plan[r], A.f[r], smem_raw, vb, nvb); break;
+    case 1024: mstft_fwd_body<1024>(A.plan[r], A.f[r], smem_raw, vb, nvb); break;
+    default: mstft_fwd_body<512>(A.plan[r], A.f[r], smem_raw, vb, nvb); break;
+  }
+  if (A.fin.loss != nullptr && mstft_last_cta(A.counter)) mstft_finalize_body(A.fin);
+}
+
+template <bool FUSED>
+__global__ void __launch_bounds__(kMstftWarps * 32, 2) mstft_all_bwd_kernel(const __grid_constant__ MstftAllBwdArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int r, vb, nvb;
+  mstft_split_grid(A.n_res, &r, &vb, &nvb);
+  switch (A.plan[r].n_fft) {
+    case 2048: mstft_bwd_body<2048, FUSED>(A.plan[r], A.b[r], smem_raw, vb, nvb); break;
+    case 1024: mstft_bwd_body<1024, FUSED>(A.plan[r], A.b[r], smem_raw, vb, nvb); break;
+    default: mstft_bwd_body<512, FUSED>(A.plan[r], A.b[r], smem_raw, vb, nvb); break;
+  }
+  // grid barrier: every gradient frame and partial sum is written and visible
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(A.counter, 1u);
+    unsigned seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(A.counter) : "memory");
+    } while (seen < gridDim.x);
+    __threadfence();
+  }
+  __syncthreads();
+  if constexpr (FUSED) {
+    if (blockIdx.x == 0) mstft_finalize_body(A.fin);
+  }
+  const long long total = static_cast<long long>(A.ola.B) * A.ola.T;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(i / A.ola.T);
+    A.ola.g[i] = grad_ola_sample<true>(A.ola, b, i - static_cast<long long>(b) * A.ola.T);
   }
 }
 

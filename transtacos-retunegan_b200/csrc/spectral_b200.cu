@@ -64,6 +64,7 @@ int make_batch_signal(const sb200_plan* plan, const sb200_batch* b, BatchDev* ou
     d.frame_off = reinterpret_cast<const long long*>(b->frame_off);
     d.item_off = reinterpret_cast<const long long*>(b->item_off);
     d.total_items = b->total_items;
+    d.total_samples = b->total_samples;
     *total_frames = b->total_frames;
   }
   *out = d;

@@ -1,4 +1,5 @@
 // C-ABI entry points: multi-resolution STFT loss forward / backward (include/spectral_b200.h).
+#include <cstdlib>
 #include <mutex>
 
 #include "capi_common.cuh"
@@ -90,6 +91,49 @@ static int64_t mstft_ws_gfb_off(const sb200_plan* const* plans, int r, int32_t B
   return off;
 }
 static int64_t mstft_partials_bytes() { return ((2LL * sm_count() * kMstftWarps * 4 + 255) / 256) * 256; }
+// two 32-bit counters of the single-launch kernels (finished CTAs, grid barrier), behind the partial sums
+static int64_t mstft_counter_off(const sb200_plan* const* plans, int32_t n_res, int32_t B, int64_t T) {
+  return mstft_ws_gfb_off(plans, n_res, B, T) + n_res * mstft_partials_bytes();
+}
+
+// SB200_MSTFT_SINGLE=1 selects ONE cooperative launch for all resolutions with the loss reduction and the overlap-add folded in
+// (mstft_all_*_kernel).  OFF BY DEFAULT: measured on B200 at 16 x 22 050 it is slower than the per-resolution launches on side
+// streams, 190 us against 180 us per loss-only step and 410 against 393 us with spec stacks (tools/ab_mstft.sh,
+// profiles/r02_mstft_summary.md): a warp's pass is a long dependent chain (~6000 instructions, issue-active 15-17 %), the
+// resident grid gives every warp two passes back to back where the three concurrent kernels give the hardware scheduler
+// 552 one-pass CTAs to pack, and the folded tail does not make up for it.
+static bool mstft_single_enabled() {
+  static const int v = [] {
+    const char* e = std::getenv("SB200_MSTFT_SINGLE");
+    return e ? std::atoi(e) : 0;
+  }();
+  return v != 0;
+}
+
+static size_t mstft_all_smem(const sb200_plan* const* plans, int32_t n_res, bool bwd) {
+  size_t smem = 0;
+  for (int r = 0; r < n_res; ++r) {
+    size_t s = 0;
+    SB200_DISPATCH_N(plans[r], s = bwd ? mstft_bwd_smem_bytes<kN>(plans[r]->dev) : feat_smem_bytes<kN>(plans[r]->dev));
+    smem = std::max(smem, s);
+  }
+  return smem;
+}
+
+// Grid of the all-resolution kernels: the CTAs the work needs, capped at what is resident at once (cooperative launch).
+template <class Kern>
+static int mstft_all_grid(Kern kern, size_t smem, const long long* subs, int n_res) {
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kMstftWarps * 32, smem) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    return 0;
+  }
+  long long need = 0;   // round-robin dealing: every resolution gets ceil(grid / n_res) or floor(grid / n_res) CTAs
+  for (int r = 0; r < n_res; ++r) need = std::max(need, (subs[r] + kMstftWarps - 1) / kMstftWarps);
+  need *= n_res;
+  return static_cast<int>(std::min<long long>(need, static_cast<long long>(per_sm) * sm_count()));
+}
 
 int64_t sb200_mstft_saved_bytes(const sb200_plan* const* plans, int32_t n_res, int32_t B, int64_t T) {
   if (mstft_check(plans, n_res, B, T)) return -1;
@@ -131,16 +175,104 @@ static BatchDev mstft_batch(const sb200_plan* plan, int32_t B, int64_t T) {
   return d;
 }
 
+// Backward (g_specs / g_loss) or fused loss + gradient, all resolutions + overlap-add (+ loss reduction) in one cooperative launch.
+// Returns SB200_OK, an error, or 1 when the single-launch path is not available (caller falls back).
+static int mstft_all_bwd(const sb200_plan* const* plans, int32_t n_res, const float* y, const float* y_g, int32_t B, int64_t T,
+                         int32_t phd_phase, const float* g_loss, const float* const* g_specs_g, const void* saved, float* loss,
+                         float* g_yg, char* ws, bool fused, cudaStream_t st) {
+  if (!mstft_single_enabled()) return 1;
+  MstftAllBwdArgs A{};
+  A.n_res = n_res;
+  A.fin.n_res = n_res;
+  A.fin.loss = loss;
+  A.ola.n_res = n_res;
+  A.ola.B = B;
+  A.ola.T = T;
+  A.ola.g = g_yg;
+  A.counter = reinterpret_cast<unsigned*>(ws + mstft_counter_off(plans, n_res, B, T));
+  const int64_t part0 = mstft_ws_gfb_off(plans, n_res, B, T);
+  long long subs[kMaxRes];
+  for (int r = 0; r < n_res; ++r) {
+    const sb200_plan* plan = plans[r];
+    MstftBwdArgs& a = A.b[r];
+    A.plan[r] = plan->dev;
+    a.y = y;
+    a.yg = y_g;
+    a.bd = mstft_batch(plan, B, T);
+    a.Tf = static_cast<int>(a.bd.frames_per_row);
+    a.mel_r = saved ? reinterpret_cast<const float*>(static_cast<const char*>(saved) + mstft_saved_off(plans, r, B, T)) : nullptr;
+    a.g_loss = g_loss;
+    a.loss_scale = static_cast<float>(1.0 / (static_cast<double>(n_res) * B * plan->cfg.n_mel * a.Tf));
+    a.g_spec = g_specs_g ? g_specs_g[r] : nullptr;
+    a.phd_phase = phd_phase;
+    a.gfb = reinterpret_cast<float*>(ws + mstft_ws_gfb_off(plans, r, B, T));
+    a.partials = reinterpret_cast<float*>(ws + part0 + r * mstft_partials_bytes());
+    subs[r] = 2 * a.bd.total_items;
+    A.fin.partials[r] = a.partials;
+    A.fin.inv_count[r] = static_cast<float>(1.0 / (static_cast<double>(B) * plan->cfg.n_mel * a.Tf));
+    A.ola.gfb[r] = a.gfb;
+    A.ola.n_fft[r] = plan->cfg.n_fft;
+    A.ola.hop[r] = plan->cfg.hop_length;
+    A.ola.Tf[r] = a.Tf;
+  }
+  const size_t smem = mstft_all_smem(plans, n_res, true);
+  const void* kern = fused ? reinterpret_cast<const void*>(mstft_all_bwd_kernel<true>) : reinterpret_cast<const void*>(mstft_all_bwd_kernel<false>);
+  const int grid = fused ? mstft_all_grid(mstft_all_bwd_kernel<true>, smem, subs, n_res) : mstft_all_grid(mstft_all_bwd_kernel<false>, smem, subs, n_res);
+  if (grid <= 0) return 1;
+  for (int r = 0; r < n_res; ++r) A.fin.n_partials[r] = ((grid - r + n_res - 1) / n_res) * kMstftWarps;
+  cudaMemsetAsync(A.counter, 0, 2 * sizeof(unsigned), st);
+  void* args[] = {&A};
+  if (cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kMstftWarps * 32), args, smem, st) != cudaSuccess) {
+    cudaGetLastError();
+    return 1;
+  }
+  return check_launch(fused ? "mstft_all_bwd_kernel<fused>" : "mstft_all_bwd_kernel");
+}
+
 int sb200_mstft_forward(const sb200_plan* const* plans, int32_t n_res, const float* y, const float* y_g, int32_t B,
                         int64_t T, int32_t phd_phase, float* loss, float* const* specs_r, float* const* specs_g,
                         void* saved, void* workspace, sb200_stream stream) {
   if (int rc = mstft_check(plans, n_res, B, T)) return rc;
   if (!y || !y_g || !saved || !workspace) return fail(SB200_ERR_INVALID, "mstft_forward: null argument");
-  std::lock_guard<std::mutex> enqueue_lock(g_mstft_enqueue_mu);
   if (!loss && !specs_r && !specs_g) return fail(SB200_ERR_INVALID, "mstft_forward: neither loss nor specs requested (loss.py:62 raises)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   char* ws = static_cast<char*>(workspace);
   const int64_t part0 = mstft_ws_gfb_off(plans, n_res, B, T);
+  if (mstft_single_enabled()) {
+    MstftAllFwdArgs A{};
+    A.n_res = n_res;
+    A.fin.n_res = n_res;
+    A.fin.loss = loss;
+    A.counter = reinterpret_cast<unsigned*>(ws + mstft_counter_off(plans, n_res, B, T));
+    long long subs[kMaxRes];
+    for (int r = 0; r < n_res; ++r) {
+      const sb200_plan* plan = plans[r];
+      MstftFwdArgs& a = A.f[r];
+      A.plan[r] = plan->dev;
+      a.y = y;
+      a.yg = y_g;
+      a.bd = mstft_batch(plan, B, T);
+      a.Tf = static_cast<int>(a.bd.frames_per_row);
+      a.spec_r = specs_r ? specs_r[r] : nullptr;
+      a.spec_g = specs_g ? specs_g[r] : nullptr;
+      a.phd_phase = phd_phase;
+      a.mel_r = reinterpret_cast<float*>(static_cast<char*>(saved) + mstft_saved_off(plans, r, B, T));
+      a.partials = reinterpret_cast<float*>(ws + part0 + r * mstft_partials_bytes());
+      a.want_loss = loss != nullptr;
+      subs[r] = 2 * a.bd.total_items;
+      A.fin.partials[r] = a.partials;
+      A.fin.inv_count[r] = static_cast<float>(1.0 / (static_cast<double>(B) * plan->cfg.n_mel * a.Tf));
+    }
+    const size_t smem = mstft_all_smem(plans, n_res, false);
+    const int grid = mstft_all_grid(mstft_all_fwd_kernel, smem, subs, n_res);
+    if (grid > 0) {
+      for (int r = 0; r < n_res; ++r) A.fin.n_partials[r] = ((grid - r + n_res - 1) / n_res) * kMstftWarps;
+      if (loss) cudaMemsetAsync(A.counter, 0, 2 * sizeof(unsigned), st);
+      mstft_all_fwd_kernel<<<grid, kMstftWarps * 32, smem, st>>>(A);
+      return check_launch("mstft_all_fwd_kernel");
+    }
+  }
+  std::lock_guard<std::mutex> enqueue_lock(g_mstft_enqueue_mu);
   MstftFinArgs fin{};
   fin.n_res = n_res;
   fin.loss = loss;
@@ -180,9 +312,13 @@ int sb200_mstft_backward(const sb200_plan* const* plans, int32_t n_res, const fl
                          float* g_yg, void* workspace, sb200_stream stream) {
   if (int rc = mstft_check(plans, n_res, B, T)) return rc;
   if (!y_g || !saved || !g_yg || !workspace) return fail(SB200_ERR_INVALID, "mstft_backward: null argument");
-  std::lock_guard<std::mutex> enqueue_lock(g_mstft_enqueue_mu);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   char* ws = static_cast<char*>(workspace);
+  {
+    const int rc = mstft_all_bwd(plans, n_res, nullptr, y_g, B, T, phd_phase, g_loss, g_specs_g, saved, nullptr, g_yg, ws, false, st);
+    if (rc <= 0) return rc;
+  }
+  std::lock_guard<std::mutex> enqueue_lock(g_mstft_enqueue_mu);
   GradOlaArgs o{};
   o.n_res = n_res;
   o.B = B;
@@ -224,9 +360,13 @@ int sb200_mstft_loss_and_grad(const sb200_plan* const* plans, int32_t n_res, con
                               int64_t T, float* loss, float* grad_yg, void* workspace, sb200_stream stream) {
   if (int rc = mstft_check(plans, n_res, B, T)) return rc;
   if (!y || !y_g || !loss || !grad_yg || !workspace) return fail(SB200_ERR_INVALID, "mstft_loss_and_grad: null argument");
-  std::lock_guard<std::mutex> enqueue_lock(g_mstft_enqueue_mu);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   char* ws = static_cast<char*>(workspace);
+  {
+    const int rc = mstft_all_bwd(plans, n_res, y, y_g, B, T, 0, nullptr, nullptr, nullptr, loss, grad_yg, ws, true, st);
+    if (rc <= 0) return rc;
+  }
+  std::lock_guard<std::mutex> enqueue_lock(g_mstft_enqueue_mu);
   const int64_t part0 = mstft_ws_gfb_off(plans, n_res, B, T);
   MstftFinArgs fin{};
   fin.n_res = n_res;

@@ -27,6 +27,28 @@ def set_hparams(cfg) -> None:
     hp = cfg if isinstance(cfg, SpectralConfig) else SpectralConfig.from_hparam(cfg)
 
 
+_setup_cache = {}
+
+
+def _setup(cfg: SpectralConfig, dev, B: int, T: int):
+    """(plans, handle array, saved bytes, workspace bytes) of one (configuration, device, batch shape): the lookups and
+    the two size queries are per-shape constants, not per-step work."""
+    key = (cfg, dev.index, B, T)
+    hit = _setup_cache.get(key)
+    if hit is None:
+        lib = _lib.load()
+        plans = [core.get_plan(cfg, *p) for p in cfg.multi_stft_params]     # always the Slaney basis (retunegan/audio.py:158)
+        handles = (C.c_void_p * len(plans))(*[p.handle for p in plans])
+        saved_bytes = lib.sb200_mstft_saved_bytes(handles, len(plans), B, T)
+        ws_bytes = lib.sb200_mstft_workspace_bytes(handles, len(plans), B, T)
+        if saved_bytes < 0 or ws_bytes < 0:
+            _lib.check(-1)
+        if len(_setup_cache) > 64:
+            _setup_cache.clear()
+        hit = _setup_cache[key] = (plans, handles, int(saved_bytes), int(ws_bytes))
+    return hit
+
+
 def _ptr_array(tensors):
     arr = (C.c_void_p * len(tensors))()
     for i, t in enumerate(tensors):
@@ -42,13 +64,8 @@ class _MultiStftFn(torch.autograd.Function):
         yc = y.detach().to(device=dev, dtype=torch.float32).contiguous()
         gc = y_g.detach().to(device=dev, dtype=torch.float32).contiguous()
         B, T = gc.shape
-        plans = [core.get_plan(cfg, *p) for p in cfg.multi_stft_params]
+        plans, handles, saved_bytes, ws_bytes = _setup(cfg, dev, B, T)
         n_res = len(plans)
-        handles = (C.c_void_p * n_res)(*[p.handle for p in plans])
-        saved_bytes = lib.sb200_mstft_saved_bytes(handles, n_res, B, T)
-        ws_bytes = lib.sb200_mstft_workspace_bytes(handles, n_res, B, T)
-        if saved_bytes < 0 or ws_bytes < 0:
-            _lib.check(-1)
         ctx.fused = bool(want_loss and not want_specs and ctx.needs_input_grad[1])
         if ctx.fused:
             # loss-only training step: value and gradient (for a unit upstream gradient) in one pass; backward just scales it
@@ -72,7 +89,7 @@ class _MultiStftFn(torch.autograd.Function):
                                            _ptr_array(specs_r) if want_specs else None,
                                            _ptr_array(specs_g) if want_specs else None,
                                            core.ptr(saved), core.ptr(ws), core.stream_ptr()), "mstft_forward")
-        ctx.cfg, ctx.plans, ctx.handles = cfg, plans, handles
+        ctx.cfg, ctx.plans, ctx.handles, ctx.ws_bytes = cfg, plans, handles, ws_bytes
         ctx.shape = (B, T)
         ctx.want_loss, ctx.want_specs, ctx.phd_phase = want_loss, want_specs, phd_phase
         ctx.in_shape, ctx.in_dtype = y_g.shape, y_g.dtype
@@ -109,8 +126,7 @@ class _MultiStftFn(torch.autograd.Function):
             if any(g is not None for g in gs):
                 g_specs = [None if g is None else g.to(torch.float32).contiguous() for g in gs]
         g_yg = torch.empty((B, T), device=dev, dtype=torch.float32)
-        ws_bytes = lib.sb200_mstft_workspace_bytes(ctx.handles, n_res, B, T)
-        ws = core._workspace(int(ws_bytes), dev, "mstft")
+        ws = core._workspace(ctx.ws_bytes, dev, "mstft")
         _lib.check(lib.sb200_mstft_backward(ctx.handles, n_res, core.ptr(gc), B, T, ctx.phd_phase, core.ptr(g_loss),
                                             _ptr_array(g_specs) if g_specs is not None else None, core.ptr(saved),
                                             core.ptr(g_yg), core.ptr(ws), core.stream_ptr()), "mstft_backward")
