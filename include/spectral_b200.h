@@ -202,6 +202,20 @@ int sb200_mstft_backward(const sb200_plan* const* plans, int32_t n_res, const fl
                          int32_t phd_phase, const float* g_loss, const float* const* g_specs_g, const void* saved,
                          float* g_yg, void* workspace, sb200_stream stream);
 
+/* ---- get_stft_torch (retunegan/audio.py:150-170), differentiable ---------------------------------------
+ * Forward, one launch: D = torch.stft(y, n_fft, hop, win, hann, center, reflect); S = |D + 1e-9|, P = angle(D) [B, T', F] and
+ * M = mel_basis S [B, T', n_mel], frame-major (the [B, F, T'] / [B, n_mel, T'] tensors of the reference are their transposed
+ * views); any output may be NULL.  y [B, T].
+ * Backward (what torch.autograd derives from audio.py:161-168): g_y [B, T] from the upstream gradients g_S, g_P [B, T', F] and
+ * g_M [B, T', n_mel] (any may be NULL = zero): gS = g_S + mel_basis^T g_M; gD = gS (D + 1e-9)/S + g_P i D/|D|^2 (0 where
+ * the magnitude is 0, as torch.abs / torch.angle do); adjoint of the one-sided windowed rFFT; overlap-add with the reflect
+ * padding folded back.  The analysis of y is recomputed (nothing is saved by forward).  workspace: sb200_stft_smp_workspace_bytes(). */
+int64_t sb200_stft_smp_workspace_bytes(const sb200_plan* plan, int32_t B, int64_t T);
+int sb200_stft_smp_forward(const sb200_plan* plan, const float* y, int32_t B, int64_t T, float* S, float* M, float* P,
+                           sb200_stream stream);
+int sb200_stft_smp_backward(const sb200_plan* plan, const float* y, int32_t B, int64_t T, const float* g_S, const float* g_M,
+                            const float* g_P, float* g_y, void* workspace, sb200_stream stream);
+
 /* Loss value and d loss / d y_g for a unit upstream gradient in ONE pass (retunegan/train.py:165 multi_stft_loss(...,
  * ret_loss=True) followed by :192 backward, loss-only): one launch per resolution, no second analysis in backward.
  * loss: device scalar; grad_yg: [B, T]; workspace: sb200_mstft_workspace_bytes(). */

@@ -600,3 +600,57 @@ def test_concurrent_threads_and_streams_equal_serial(sb):
     for i in range(4):
         for a, b in zip(serial[i], results[i]):
             np.testing.assert_array_equal(a, b)
+
+
+# ------------------------------------------------------------------ get_stft_torch under autograd -----------
+
+def _ref_get_stft_torch(y, n_fft, win, hop, dtype):
+    """retunegan/audio.py:150-170 with real torch on the CPU (torch.stft -> abs / matmul / angle), in `dtype`."""
+    y = y.to(dtype)
+    w = torch.hann_window(win, dtype=dtype)
+    mb = torch.from_numpy(O.mel_basis(n_fft)).to(dtype)
+    D = torch.stft(y, n_fft, hop_length=hop, win_length=win, window=w, center=True, pad_mode="reflect", normalized=False,
+                   onesided=True, return_complex=True)
+    S = torch.abs(D + 1e-9)
+    return S, torch.matmul(mb, S), torch.angle(D)
+
+
+@pytest.mark.parametrize("ri", [0, 1, 2])
+def test_get_stft_torch_is_differentiable_like_the_reference(sb, ri):
+    """S, M, P and d/dy of a random linear functional of all three against torch's own autograd on the reference graph (CPU,
+    float64).  The phase gradient g_P D / |D|^2 is ill conditioned at weak bins, so its upstream weights are scaled by |D|^2;
+    bar: 1e-4 rel-L2 against float64 and no worse than 1.2x what the reference's float32 graph achieves."""
+    n_fft, win, hop = O.HP.multi_stft_params[ri]
+    B, T = 3, 6000
+    y = torch.from_numpy(np.stack([O.synth_speechlike(T, 40 + b) + 0.01 * O.synth_noise(T, 50 + b) for b in range(B)]))
+    rs = np.random.RandomState(ri)
+    S64, M64, P64 = _ref_get_stft_torch(y, n_fft, win, hop, torch.float64)
+    uS = torch.from_numpy(rs.randn(*S64.shape))
+    uM = torch.from_numpy(rs.randn(*M64.shape))
+    uP = torch.from_numpy(rs.randn(*P64.shape)) * S64.detach() ** 2 / float((S64 ** 2).mean())
+
+    def grad_of(fn_outputs, leaf, dt):
+        S, M, P = fn_outputs
+        tot = (S * uS.to(S.device, dt)).sum() + (M * uM.to(S.device, dt)).sum() + (P * uP.to(S.device, dt)).sum()
+        return torch.autograd.grad(tot, leaf, retain_graph=True)[0]
+    y64 = y.double().requires_grad_(True)
+    g64 = grad_of(_ref_get_stft_torch(y64, n_fft, win, hop, torch.float64), y64, torch.float64).numpy()
+    y32 = y.float().requires_grad_(True)
+    g32 = grad_of(_ref_get_stft_torch(y32, n_fft, win, hop, torch.float32), y32, torch.float32).numpy()
+    yc = y.float().cuda().requires_grad_(True)
+    S, M, P = sb.retunegan_audio.get_stft_torch(yc, n_fft, win, hop)
+    assert S.requires_grad and M.requires_grad and P.requires_grad and tuple(S.shape) == tuple(S64.shape)
+    _close(S.detach().cpu().numpy(), S64.numpy(), 1e-5)
+    _close(M.detach().cpu().numpy(), M64.numpy(), 1e-5)
+    d = np.abs(np.exp(1j * P.detach().cpu().numpy().astype(np.float64)) - np.exp(1j * P64.numpy())) * S64.numpy()
+    assert d.max() < 1e-4 * S64.numpy().max()
+    g = grad_of((S, M, P), yc, torch.float32).cpu().numpy()
+    err, ref32 = rel_fro(g, g64), rel_fro(g32, g64)
+    assert err <= max(1e-4, 1.2 * ref32), (err, ref32)
+    # each output on its own (null upstream gradients for the others), and a 1-D signal like torch.stft accepts
+    (gM_only,) = torch.autograd.grad((M * uM.float().cuda()).sum(), yc, retain_graph=True)
+    y64b = y.double().requires_grad_(True)
+    (gM_ref,) = torch.autograd.grad((_ref_get_stft_torch(y64b, n_fft, win, hop, torch.float64)[1] * uM).sum(), y64b)
+    assert rel_fro(gM_only.cpu().numpy(), gM_ref.numpy()) <= 1e-4
+    S1, M1, P1 = sb.retunegan_audio.get_stft_torch(yc[0].detach(), n_fft, win, hop)
+    assert S1.dim() == 2 and torch.equal(S1, S[0].detach())

@@ -54,6 +54,43 @@ __global__ void handoff(float* out, int rounds) {
   if (threadIdx.x >= 32) out[lane] = acc;
 }
 
+// The same hand-off for PAIRS producer / consumer warp pairs in one CTA, laid out like feat3.cuh: producers are warps 0 .. PAIRS-1,
+// consumers warps PAIRS .. 2 PAIRS-1, barriers full[PAIRS] then empty[PAIRS] back to back (8 bytes apart), one lane per barrier
+// initialises it.
+// delay: cycles the producer spends on an item before it arrives (feat3's analysis warp needs ~15 k cycles per item, so its
+// consumer sits in try_wait across many suspend time-outs; with delay = 0 the waits are over at once).
+// hi: byte offset of the buffers and barriers inside the dynamic shared memory (feat3 keeps them at 132 .. 224 KB).
+template <int PAIRS>
+__global__ void handoff_pairs(float* out, int rounds, long long delay, int hi) {
+  extern __shared__ __align__(16) unsigned char dyn_base[];
+  unsigned char* dyn = dyn_base + hi;
+  float* bufs = reinterpret_cast<float*>(dyn);
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(dyn + PAIRS * 32 * 4);
+  if (threadIdx.x < 2 * PAIRS) {
+    mbar_init(smem_u32(bar + threadIdx.x), 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, w = warp % PAIRS;
+  const unsigned full = smem_u32(bar + w), empty = smem_u32(bar + PAIRS + w);
+  float* buf = bufs + 32 * w;
+  float acc = 0.f;
+  for (int r = 0; r < rounds; ++r) {
+    if (warp < PAIRS) {
+      const long long t0 = clock64();
+      while (clock64() - t0 < delay) {}
+      mbar_wait(empty, (r & 1) ^ 1);
+      buf[lane] = static_cast<float>(r * 32 + lane);
+      mbar_arrive(full);
+    } else {
+      mbar_wait(full, r & 1);
+      acc += buf[31 - lane];
+      mbar_arrive(empty);
+    }
+  }
+  if (warp >= PAIRS) out[32 * w + lane] = acc;
+}
+
 int main() {
   float* out;
   cudaMalloc(&out, 32 * sizeof(float));
@@ -65,5 +102,18 @@ int main() {
   cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
   printf("dynamic smem: %s, static smem: %s, out[0] = %g (expect %g)\n", cudaGetErrorString(e1), cudaGetErrorString(e2), h[0],
          8 * 31.f + 32.f * 28);
+  float* out8;
+  cudaMalloc(&out8, 8 * 32 * sizeof(float));
+  cudaFuncSetAttribute(handoff_pairs<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  const int his[] = {0, 40 * 1024, 100 * 1024, 220 * 1024};
+  for (int hi : his)
+    for (long long delay : {0LL, 20000LL}) {
+      handoff_pairs<8><<<1, 512, hi + 8 * 32 * 4 + 16 * 8>>>(out8, 8, delay, hi);
+      cudaError_t e3 = cudaDeviceSynchronize();
+      float h8[256];
+      cudaMemcpy(h8, out8, sizeof(h8), cudaMemcpyDeviceToHost);
+      printf("8 warp pairs, 16 barriers at +%d KB, producer delay %lld cycles: %s, out[0] = %g, out[255] = %g (expect %g, %g)\n",
+             hi / 1024, delay, cudaGetErrorString(e3), h8[0], h8[255], 8 * 31.f + 32.f * 28, 8 * 0.f + 32.f * 28);
+    }
   return 0;
 }

@@ -55,6 +55,9 @@ SIGNATURES = {
     "sb200_griffinlim_workspace_bytes": (_I64, [_P, _I64, _I32, _I32]),
     "sb200_istft": (C.c_int, [_P, _P, C.POINTER(Batch), _I64, _P, _P, _P]),
     "sb200_griffinlim": (C.c_int, [_P, _P, _P, C.POINTER(Batch), _I64, _I32, _F, _I32, _F, _P, _P, _P]),
+    "sb200_stft_smp_workspace_bytes": (_I64, [_P, _I32, _I64]),
+    "sb200_stft_smp_forward": (C.c_int, [_P, _P, _I32, _I64, _P, _P, _P, _P]),
+    "sb200_stft_smp_backward": (C.c_int, [_P, _P, _I32, _I64, _P, _P, _P, _P, _P, _P]),
     "sb200_mstft_saved_bytes": (_I64, [C.POINTER(_P), _I32, _I32, _I64]),
     "sb200_mstft_workspace_bytes": (_I64, [C.POINTER(_P), _I32, _I32, _I64]),
     "sb200_mstft_forward": (C.c_int, [C.POINTER(_P), _I32, _P, _P, _I32, _I64, _I32, _P, C.POINTER(_P),

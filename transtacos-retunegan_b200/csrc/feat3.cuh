@@ -445,7 +445,12 @@ __global__ void __launch_bounds__(kFeat3Threads, 1) stft_feature3_kernel(const P
   extern __shared__ __align__(128) unsigned char smem_raw[];   // bulk-tensor copies land in 128-byte aligned shared memory
   Smem3<N> sm;
   sm.carve(smem_raw, p);
+#ifndef SB200_BISECT_NO_FILL   // (sanitizer bisection variants: results are garbage, only the tools' reports matter)
   sm.fill(p, a.mel != nullptr);
+#endif
+#ifdef SB200_BISECT_SYNC_BEFORE_INIT
+  __syncthreads();
+#endif
   if (threadIdx.x < 3 * kFeat3Pairs) {   // full / empty: 32 lane arrivals; staged: the one expect_tx arrival of the issuing lane
     mbar_init(smem_u32(sm.bar + threadIdx.x), threadIdx.x < 2 * kFeat3Pairs ? 32 : 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");

@@ -33,7 +33,8 @@ struct MstftFwdArgs {
   int want_loss;
 };
 
-template <int N>
+// RAW (get_stft_torch, retunegan/audio.py:166-168): ch0 receives S = |D + 1e-9| itself and ch1 angle(D), instead of ln S and angle / PI
+template <int N, bool RAW = false>
 __device__ __forceinline__ void mstft_analyse(const PlanDev& p, const SmemTables<N>& sm, float2* buf, float2 (&v)[32],
                                               const float* x, long long L, int t0, int T, int lane, float* ch0,
                                               float* ch0_alias, float* ch1, long long row0 /* (b*2*Tf + t0) * F */,
@@ -49,9 +50,9 @@ __device__ __forceinline__ void mstft_analyse(const PlanDev& p, const SmemTables
       float2* zq = buf + q * C::kZS;
       const long long row = row0 + static_cast<long long>(q) * C::kF;
       auto emit = [&](float2 X, int k, float S) {
-        if (ch0) ch0[row + k] = logf(S);
+        if (ch0) ch0[row + k] = RAW ? S : logf(S);
         if (ch0_alias) ch0_alias[row + k] = logf(S);
-        if (ch1) ch1[row + ch_stride + k] = atan2f(X.y, X.x) / kRefPI;
+        if (ch1) ch1[row + ch_stride + k] = RAW ? atan2f(X.y, X.x) : atan2f(X.y, X.x) / kRefPI;
       };
 #pragma unroll 2
       for (int i = 0; i < C::kPairIters; ++i) {
@@ -137,6 +138,43 @@ __global__ void __launch_bounds__(kMstftWarps * 32, 2) mstft_fwd_kernel(const Pl
   mstft_fwd_body<N>(p, a, smem_raw, blockIdx.x, gridDim.x);
 }
 
+// get_stft_torch (retunegan/audio.py:150-170) as one launch: S = |D + 1e-9| [B, Tf, F], P = angle(D) [B, Tf, F] and
+// M = mel_basis S [B, Tf, n_mel], frame-major; any output may be null.
+struct StftSmpArgs {
+  const float* y;
+  BatchDev bd;     // uniform [B, T]
+  int Tf;
+  float* S;
+  float* P;
+  float* M;
+};
+template <int N>
+__global__ void __launch_bounds__(kMstftWarps * 32, 2) stft_smp_kernel(const PlanDev p, const StftSmpArgs a) {
+  using C = FftCfg<N>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmemTables<N> sm;
+  sm.carve(smem_raw, p);
+  sm.fill(p, p.window, a.M != nullptr);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float2* buf = sm.bufs + warp * C::kBufF2;
+  for (long long sub = static_cast<long long>(blockIdx.x) * kMstftWarps + warp; sub < 2 * a.bd.total_items;
+       sub += static_cast<long long>(gridDim.x) * kMstftWarps) {
+    Item it = decode_item(a.bd, sub >> 1, 2 * C::kQ);
+    it.t0 += static_cast<int>(sub & 1) * C::kQ;
+    if (it.t0 >= it.T) continue;
+    float2 v[32];
+    const long long row0 = (it.frame_base + it.t0) * C::kF;
+    mstft_analyse<N, true>(p, sm, buf, v, a.y + it.sig_base, it.L, it.t0, it.T, lane, a.S, nullptr, a.P, row0, 0);
+    if (a.M) {
+      mel_project_smem<N>(p, sm.melw, sm.mel_lo, buf, lane, [&](int q, int, int m, float val) {
+        if (m < p.n_mel && it.t0 + q < it.T) a.M[(it.frame_base + it.t0 + q) * p.n_mel + m] = val;
+      });
+    }
+    __syncwarp();
+  }
+}
+
 struct MstftFinArgs {
   int n_res;
   const float* partials[kMaxRes];
@@ -178,6 +216,11 @@ struct MstftBwdArgs {
   float* gfb;              // [B*Tf, win] gradient frames
   const float* y;          // FUSED: real audio (its mel rows are computed here instead of read from mel_r)
   float* partials;         // FUSED: [gridDim.x * kMstftWarps] loss partial sums
+  // backward of get_stft_torch (raw != 0): upstream gradients of S, P [B, Tf, F] and M [B, Tf, n_mel], any may be null
+  int raw;
+  const float* g_s_raw;
+  const float* g_p_raw;
+  const float* g_m_raw;
 };
 
 // Shared-memory bytes of mstft_bwd_kernel: the tables and per-warp FFT buffers of the forward kernel plus, per warp, the
@@ -291,7 +334,9 @@ __device__ __forceinline__ void mstft_bwd_body(const PlanDev& p, const MstftBwdA
             mr[r2][q] = mg;
           } else {
             float g = 0.f;
-            if (gl != 0.f && m < p.n_mel && it.t0 + q < it.T) {
+            if (a.raw) {
+              if (a.g_m_raw && m < p.n_mel && it.t0 + q < it.T) g = __ldg(a.g_m_raw + (it.frame_base + it.t0 + q) * p.n_mel + m);
+            } else if (gl != 0.f && m < p.n_mel && it.t0 + q < it.T) {
               float r;
               if constexpr (FUSED) {
                 r = mr[r2][q];
@@ -328,7 +373,11 @@ __device__ __forceinline__ void mstft_bwd_body(const PlanDev& p, const MstftBwdA
         const float S = sqrtf(fmaf(re, re, X.y * X.y));
         float gS = fmaf(c0, gmbuf[q * 128 + r0], c1 * gmbuf[q * 128 + r0 + 1]);
         float gP = 0.f;
-        if (a.g_spec) {
+        if (a.raw) {
+          const long long idx = (it.frame_base + t) * C::kF + k;
+          if (a.g_s_raw) gS += __ldg(a.g_s_raw + idx);
+          if (a.g_p_raw) gP = __ldg(a.g_p_raw + idx);
+        } else if (a.g_spec) {
           const long long idx = (static_cast<long long>(it.b) * 2 * a.Tf + t) * C::kF + k;
           if (!a.phd_phase) gS += __ldg(a.g_spec + idx) / S;
           gP = __ldg(a.g_spec + idx + chs) / kRefPI;

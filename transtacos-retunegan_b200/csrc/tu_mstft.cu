@@ -407,3 +407,72 @@ int sb200_mstft_loss_and_grad(const sb200_plan* const* plans, int32_t n_res, con
   grad_ola_kernel<<<grid, 256, 0, st>>>(o);
   return check_launch("grad_ola_kernel");
 }
+
+// ---- get_stft_torch, differentiable (retunegan/audio.py:150-170) ------------------------------------------------------------
+
+static int stft_smp_check(const sb200_plan* plan, int32_t B, int64_t T) {
+  if (!plan) return fail(SB200_ERR_INVALID, "stft_smp: null plan");
+  if (B < 1) return fail(SB200_ERR_INVALID, "stft_smp: B must be >= 1");
+  if (T <= plan->cfg.n_fft / 2) return fail(SB200_ERR_INVALID, "stft_smp: reflect padding needs T > n_fft/2 (torch.stft raises)");
+  return SB200_OK;
+}
+
+int64_t sb200_stft_smp_workspace_bytes(const sb200_plan* plan, int32_t B, int64_t T) {
+  if (stft_smp_check(plan, B, T)) return -1;
+  const int64_t Tf = 1 + T / plan->cfg.hop_length;
+  return B * Tf * plan->cfg.win_length * 4 + 256;
+}
+
+template <int N>
+static void launch_stft_smp(const sb200_plan* plan, const StftSmpArgs& a, int grid, cudaStream_t st) {
+  const size_t smem = feat_smem_bytes<N>(plan->dev);
+  cudaFuncSetAttribute(stft_smp_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  stft_smp_kernel<N><<<grid, kMstftWarps * 32, smem, st>>>(plan->dev, a);
+}
+
+int sb200_stft_smp_forward(const sb200_plan* plan, const float* y, int32_t B, int64_t T, float* S, float* M, float* P,
+                           sb200_stream stream) {
+  if (int rc = stft_smp_check(plan, B, T)) return rc;
+  if (!y || (!S && !M && !P)) return fail(SB200_ERR_INVALID, "stft_smp_forward: null argument");
+  StftSmpArgs a{};
+  a.y = y;
+  a.bd = mstft_batch(plan, B, T);
+  a.Tf = static_cast<int>(a.bd.frames_per_row);
+  a.S = S;
+  a.P = P;
+  a.M = M;
+  const int grid = mstft_grid(2 * a.bd.total_items);
+  SB200_DISPATCH_N(plan, launch_stft_smp<kN>(plan, a, grid, static_cast<cudaStream_t>(stream)));
+  return check_launch("stft_smp_kernel");
+}
+
+int sb200_stft_smp_backward(const sb200_plan* plan, const float* y, int32_t B, int64_t T, const float* g_S, const float* g_M,
+                            const float* g_P, float* g_y, void* workspace, sb200_stream stream) {
+  if (int rc = stft_smp_check(plan, B, T)) return rc;
+  if (!y || !g_y || !workspace) return fail(SB200_ERR_INVALID, "stft_smp_backward: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MstftBwdArgs a{};
+  a.yg = y;
+  a.bd = mstft_batch(plan, B, T);
+  a.Tf = static_cast<int>(a.bd.frames_per_row);
+  a.raw = 1;
+  a.g_s_raw = g_S;
+  a.g_p_raw = g_P;
+  a.g_m_raw = g_M;
+  a.gfb = static_cast<float*>(workspace);
+  const int grid = mstft_grid(2 * a.bd.total_items);
+  SB200_DISPATCH_N(plan, launch_mstft_bwd<kN>(plan, a, grid, st));
+  if (int rc = check_launch("mstft_bwd_kernel<raw>")) return rc;
+  GradOlaArgs o{};
+  o.n_res = 1;
+  o.B = B;
+  o.T = T;
+  o.g = g_y;
+  o.gfb[0] = a.gfb;
+  o.n_fft[0] = plan->cfg.n_fft;
+  o.hop[0] = plan->cfg.hop_length;
+  o.Tf[0] = a.Tf;
+  dim3 og(grid_for(T, 256, 2), B);
+  grad_ola_kernel<<<og, 256, 0, st>>>(o);
+  return check_launch("grad_ola_kernel");
+}

@@ -191,25 +191,58 @@ def inv_mag_batch(mag_fm: torch.Tensor, frames, wavlens=None, init_phase="seeded
     return y, fb.out_off
 
 
+class _StftTorchFn(torch.autograd.Function):
+    """S, M, P of get_stft_torch in ONE launch (``stft_smp_kernel``); backward = one launch of the mstft backward kernel on the
+    upstream gradients of S, M and P plus the overlap-add (``sb200_stft_smp_backward``): no ATen op on either path."""
+
+    @staticmethod
+    def forward(ctx, y, plan):
+        lib = core._lib.load()
+        dev = core.require_cuda()
+        yc = y.detach().to(device=dev, dtype=torch.float32).contiguous()
+        B, T = yc.shape
+        Tf = 1 + T // plan.hop_length
+        S = torch.empty((B, Tf, plan.F), device=dev, dtype=torch.float32)
+        P = torch.empty((B, Tf, plan.F), device=dev, dtype=torch.float32)
+        M = torch.empty((B, Tf, plan.n_mel), device=dev, dtype=torch.float32)
+        core.check(lib.sb200_stft_smp_forward(plan.handle, core.ptr(yc), B, T, core.ptr(S), core.ptr(M), core.ptr(P),
+                                              core.stream_ptr()), "stft_smp_forward")
+        ctx.plan, ctx.in_dtype, ctx.in_shape = plan, y.dtype, y.shape
+        ctx.save_for_backward(yc)
+        return S.transpose(1, 2), M.transpose(1, 2), P.transpose(1, 2)
+
+    @staticmethod
+    def backward(ctx, gS, gM, gP):
+        lib = core._lib.load()
+        (yc,) = ctx.saved_tensors
+        plan = ctx.plan
+        B, T = yc.shape
+
+        def fm(g):   # [B, F, T'] upstream (normally a view of frame-major memory, then this is free) -> contiguous [B, T', F]
+            return None if g is None else g.to(device=yc.device, dtype=torch.float32).transpose(1, 2).contiguous()
+        gS, gM, gP = fm(gS), fm(gM), fm(gP)
+        g_y = torch.empty((B, T), device=yc.device, dtype=torch.float32)
+        ws = core._workspace(int(lib.sb200_stft_smp_workspace_bytes(plan.handle, B, T)), yc.device, "stft_smp")
+        core.check(lib.sb200_stft_smp_backward(plan.handle, core.ptr(yc), B, T, core.ptr(gS), core.ptr(gM), core.ptr(gP),
+                                               core.ptr(g_y), core.ptr(ws), core.stream_ptr()), "stft_smp_backward")
+        return g_y.to(ctx.in_dtype).reshape(ctx.in_shape), None
+
+
 def get_stft_torch(y, n_fft, win_length, hop_length):
     """S = |D + 1e-9|, M = mel_basis @ S, P = angle(D) for y [B, T] (retunegan/audio.py:150-170).
 
-    Outputs are [B, F, T'] / [B, n_mel, T'] views of frame-major buffers.  This standalone entry is not
-    differentiable; gradients flow through ``multi_stft_loss`` (the only differentiable use in the reference).
+    Outputs are [B, F, T'] / [B, n_mel, T'] views of frame-major buffers, computed by one fused launch, and they are
+    differentiable with respect to ``y`` like the reference's (torch.stft -> abs / matmul / angle under autograd).
+    The mel basis is the Slaney one whatever ``hp.mel_scale`` says (audio.py:158).
     """
     if not isinstance(y, torch.Tensor):
         raise TypeError("get_stft_torch expects a torch.Tensor [B, T]")
-    if y.dim() == 1:
+    squeeze = y.dim() == 1
+    if squeeze:
         y = y.unsqueeze(0)
     if y.shape[-1] <= n_fft // 2:
         raise RuntimeError(f"Argument #4: Padding size should be less than the corresponding input dimension, "
                            f"but got: padding ({n_fft // 2}, {n_fft // 2}) at dimension 2 of input")   # torch.stft
     plan = core.get_plan(hp, n_fft, win_length, hop_length)
-    batch = core.SignalBatch(plan, y)
-    _, _, D = core.stft_features(plan, batch, 0.0, None, None, False, False, True)
-    B, Tf = batch.B, int(batch.frames[0])
-    S = torch.abs(D + 1e-9)
-    M = core.mel_project(plan, S.contiguous())
-    P = torch.angle(D)
-    return (S.view(B, Tf, plan.F).transpose(1, 2), M.view(B, Tf, plan.n_mel).transpose(1, 2),
-            P.view(B, Tf, plan.F).transpose(1, 2))
+    S, M, P = _StftTorchFn.apply(y, plan)
+    return (S[0], M[0], P[0]) if squeeze else (S, M, P)
