@@ -139,6 +139,15 @@ int sb200_spec_to_amplitude(const float* in, int64_t n, int32_t mode, float p0, 
 int sb200_frame_stats(const float* x, const sb200_batch* batch, int32_t frame_length, int32_t hop_length, float* rms,
                       float* zcr, sb200_stream stream);
 
+/* librosa.effects.trim bounds (trim_silence, transtacos/audio.py:59-61) from the RMS track sb200_frame_stats wrote with
+ *   frame_length 512 / hop 128: frames whose power is within top_db of the row's loudest frame are non-silent
+ *   (power_to_db(ref = max, amin = 1e-10, top_db = None) > -top_db).  frame_off: device [B+1] prefix sums of the rows' frame
+ *   counts, or NULL with frames_per_row for a uniform batch.  bounds (device, int64 [B, 2]): first non-silent frame and last
+ *   non-silent frame + 1 of every row, (0, 0) for an all-silent row; the caller turns frames into samples (x hop, clipped to
+ *   the length). */
+int sb200_trim_bounds(const float* rms, const int64_t* frame_off, int64_t frames_per_row, int32_t B, float top_db,
+                      int64_t* bounds, sb200_stream stream);
+
 /* f0[t]: librosa.yin(y, fmin, fmax, sr, frame_length, hop_length=hop_length) (win_length = frame_length / 2, trough
  *   threshold 0.1, center=True, reflect padding) -- get_f0 at transtacos/audio.py:107-109.  Same batch convention as
  *   sb200_frame_stats.  frame_length <= 4096. */

@@ -47,6 +47,7 @@ SIGNATURES = {
     "sb200_mel_to_linear": (C.c_int, [_P, _P, _I64, _P, _P]),
     "sb200_spec_to_amplitude": (C.c_int, [_P, _I64, _I32, _F, _F, _F, _F, _P, _P]),
     "sb200_frame_stats": (C.c_int, [_P, C.POINTER(Batch), _I32, _I32, _P, _P, _P]),
+    "sb200_trim_bounds": (C.c_int, [_P, _P, _I64, _I32, _F, _P, _P]),
     "sb200_yin": (C.c_int, [_P, C.POINTER(Batch), _I32, _F, _F, _I32, _I32, _F, _P, _P]),
     "sb200_pool_loss_workspace_bytes": (_I64, []),
     "sb200_pool_loss": (C.c_int, [_P, _P, _I32, _I64, _I32, _I32, _P, _P, _P, _P]),

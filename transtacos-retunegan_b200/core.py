@@ -290,19 +290,18 @@ def yin(ys, sample_rate: int, fmin: float, fmax: float, frame_length: int, hop_l
 
 
 def trim_bounds(rms: torch.Tensor, frames, lens, hop_length: int, top_db: float):
-    """librosa.effects.trim on a precomputed RMS track (ref = max, amin = 1e-10): [(start, end)] sample bounds per row."""
-    out, o = [], 0
-    r = rms.double().cpu().numpy()
-    for T, L in zip(frames, lens):
-        mse = r[o:o + int(T)] ** 2
-        o += int(T)
-        db = 10.0 * np.log10(np.maximum(1e-10, mse)) - 10.0 * np.log10(np.maximum(1e-10, mse.max()))
-        nz = np.flatnonzero(db > -top_db)
-        if nz.size:
-            out.append((int(nz[0]) * hop_length, min(int(L), (int(nz[-1]) + 1) * hop_length)))
-        else:
-            out.append((0, 0))
-    return out
+    """librosa.effects.trim on a precomputed RMS track (ref = max, amin = 1e-10): [(start, end)] sample bounds per row.
+    The threshold and the first / last scan run on the device (``trim_bounds_kernel``, one warp per row); only the two
+    frame indices per row come back to the host (slicing host arrays needs host integers)."""
+    frames = np.asarray(frames, np.int64)
+    B = len(frames)
+    off = np.zeros(B + 1, np.int64)
+    off[1:] = np.cumsum(frames)
+    off_d = torch.from_numpy(off).to(rms.device)
+    out_d = torch.empty((B, 2), device=rms.device, dtype=torch.int64)
+    check(_lib.load().sb200_trim_bounds(ptr(rms), ptr(off_d), 0, B, float(top_db), ptr(out_d), stream_ptr()), "trim_bounds")
+    fl = out_d.cpu().numpy()
+    return [(int(f) * hop_length, min(int(L), int(l) * hop_length)) for (f, l), L in zip(fl, lens)]
 
 
 class FramesBatch:

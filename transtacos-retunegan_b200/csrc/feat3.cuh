@@ -350,6 +350,11 @@ __device__ __forceinline__ void feat3_epilogue(const PlanDev& p, const FeatArgs&
     pair_bar_sync(w);
     mbar_wait(full, round & 1);
     pair_bar_sync(w);
+#ifdef SB200_ABLATE_EPILOGUE   // ablation builds (tools/variants.py): what the analysis role costs on its own
+    if (a.mag == reinterpret_cast<float*>(1)) a.mag[0] = plo(pbuf[lane]);
+    mbar_arrive(empty);
+    continue;
+#endif
 #pragma unroll
     for (int q = 0; q < C::kP; ++q) {
       const int fA = it.t0 + 2 * q;
@@ -391,7 +396,11 @@ __device__ __forceinline__ void feat3_epilogue(const PlanDev& p, const FeatArgs&
       if (fA + 1 < it.T) row[C::kF] = phi(o);
     }
     __syncwarp();
+#ifdef SB200_ABLATE_MEL
+    if (false) {
+#else
     if (want_mel) {
+#endif
 #pragma unroll
       for (int rd = 0; rd < kMaxMelRounds; ++rd) {
         if (rd < p.mel_rounds) {

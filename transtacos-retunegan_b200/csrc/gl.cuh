@@ -66,5 +66,4 @@ __device__ __forceinline__ float synth_scale_edge(const PlanDev& p, int t, int n
   return wss > 1.1754943508222875e-38f ? w / wss : w;
 }
 
-// Inverse FFT of the natural-order Z' in buf, window / normalise, store Q frames to fb_out.
 }  // namespace sb200

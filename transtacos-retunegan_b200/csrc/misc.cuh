@@ -509,4 +509,52 @@ __global__ void pool_loss_finalize_kernel(const float* __restrict__ partials, in
   }
 }
 
+// ---- librosa.effects.trim bounds from a precomputed RMS track (transtacos/audio.py:59-61 trim_silence) ---------------------
+// Row b owns frames [frame_off[b], frame_off[b+1]) of rms (uniform: frames_per_row each).  db = 10 log10(max(1e-10, rms^2)) -
+// 10 log10(max(1e-10, max_t rms^2)) (power_to_db with ref = max, amin = 1e-10, top_db = None); non-silent frames are those with
+// db > -top_db; out[2b] = first non-silent frame, out[2b+1] = last non-silent frame + 1, (0, 0) if there is none.  The
+// comparison is carried out in double like numpy does (the track itself is float32).  One warp per row.
+struct TrimArgs {
+  const float* rms;
+  const long long* frame_off;   // [B+1] or null (uniform)
+  long long frames_per_row;
+  int B;
+  double top_db;
+  long long* out;               // [B, 2]
+};
+__global__ void __launch_bounds__(128) trim_bounds_kernel(const TrimArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int b = warp; b < a.B; b += nwarps) {
+    const long long f0 = a.frame_off ? __ldg(a.frame_off + b) : b * a.frames_per_row;
+    const long long T = a.frame_off ? __ldg(a.frame_off + b + 1) - f0 : a.frames_per_row;
+    double mx = 0.0;
+    for (long long t = lane; t < T; t += 32) {
+      const double r = static_cast<double>(__ldg(a.rms + f0 + t));
+      mx = fmax(mx, r * r);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    const double ref_db = 10.0 * log10(fmax(1e-10, mx));
+    long long first = T, last = -1;
+    for (long long t = lane; t < T; t += 32) {
+      const double r = static_cast<double>(__ldg(a.rms + f0 + t));
+      const double db = 10.0 * log10(fmax(1e-10, r * r)) - ref_db;
+      if (db > -a.top_db) {
+        first = min(first, t);
+        last = max(last, t);
+      }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      first = min(first, __shfl_xor_sync(0xffffffffu, first, d));
+      last = max(last, __shfl_xor_sync(0xffffffffu, last, d));
+    }
+    if (lane == 0) {
+      a.out[2 * b] = last >= 0 ? first : 0;
+      a.out[2 * b + 1] = last >= 0 ? last + 1 : 0;
+    }
+  }
+}
+
 }  // namespace sb200

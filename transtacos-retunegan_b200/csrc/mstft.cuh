@@ -476,11 +476,48 @@ __device__ __forceinline__ float grad_ola_sample(const GradOlaArgs& a, int b, lo
   }
   return acc;
 }
-__global__ void grad_ola_kernel(const GradOlaArgs a) {
+// Four consecutive samples j0 .. j0+3 (j0 % 4 == 0) away from the reflected borders of every resolution: with hop % 4 == 0 they are
+// covered by the same frames at offsets that are multiples of 4, so each frame contributes one 16-byte load (same summation
+// order per sample as grad_ola_sample: resolutions in order, frames from the last covering one backwards).
+__device__ __forceinline__ float4 grad_ola_quad(const GradOlaArgs& a, int b, long long j0) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = 0; r < a.n_res; ++r) {
+    const int N = a.n_fft[r], win = N / 2, hop = a.hop[r], Tf = a.Tf[r];
+    const float* fb = a.gfb[r] + static_cast<long long>(b) * Tf * win;
+    const long long pp = N / 4 + j0;                         // (h + j0) - N/4
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int tp = static_cast<int>(min(static_cast<long long>(Tf - 1), pp / hop)); tp >= 0; --tp) {
+      const long long off = pp - static_cast<long long>(tp) * hop;
+      if (off >= win) break;
+      const float4 v = *reinterpret_cast<const float4*>(fb + static_cast<long long>(tp) * win + off);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    acc.x += s.x; acc.y += s.y; acc.z += s.z; acc.w += s.w;
+  }
+  return acc;
+}
+
+// One thread per 4 samples; block (0, 0) first reduces the loss partial sums when fin.loss is set (the loss-only step: saves the
+// separate one-block launch, which sat between the analysis kernels and this one).
+__global__ void __launch_bounds__(256) grad_ola_kernel(const GradOlaArgs a, const MstftFinArgs fin) {
+  if (fin.loss != nullptr && blockIdx.x == 0 && blockIdx.y == 0) mstft_finalize_body(fin);
   const int b = blockIdx.y;
-  for (long long j = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; j < a.T;
-       j += static_cast<long long>(gridDim.x) * blockDim.x)
-    a.g[static_cast<long long>(b) * a.T + j] = grad_ola_sample<false>(a, b, j);
+  int hmax = 0;
+  bool vec = (a.T >= 8);
+  for (int r = 0; r < a.n_res; ++r) {
+    hmax = max(hmax, a.n_fft[r] / 2);
+    vec = vec && (a.hop[r] % 4 == 0) && (a.n_fft[r] % 16 == 0);
+  }
+  float* g = a.g + static_cast<long long>(b) * a.T;
+  for (long long j0 = 4 * (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x); j0 < a.T;
+       j0 += 4 * static_cast<long long>(gridDim.x) * blockDim.x) {
+    if (vec && j0 > hmax && j0 + 3 <= a.T - 2 - hmax) {
+      const float4 v = grad_ola_quad(a, b, j0);
+      g[j0] = v.x; g[j0 + 1] = v.y; g[j0 + 2] = v.z; g[j0 + 3] = v.w;
+    } else {
+      for (long long j = j0; j < min(j0 + 4, a.T); ++j) g[j] = grad_ola_sample<false>(a, b, j);
+    }
+  }
 }
 
 // ---- all resolutions in ONE launch ------------------------------------------------------------------------------------------

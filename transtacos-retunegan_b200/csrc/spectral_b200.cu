@@ -227,6 +227,20 @@ int sb200_frame_stats(const float* x, const sb200_batch* batch, int32_t frame_le
   return check_launch("frame_stats_kernel");
 }
 
+int sb200_trim_bounds(const float* rms, const int64_t* frame_off, int64_t frames_per_row, int32_t B, float top_db,
+                      int64_t* bounds, sb200_stream stream) {
+  if (!rms || !bounds || B < 1 || (!frame_off && frames_per_row < 1)) return fail(SB200_ERR_INVALID, "trim_bounds: bad argument");
+  TrimArgs a{};
+  a.rms = rms;
+  a.frame_off = reinterpret_cast<const long long*>(frame_off);
+  a.frames_per_row = frames_per_row;
+  a.B = B;
+  a.top_db = static_cast<double>(top_db);
+  a.out = reinterpret_cast<long long*>(bounds);
+  trim_bounds_kernel<<<grid_for(static_cast<long long>(B) * 32, 128, 8), 128, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  return check_launch("trim_bounds_kernel");
+}
+
 int sb200_yin(const float* x, const sb200_batch* batch, int32_t sample_rate, float fmin, float fmax, int32_t frame_length,
               int32_t hop_length, float trough_threshold, float* f0, sb200_stream stream) {
   if (!x || !f0) return fail(SB200_ERR_INVALID, "yin: null argument");

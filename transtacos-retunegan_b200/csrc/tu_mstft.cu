@@ -348,8 +348,8 @@ int sb200_mstft_backward(const sb200_plan* const* plans, int32_t n_res, const fl
     o.Tf[r] = a.Tf;
   }
   mstft_join(side, n_res, st);
-  dim3 grid(grid_for(T, 256, 2), B);
-  grad_ola_kernel<<<grid, 256, 0, st>>>(o);
+  dim3 grid(grid_for((T + 3) / 4, 256, 2), B);
+  grad_ola_kernel<<<grid, 256, 0, st>>>(o, MstftFinArgs{});
   return check_launch("grad_ola_kernel");
 }
 
@@ -401,10 +401,8 @@ int sb200_mstft_loss_and_grad(const sb200_plan* const* plans, int32_t n_res, con
     o.Tf[r] = a.Tf;
   }
   mstft_join(side, n_res, st);
-  mstft_finalize_kernel<<<1, 256, 0, st>>>(fin);
-  if (int rc = check_launch("mstft_finalize_kernel")) return rc;
-  dim3 grid(grid_for(T, 256, 2), B);
-  grad_ola_kernel<<<grid, 256, 0, st>>>(o);
+  dim3 grid(grid_for((T + 3) / 4, 256, 2), B);
+  grad_ola_kernel<<<grid, 256, 0, st>>>(o, fin);   // block (0, 0) also reduces the loss partial sums
   return check_launch("grad_ola_kernel");
 }
 
@@ -472,7 +470,7 @@ int sb200_stft_smp_backward(const sb200_plan* plan, const float* y, int32_t B, i
   o.n_fft[0] = plan->cfg.n_fft;
   o.hop[0] = plan->cfg.hop_length;
   o.Tf[0] = a.Tf;
-  dim3 og(grid_for(T, 256, 2), B);
-  grad_ola_kernel<<<og, 256, 0, st>>>(o);
+  dim3 og(grid_for((T + 3) / 4, 256, 2), B);
+  grad_ola_kernel<<<og, 256, 0, st>>>(o, MstftFinArgs{});
   return check_launch("grad_ola_kernel");
 }
