@@ -3,7 +3,7 @@
 #include <cstdio>
 #include <cstdlib>
 
-#include "feat3.cuh"
+#include "feat4.cuh"
 
 using namespace sb200;
 using namespace sb200::host;
@@ -69,13 +69,50 @@ long long make_stage_map(const FeatArgs& a, CUtensorMap* map) {
   return r == CUDA_SUCCESS ? total : 0;
 }
 
-// SB200_FEAT_KERNEL=2 selects the single-role kernel (feat2.cuh) for A/B measurements; default: warp-specialised (feat3.cuh)
-bool use_feat3(size_t smem3) {
+// SB200_FEAT_KERNEL selects the n_fft 2048 feature kernel for A/B measurements: 2 = single role (feat2.cuh), 3 = 8 analysis +
+// 8 epilogue warps (feat3.cuh, the default), 4 = 12 transform + 4 mel warps (feat4.cuh).  Measured on config 3 (tools/ab_feat.sh):
+// 97.6 / 86.8 / 96.9 us.
+int feat_kernel_choice() {
   static const int forced = [] {
     const char* e = std::getenv("SB200_FEAT_KERNEL");
     return e ? std::atoi(e) : 0;
   }();
-  return forced != 2 && smem3 <= 227u * 1024u;
+  return forced;
+}
+bool use_feat3(size_t smem3) { return feat_kernel_choice() != 2 && smem3 <= 227u * 1024u; }
+
+template <int N, bool PRE, bool LOGMAG, int HS>
+void launch_features4_t(const sb200_plan* plan, const FeatArgs& a, int grid, size_t smem, cudaStream_t st) {
+  cudaFuncSetAttribute(stft_feature4_kernel<N, PRE, LOGMAG, HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  stft_feature4_kernel<N, PRE, LOGMAG, HS><<<grid, kF4Threads, smem, st>>>(plan->dev, a);
+}
+
+// 12 + 4 kernel (n_fft 2048).  Returns false if not selected or the tables do not fit.
+template <int N>
+bool launch_features4(const sb200_plan* plan, const FeatArgs& a, cudaStream_t st) {
+  if constexpr (N != 2048) {
+    return false;
+  } else {
+    const int choice = feat_kernel_choice();
+    if (choice != 4) return false;
+    const size_t smem = feat4_smem_bytes<N>(plan->dev);
+    if (smem > 227u * 1024u) return false;
+    const long long ctas_needed = (a.bd.total_items + kF4Fft - 1) / kF4Fft;
+    const int grid = static_cast<int>(std::min<long long>(ctas_needed, sm_count()));
+    const bool pre = a.pre != 0.f, lg = a.mag_scale.log != 0;
+    if (plan->cfg.hop_length == 256) {
+      if (pre && lg) launch_features4_t<N, true, true, 4>(plan, a, grid, smem, st);
+      else if (pre) launch_features4_t<N, true, false, 4>(plan, a, grid, smem, st);
+      else if (lg) launch_features4_t<N, false, true, 4>(plan, a, grid, smem, st);
+      else launch_features4_t<N, false, false, 4>(plan, a, grid, smem, st);
+    } else {
+      if (pre && lg) launch_features4_t<N, true, true, 0>(plan, a, grid, smem, st);
+      else if (pre) launch_features4_t<N, true, false, 0>(plan, a, grid, smem, st);
+      else if (lg) launch_features4_t<N, false, true, 0>(plan, a, grid, smem, st);
+      else launch_features4_t<N, false, false, 0>(plan, a, grid, smem, st);
+    }
+    return true;
+  }
 }
 
 // Warp-specialised packed engine (the hot path).  Returns false if the configuration does not fit (tables too large).
@@ -111,6 +148,7 @@ bool launch_features3(const sb200_plan* plan, const FeatArgs& a, cudaStream_t st
 // Packed engine: magnitude / mel features.
 template <int N>
 int launch_features2(const sb200_plan* plan, const FeatArgs& a, cudaStream_t st) {
+  if (launch_features4<N>(plan, a, st)) return check_launch("stft_feature4_kernel");
   if (launch_features3<N>(plan, a, st)) return check_launch("stft_feature3_kernel");
   const size_t smem = feat2_smem_bytes<N>(plan->dev);
   const long long ctas_needed = (a.bd.total_items + kFeat2Warps - 1) / kFeat2Warps;
