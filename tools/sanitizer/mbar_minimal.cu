@@ -91,6 +91,29 @@ __global__ void handoff_pairs(float* out, int rounds, long long delay, int hi) {
   if (warp >= PAIRS) out[32 * w + lane] = acc;
 }
 
+// The same hand-off with ONE named barrier per warp pair (bar.sync id, 64), hit twice per round by both warps from their own
+// branches -- the producer / consumer use of named barriers (as CUTLASS's NamedBarrier), and feat3.cuh's default hand-off.
+template <int PAIRS>
+__global__ void handoff_named(float* out, int rounds) {
+  extern __shared__ __align__(16) unsigned char dyn[];
+  float* bufs = reinterpret_cast<float*>(dyn);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, w = warp % PAIRS;
+  float* buf = bufs + 32 * w;
+  float acc = 0.f;
+  for (int r = 0; r < rounds; ++r) {
+    if (warp < PAIRS) {
+      asm volatile("bar.sync %0, 64;" ::"r"(w + 1) : "memory");   // empty
+      buf[lane] = static_cast<float>(r * 32 + lane);
+      asm volatile("bar.sync %0, 64;" ::"r"(w + 1) : "memory");   // full
+    } else {
+      asm volatile("bar.sync %0, 64;" ::"r"(w + 1) : "memory");   // empty
+      asm volatile("bar.sync %0, 64;" ::"r"(w + 1) : "memory");   // full
+      acc += buf[31 - lane];
+    }
+  }
+  if (warp >= PAIRS) out[32 * w + lane] = acc;
+}
+
 int main() {
   float* out;
   cudaMalloc(&out, 32 * sizeof(float));
@@ -115,5 +138,11 @@ int main() {
       printf("8 warp pairs, 16 barriers at +%d KB, producer delay %lld cycles: %s, out[0] = %g, out[255] = %g (expect %g, %g)\n",
              hi / 1024, delay, cudaGetErrorString(e3), h8[0], h8[255], 8 * 31.f + 32.f * 28, 8 * 0.f + 32.f * 28);
     }
+  handoff_named<8><<<1, 512, 8 * 32 * 4>>>(out8, 8);
+  cudaError_t e4 = cudaDeviceSynchronize();
+  float h8[256];
+  cudaMemcpy(h8, out8, sizeof(h8), cudaMemcpyDeviceToHost);
+  printf("8 warp pairs, named barriers (bar.sync id, 64 from both branches): %s, out[0] = %g, out[255] = %g (expect %g, %g)\n",
+         cudaGetErrorString(e4), h8[0], h8[255], 8 * 31.f + 32.f * 28, 8 * 0.f + 32.f * 28);
   return 0;
 }

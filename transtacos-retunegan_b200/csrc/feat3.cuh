@@ -5,7 +5,7 @@
 // Why two roles: in the single-role kernel (feat2.cuh) the 8 warps of an SM drift into lock-step, so the FMA-bound
 // FFT, the shared-memory-bound exchange / mel phases and the MUFU-bound log phase run one after the other and each
 // pipe idles most of the time.  Here analysis warp w hands the squared magnitudes of one item (a frame pair set,
-// see feat2.cuh) to epilogue warp w through a private shared-memory buffer guarded by two mbarriers (full / empty),
+// see feat2.cuh) to epilogue warp w through a private shared-memory buffer guarded by a named barrier per warp pair (pair_bar_sync),
 // and moves on to the next item's FFT while the epilogue warp takes logs, stores and runs the mel filterbank.
 // Registers are re-partitioned with setmaxnreg (analysis 200, epilogue 56 per thread; 128 at launch).
 #pragma once
@@ -68,15 +68,24 @@ constexpr int kStageBoxCols = 64, kStageBoxRows = 21;
 constexpr int kStageFloats = kStageBoxCols * kStageBoxRows;     // 1344 >= 7 + 1280
 constexpr unsigned kStageBytes = kStageFloats * 4;
 
-// SB200_SANITIZER_NAMED_BARRIERS (tools/variants.py, sanitizer runs only): the same hand-off additionally bracketed by a named
-// barrier per warp pair (bar.sync id, 64: "empty" then "full", both warps run the same sequence).  compute-sanitizer's racecheck
-// models bar.sync but not an mbarrier arrive / try_wait pair written in inline PTX, so the product build shows the accesses on
-// either side of the mbarriers as hazards; with this variant it reports none, i.e. they are exactly the mbarrier-ordered pairs.
+// Hand-off between analysis warp w and epilogue warp w.  DEFAULT: one named barrier per warp pair (bar.sync id, 64), hit twice
+// per item by both warps: "empty" (the epilogue warp is done reading the previous item's powers; the analysis warp may
+// overwrite them) and "full" (the powers of this item are written; the epilogue warp may read them).  The hardware parks the
+// waiting warp: no polling loop, and compute-sanitizer's racecheck / synccheck model bar.sync exactly (0 hazards / 0 errors on
+// this build, profiles/r02_sanitizer/).  -DSB200_HANDOFF_MBARRIER (tools/variants.py) selects round 1's formulation instead, two
+// mbarriers per pair (full / empty, 32 arrivals each, try_wait loops): same speed within 0.3 % (87.3 vs 87.0 us on config 3), but
+// the two tools report the accesses on either side of it as hazards / "missing init" although a minimal kernel with the same
+// PTX (tools/sanitizer/mbar_minimal.cu) is clean under both -- an unexplained tool report the product build should not carry.
 __device__ __forceinline__ void pair_bar_sync(int w) {
-#ifdef SB200_SANITIZER_NAMED_BARRIERS
+#ifndef SB200_HANDOFF_MBARRIER
   asm volatile("bar.sync %0, 64;" ::"r"(w + 1) : "memory");
 #endif
 }
+#ifdef SB200_HANDOFF_MBARRIER
+#define SB200_HANDOFF_MBAR(x) x
+#else
+#define SB200_HANDOFF_MBAR(x)
+#endif
 
 template <int N>
 struct Smem3 {
@@ -309,7 +318,7 @@ __device__ __forceinline__ void feat3_analysis(const PlanDev& p, const FeatArgs&
       constexpr int s = decltype(sc)::value;
       spv[s] = sp[s * 32];
     });
-    mbar_wait(empty, (round & 1) ^ 1);   // the epilogue warp is done with the previous item's powers
+    SB200_HANDOFF_MBAR(mbar_wait(empty, (round & 1) ^ 1));   // the epilogue warp is done with the previous item's powers
     pair_bar_sync(w);
     {
       // self pair of column 0 (bin Nz/2) first: the exchange below overwrites v[16]
@@ -327,7 +336,7 @@ __device__ __forceinline__ void feat3_analysis(const PlanDev& p, const FeatArgs&
       if constexpr (s == 0) sb0[0] = norm2(am);
       else sb[-C::kR2 * s] = norm2(am);
     });
-    mbar_arrive(full);
+    SB200_HANDOFF_MBAR(mbar_arrive(full));
     pair_bar_sync(w);
   }
 }
@@ -348,11 +357,11 @@ __device__ __forceinline__ void feat3_epilogue(const PlanDev& p, const FeatArgs&
   for (long long item = static_cast<long long>(blockIdx.x) * kFeat3Pairs + w; item < a.bd.total_items; item += warps_total, ++round) {
     const Item it = decode_item(a.bd, item, C::kFrames);
     pair_bar_sync(w);
-    mbar_wait(full, round & 1);
+    SB200_HANDOFF_MBAR(mbar_wait(full, round & 1));
     pair_bar_sync(w);
 #ifdef SB200_ABLATE_EPILOGUE   // ablation builds (tools/variants.py): what the analysis role costs on its own
     if (a.mag == reinterpret_cast<float*>(1)) a.mag[0] = plo(pbuf[lane]);
-    mbar_arrive(empty);
+    SB200_HANDOFF_MBAR(mbar_arrive(empty));
     continue;
 #endif
 #pragma unroll
@@ -443,7 +452,7 @@ __device__ __forceinline__ void feat3_epilogue(const PlanDev& p, const FeatArgs&
         }
       }
     }
-    mbar_arrive(empty);
+    SB200_HANDOFF_MBAR(mbar_arrive(empty));
   }
 }
 

@@ -181,7 +181,7 @@ __device__ __forceinline__ void feat4_transform(const PlanDev& p, const FeatArgs
     float* const pa = a.mag + (it.frame_base + it.t0) * C::kF + k1;             // bins k1 + 32 s       (frame B: + F)
     float* const pb = a.mag + (it.frame_base + it.t0) * C::kF + C::kNz - k1;    // bins Nz - k1 - 32 s
     if (want_mel) {
-      mbar_wait(empty, (round & 1) ^ 1);   // the mel warp is done with the previous item's band
+      SB200_HANDOFF_MBAR(mbar_wait(empty, (round & 1) ^ 1));   // the mel warp is done with the previous item's band
       pair_bar_sync(w);
     }
     {
@@ -224,7 +224,7 @@ __device__ __forceinline__ void feat4_transform(const PlanDev& p, const FeatArgs
       });
     });
     if (want_mel) {
-      mbar_arrive(full);
+      SB200_HANDOFF_MBAR(mbar_arrive(full));
       pair_bar_sync(w);
     }
   }
@@ -246,7 +246,7 @@ __device__ __forceinline__ void feat4_mel(const PlanDev& p, const FeatArgs& a, S
       const pf* band = sm.bands + w * kF4BandElems;
       const Item it = decode_item(a.bd, item, C::kFrames);
       pair_bar_sync(w);
-      mbar_wait(smem_u32(sm.bar + w), round & 1);
+      SB200_HANDOFF_MBAR(mbar_wait(smem_u32(sm.bar + w), round & 1));
       pair_bar_sync(w);
 #pragma unroll
       for (int rd = 0; rd < kMaxMelRounds; ++rd) {
@@ -278,7 +278,7 @@ __device__ __forceinline__ void feat4_mel(const PlanDev& p, const FeatArgs& a, S
           }
         }
       }
-      mbar_arrive(smem_u32(sm.bar + kF4Fft + w));
+      SB200_HANDOFF_MBAR(mbar_arrive(smem_u32(sm.bar + kF4Fft + w)));
     }
   }
 }
