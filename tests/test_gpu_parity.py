@@ -654,3 +654,30 @@ def test_get_stft_torch_is_differentiable_like_the_reference(sb, ri):
     assert rel_fro(gM_only.cpu().numpy(), gM_ref.numpy()) <= 1e-4
     S1, M1, P1 = sb.retunegan_audio.get_stft_torch(yc[0].detach(), n_fft, win, hop)
     assert S1.dim() == 2 and torch.equal(S1, S[0].detach())
+
+
+# ------------------------------------------------------------------ bounded caches -----------
+
+def test_host_pipeline_and_phase_cache_stay_bounded(sb):
+    """A corpus / DataLoader changes the padded length every step: one host-batch pipeline per (plan, chunk) serves every length
+    (grow-only slots), and the seeded-phase cache keeps at most _PHASE_LRU layouts.  Results do not depend on the order."""
+    ta, ra = sb.transtacos_audio, sb.retunegan_audio
+    before = len(sb.core._pipelines)
+    for i, T in enumerate([40, 25, 61, 33, 61, 12]):
+        yb = np.stack([O.synth_noise(256 * T - 1, 700 + 3 * i + b) for b in range(3)])
+        Sb, Mb = ta.get_specs(yb, out_dtype=np.float32)                 # host [B, L] batch -> chunked copy pipeline
+        for b in range(3):
+            S1, M1 = ta.get_specs(yb[b], out_dtype=np.float32)
+            np.testing.assert_array_equal(Sb[b], S1)
+            np.testing.assert_array_equal(Mb[b], M1)
+    assert len(sb.core._pipelines) <= before + 1
+    ra._phase_cache.clear()
+    mag = ra.get_mag(O.synth_speechlike(256 * 40 - 1, 3))
+    first = ra.inv_mag(mag[:, :21], wavlen=256 * 21 - 1)
+    for T in range(8, 8 + 2 * ra._PHASE_LRU):
+        ra.inv_mag(mag[:, :T], wavlen=256 * T - 1)
+    assert len(ra._phase_cache) <= ra._PHASE_LRU
+    np.testing.assert_array_equal(ra.inv_mag(mag[:, :21], wavlen=256 * 21 - 1), first)
+    u = np.random.RandomState(114514).rand(1025, 21)                    # librosa.griffinlim(random_state=114514) draws this afresh
+    ref = O.rtg_inv_mag(mag[:, :21].astype(np.float32), wavlen=256 * 21 - 1, init_angles=np.exp(2j * np.pi * u))
+    assert rel_fro(first, ref) <= 1e-3

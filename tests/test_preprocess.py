@@ -174,3 +174,21 @@ def test_preprocess_small_corpus_end_to_end(tmp_path):
     assert stats['min_mag'] >= -5.6 - 1e-3                       # floor of the normalised dB scale (stats/DataBaker.stats:13)
     P.write_metadata(metadata, stats, wav_dp, str(base), "preprocessed")
     assert sorted(os.listdir(base / "preprocessed"))[-4:] == ["stats.txt", "test.txt", "train.txt", "wav_path.txt"]
+
+
+@pytest.mark.gpu
+def test_too_short_clip_is_skipped_not_fatal(tmp_path):
+    """One clip that is too short for the centred window (after trimming) must not abort the batch: the reference handles clips
+    one by one (datasets/databaker.py:91-122), so the others are still written and the short one comes back as None."""
+    import transtacos_retunegan_b200 as sb
+    P = sb.preprocess
+    good = (1e-4 * O.synth_noise(20000, 1)).astype(np.float32)
+    good[2000:18000] += O.synth_speechlike(16000, 5)
+    items = [("a", ("ka2 er2", "01"), good), ("b", ("pu3 pei2", "01"), np.zeros(300, np.float32) + 1e-3),
+             ("c", ("wai4 sun1", "01"), np.ones(1, np.float32)), ("d", ("wan2 hua2", "01"), good[::-1].copy())]
+    with pytest.warns(UserWarning, match="too short"):
+        out = P.make_metadata_batch(items, str(tmp_path))
+    assert out[1] is None and out[2] is None and out[0] is not None and out[3] is not None
+    assert out[0][0] == "a" and os.path.exists(tmp_path / "mag-a.npy") and not os.path.exists(tmp_path / "mag-b.npy")
+    with pytest.raises(ValueError):
+        sb.core.yin(np.zeros(100, np.float32), 22050, 73.0, 590.0, 1024, 256)      # shorter than frame_length / 2 + 1

@@ -15,6 +15,14 @@
 
 namespace sb200 {
 
+// Mel formulation of the epilogue: the banded ELL filterbank (default) or, with -DSB200_MEL_SEGMENTS (tools/variants.py,
+// tools/ab_mel.sh), the segment formulation (PlanDev::seg_slot: every band bin read once, no weight loads).  Measured on
+// config 3: segments 91.6 us, ELL 87.0 us -- fewer shared-memory wavefronts, but the masked trips and the carry chain between
+// rounds cost more issue slots than the weights did.
+#ifndef SB200_MEL_SEGMENTS
+#define SB200_MEL_ELL
+#endif
+
 constexpr int kFeat3Pairs = 8;                 // analysis / epilogue warp pairs per CTA
 constexpr int kFeat3Threads = 2 * kFeat3Pairs * 32;
 constexpr int kFeat3PbufElems = 1024 + 16;     // [P][Nz] powers of both frames of a pair + P Nyquist bins + zero pad
@@ -95,13 +103,25 @@ struct Smem3 {
   float* win;               // [win] 0.5 * analysis window
   float2* tw;               // [kTwCount]
   float2* sp2;              // [17*32]
+#ifdef SB200_MEL_ELL
   float* melw;              // [melw_count]
   int* mel_lo;              // [32*rounds]
+#else
+  int4* seg_slot;           // [32*seg_rounds] segment view of the filterbank (plan.cuh)
+  float2* seg_coef;         // [32*seg_rounds]
+  float* enorm;             // [n_mel rounded up to 4]
+#endif
   unsigned long long* bar;  // [3*pairs]: full[w], empty[w], staged[w] (bulk-tensor copy of the next item's samples landed)
-  __host__ __device__ static size_t bytes(int melw_count, int mel_rounds) {
+  __host__ __device__ static size_t mel_table_bytes(const PlanDev& p) {
+#ifdef SB200_MEL_ELL
+    return sizeof(float) * p.melw_count + sizeof(int) * 32 * p.mel_rounds;
+#else
+    return (sizeof(int4) + sizeof(float2)) * 32 * p.seg_rounds + sizeof(float) * ((p.n_mel + 3) / 4 * 4);
+#endif
+  }
+  __host__ __device__ static size_t bytes(const PlanDev& p) {
     return static_cast<size_t>(kFeat3Pairs) * (C::kXBytes + kFeat3PbufElems * sizeof(pf)) + sizeof(float) * C::kWin +
-           sizeof(float2) * (C::kTwCount + 17 * 32) + sizeof(float) * melw_count + sizeof(int) * 32 * mel_rounds +
-           sizeof(unsigned long long) * 3 * kFeat3Pairs;
+           sizeof(float2) * (C::kTwCount + 17 * 32) + mel_table_bytes(p) + sizeof(unsigned long long) * 3 * kFeat3Pairs;
   }
   __device__ __forceinline__ void carve(unsigned char* raw, const PlanDev& p) {
     xbufs = reinterpret_cast<uint4*>(raw);
@@ -109,9 +129,16 @@ struct Smem3 {
     win = reinterpret_cast<float*>(pbufs + kFeat3Pairs * kFeat3PbufElems);
     tw = reinterpret_cast<float2*>(win + C::kWin);
     sp2 = tw + C::kTwCount;
+#ifdef SB200_MEL_ELL
     melw = reinterpret_cast<float*>(sp2 + 17 * 32);
     mel_lo = reinterpret_cast<int*>(melw + p.melw_count);
     bar = reinterpret_cast<unsigned long long*>(mel_lo + 32 * p.mel_rounds);
+#else
+    seg_slot = reinterpret_cast<int4*>(sp2 + 17 * 32);
+    seg_coef = reinterpret_cast<float2*>(seg_slot + 32 * p.seg_rounds);
+    enorm = reinterpret_cast<float*>(seg_coef + 32 * p.seg_rounds);
+    bar = reinterpret_cast<unsigned long long*>(enorm + (p.n_mel + 3) / 4 * 4);
+#endif
   }
   template <class T>
   static __device__ __forceinline__ void copy16(T* dst, const T* src, int count, float scale = 1.f) {
@@ -130,8 +157,14 @@ struct Smem3 {
     copy16(tw, p.tw, C::kTwCount);
     copy16(sp2, p.sp2, 17 * 32);
     if (with_mel) {
+#ifdef SB200_MEL_ELL
       copy16(melw, p.melw, p.melw_count);
       copy16(mel_lo, p.mel_lo, 32 * p.mel_rounds);
+#else
+      copy16(seg_slot, p.seg_slot, 32 * p.seg_rounds);
+      copy16(seg_coef, p.seg_coef, 32 * p.seg_rounds);
+      for (int i = threadIdx.x; i < p.n_mel; i += kFeat3Threads) enorm[i] = p.mel_enorm[i];
+#endif
     }
     for (int i = threadIdx.x; i < kFeat3Pairs * kFeat3PbufElems; i += kFeat3Threads) pbufs[i] = 0ull;
   }
@@ -351,7 +384,11 @@ __device__ __forceinline__ void feat3_epilogue(const PlanDev& p, const FeatArgs&
   const bool logmag = a.mag_scale.log != 0;
   // squared-magnitude form of the log scale: a log2 max(floor, sqrt p) + b = a/2 log2 max(floor^2, p) + b
   const float mag_a = 0.5f * a.mag_scale.a, mag_b = a.mag_scale.b, mag_fl = a.mag_scale.floor * a.mag_scale.floor;
+#if defined(SB200_MEL_ELL) || !defined(SB200_MEL_SEG_SQRT)
   const int c_lo = want_mel ? p.mel_kmin / 32 : 1 << 30, c_hi = want_mel ? p.mel_kmax / 32 : -1;   // chunks the mel filters read
+#else
+  constexpr int c_lo = 1 << 30, c_hi = -1;   // segment mel taking the square roots itself: nothing is written back
+#endif
   const long long warps_total = static_cast<long long>(gridDim.x) * kFeat3Pairs;
   unsigned round = 0;
   for (long long item = static_cast<long long>(blockIdx.x) * kFeat3Pairs + w; item < a.bd.total_items; item += warps_total, ++round) {
@@ -406,10 +443,12 @@ __device__ __forceinline__ void feat3_epilogue(const PlanDev& p, const FeatArgs&
     }
     __syncwarp();
 #ifdef SB200_ABLATE_MEL
-    if (false) {
+    const bool mel_on = false;
 #else
-    if (want_mel) {
+    const bool mel_on = want_mel;
 #endif
+#ifdef SB200_MEL_ELL
+    if (mel_on) {
 #pragma unroll
       for (int rd = 0; rd < kMaxMelRounds; ++rd) {
         if (rd < p.mel_rounds) {
@@ -452,6 +491,76 @@ __device__ __forceinline__ void feat3_epilogue(const PlanDev& p, const FeatArgs&
         }
       }
     }
+#else
+    // Mel by segments (PlanDev::seg_slot): lane l of round r owns segment j = 32 r + l, the bins between filter centres c_j and
+    // c_{j+1}.  It reads every bin of its segment ONCE (the power itself: the square root is taken here, nothing is written
+    // back to the buffer and no weight is loaded), accumulating A = sum S_k and B = sum (k - k0) S_k; then R = r0 A + a B is
+    // what the segment gives the rising filter j and E = A - R what it gives the falling filter j - 1, and
+    // mel[m] = enorm_m (R_m + E_{m+1}) with E_{m+1} from the next lane (rounds run from the last to the first, the first lane
+    // of the later round hands its E to lane 31 of the earlier one).  Trips before the segment starts (the d bins of bank
+    // alignment) and after it ends are masked by predication, so whatever lies there never enters the sums.
+    if (mel_on) {
+      pf carryE[C::kP];   // E of segment 32 (r + 1), from round r + 1
+#pragma unroll
+      for (int q = 0; q < C::kP; ++q) carryE[q] = 0ull;
+#pragma unroll
+      for (int rdi = 0; rdi < kMaxSegRounds; ++rdi) {
+        const int rd = p.seg_rounds - 1 - rdi;
+        if (rd >= 0) {
+          const int4 slot = sm.seg_slot[rd * 32 + lane];
+          const float2 cf = sm.seg_coef[rd * 32 + lane];
+          const pf* sr = pbuf + slot.x;
+          const int n = p.seg_round_len[rd];   // multiple of 4
+          const unsigned d = static_cast<unsigned>(slot.y), len = static_cast<unsigned>(slot.z);
+          pf accA[C::kP], accB[C::kP];
+#pragma unroll
+          for (int q = 0; q < C::kP; ++q) accA[q] = accB[q] = 0ull;
+          float kk = -static_cast<float>(slot.y);
+#pragma unroll 1
+          for (int i0 = 0; i0 < n; i0 += 4) {
+            pf pv[C::kP][4];
+#pragma unroll
+            for (int q = 0; q < C::kP; ++q)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) pv[q][j] = sr[q * C::kNz + i0 + j];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const bool in = static_cast<unsigned>(i0 + j) - d < len;
+#pragma unroll
+              for (int q = 0; q < C::kP; ++q) {
+#ifdef SB200_MEL_SEG_SQRT
+                const pf sq = sqrt2(pv[q][j]);
+#else
+                const pf sq = pv[q][j];   // the log loop above has written the magnitudes of the band back in place
+#endif
+                if (in) {
+                  accA[q] = add2(accA[q], sq);
+                  accB[q] = fma2s(sq, kk, accB[q]);
+                }
+              }
+              kk += 1.f;
+            }
+          }
+          const int m = rd * 32 + lane;   // filter m rises in segment m and falls in segment m + 1
+#pragma unroll
+          for (int q = 0; q < C::kP; ++q) {
+            const pf R = fma2s(accB[q], cf.y, mul2s(accA[q], cf.x));
+            const pf E = sub2(accA[q], R);
+            pf En = __shfl_down_sync(kFullMask, E, 1);
+            if (lane == 31) En = carryE[q];
+            carryE[q] = __shfl_sync(kFullMask, E, 0);
+            if (m < p.n_mel) {
+              const pf s = mul2s(add2(R, En), sm.enorm[m]);
+              const int f = it.t0 + 2 * q;
+              float* dst = a.mel + (it.frame_base + f) * p.n_mel + m;
+              if (f < it.T) dst[0] = apply_scale(a.mel_scale, plo(s));
+              if (f + 1 < it.T) dst[p.n_mel] = apply_scale(a.mel_scale, phi(s));
+            }
+          }
+        }
+      }
+    }
+#endif
     SB200_HANDOFF_MBAR(mbar_arrive(empty));
   }
 }
@@ -493,7 +602,7 @@ __global__ void __launch_bounds__(kFeat3Threads, 1) stft_feature3_kernel(const P
 
 template <int N>
 inline size_t feat3_smem_bytes(const PlanDev& p) {
-  return Smem3<N>::bytes(p.melw_count, p.mel_rounds);
+  return Smem3<N>::bytes(p);
 }
 
 }  // namespace sb200

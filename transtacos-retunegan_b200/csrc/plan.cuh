@@ -18,6 +18,7 @@
 namespace sb200 {
 
 constexpr int kMaxMelRounds = 4;   // n_mel <= 128
+constexpr int kMaxSegRounds = 5;   // n_mel + 1 <= 129 segments between neighbouring filter centres
 
 // Device view of a plan, passed by value to kernels.
 struct PlanDev {
@@ -43,6 +44,18 @@ struct PlanDev {
   int mel_round_len[kMaxMelRounds];
   int melw_count;         // floats in melw
   int mel_kmin, mel_kmax; // first / last bin with a non-zero filter weight
+  // Segment view of the triangular filterbank (feat3.cuh): segment j = the bins between filter centres c_j and c_{j+1}
+  // (j = 0 .. n_mel), where filter j rises with r_k = r0_j + a_j (k - k0_j) and filter j-1 falls with 1 - r_k.  With
+  // A_j = sum S_k and B_j = sum (k - k0_j) S_k over the segment, R_j = r0_j A_j + a_j B_j, E_j = A_j - R_j:
+  //   mel[m] = enorm_m (R_m + E_{m+1}).
+  // Every band bin is read ONCE and no weight is loaded.  Segments sit in their natural order (round j / 32, lane j % 32);
+  // lane l of round r starts its reads seg_slot[].y bins early (masked) so that the 16 lanes of a half-warp hit 16 different
+  // 8-byte bank pairs in every trip (exact matching, minimal round length).
+  const int4* seg_slot;   // [32*seg_rounds]  {first bin read = k0 - d, d, len, 1 if the slot holds a segment}
+  const float2* seg_coef; // [32*seg_rounds]  {r0, a}
+  const float* mel_enorm; // [n_mel]          2 / (c_{m+2} - c_m)  (Slaney area normalisation)
+  int seg_rounds;
+  int seg_round_len[kMaxSegRounds];
   // column view (<= 2 non-zeros per column, consecutive rows): basis[r0[k], k] = c0[k], basis[r0[k]+1, k] = c1[k]
   const int* col_r0;      // [F]
   const float* col_c0;    // [F]
@@ -293,6 +306,79 @@ inline std::string build_plan(const sb200_config& c, sb200_plan* p, int* st) {
       d.mel_kmin = std::min(d.mel_kmin, lo[m]);
       d.mel_kmax = std::max(d.mel_kmax, lo[m] + len[m] - 1);
     }
+  // ---- segment view (see PlanDev) ----
+  const int n_seg = c.n_mel + 1;
+  const int seg_rounds = (n_seg + 31) / 32;
+  d.seg_rounds = seg_rounds;
+  std::vector<int4> seg_slot(static_cast<size_t>(32) * seg_rounds, make_int4(0, 0, 0, 0));
+  std::vector<float2> seg_coef(static_cast<size_t>(32) * seg_rounds, make_float2(0.f, 0.f));
+  std::vector<float> enorm(c.n_mel, 0.f);
+  for (int r = 0; r < kMaxSegRounds; ++r) d.seg_round_len[r] = 0;
+  {
+    const bool htk = c.mel_htk != 0;
+    std::vector<double> cf(c.n_mel + 2);
+    const double m0 = hz_to_mel(c.fmin, htk), m1 = hz_to_mel(c.fmax, htk), step = (m1 - m0) / (c.n_mel + 1);
+    for (int i = 0; i < c.n_mel + 2; ++i) cf[i] = mel_to_hz(i == c.n_mel + 1 ? m1 : m0 + i * step, htk);
+    const double df = (c.sample_rate / 2.0) / (F - 1);
+    auto first_bin_at = [&](double hz) {   // first k with f_k >= hz
+      int k = static_cast<int>(std::floor(hz / df)) - 1;
+      if (k < 0) k = 0;
+      while (k < F && k * df < hz) ++k;
+      return k;
+    };
+    std::vector<int> sk0(n_seg), slen(n_seg);
+    for (int j = 0; j < n_seg; ++j) {
+      sk0[j] = first_bin_at(cf[j]);
+      slen[j] = std::max(0, first_bin_at(cf[j + 1]) - sk0[j]);
+    }
+    for (int m = 0; m < c.n_mel; ++m) enorm[m] = static_cast<float>(2.0 / (cf[m + 2] - cf[m]));
+    for (int r = 0; r < seg_rounds; ++r) {
+      int k0r[32], lenr[32], dsh[32];
+      int mx = 0;
+      for (int l = 0; l < 32; ++l) {
+        const int j = 32 * r + l;
+        k0r[l] = j < n_seg ? sk0[j] : 64 + l;   // empty slots: masked entirely, any bank will do
+        lenr[l] = j < n_seg ? slen[j] : 0;
+        mx = std::max(mx, lenr[l]);
+      }
+      // smallest round length L for which both half-warps have a perfect matching lane -> residue (k0 - d) mod 16, d <= L - len
+      int L = std::max(mx, 1);
+      for (;; ++L) {
+        bool ok = true;
+        for (int h = 0; h < 2 && ok; ++h) {
+          int owner[16];
+          for (int q = 0; q < 16; ++q) owner[q] = -1;
+          std::function<bool(int, std::vector<char>&)> place = [&](int l, std::vector<char>& seen) -> bool {
+            for (int dd = 0; dd <= std::min(L - lenr[l], k0r[l]); ++dd) {
+              const int q = (k0r[l] - dd) & 15;
+              if (seen[q]) continue;
+              seen[q] = 1;
+              if (owner[q] < 0 || place(owner[q], seen)) {
+                owner[q] = l;
+                dsh[l] = dd;
+                return true;
+              }
+            }
+            return false;
+          };
+          for (int l = 16 * h; l < 16 * h + 16 && ok; ++l) {
+            std::vector<char> seen(16, 0);
+            ok = place(l, seen);
+          }
+        }
+        if (ok || L > mx + 32) break;   // (L > mx + 32 cannot happen: 16 shifts reach every residue)
+      }
+      d.seg_round_len[r] = (L + 3) / 4 * 4;   // the kernel walks a round in chunks of 4 trips
+      for (int l = 0; l < 32; ++l) {
+        const int j = 32 * r + l;
+        seg_slot[32 * r + l] = make_int4(k0r[l] - dsh[l], dsh[l], lenr[l], j < n_seg ? 1 : 0);
+        if (j < n_seg) {
+          const double delta = cf[j + 1] - cf[j];
+          seg_coef[32 * r + l] = make_float2(static_cast<float>((sk0[j] * df - cf[j]) / delta), static_cast<float>(df / delta));
+        }
+      }
+    }
+  }
   std::vector<int> r0(F, 0);
   std::vector<float> c0(F, 0.f), c1(F, 0.f);
   for (int k = 0; k < F; ++k) {
@@ -329,6 +415,7 @@ inline std::string build_plan(const sb200_config& c, sb200_plan* p, int* st) {
 #define SB200_UP(vec, field) \
   if ((e = upload(p, vec, &d.field)) != cudaSuccess) return std::string("cuda upload: ") + cudaGetErrorString(e);
   SB200_UP(wf, window) SB200_UP(wout, wout) SB200_UP(wnorm, wnorm) SB200_UP(wsq, wsq) SB200_UP(wedge, wedge) SB200_UP(tw, tw) SB200_UP(ws, ws) SB200_UP(sp2, sp2) SB200_UP(spn, spn)
+  SB200_UP(seg_slot, seg_slot) SB200_UP(seg_coef, seg_coef) SB200_UP(enorm, mel_enorm)
   SB200_UP(melw, melw) SB200_UP(slots, mel_lo) SB200_UP(r0, col_r0) SB200_UP(c0, col_c0) SB200_UP(c1, col_c1) SB200_UP(lc0, lin_c0) SB200_UP(lc1, lin_c1)
 #undef SB200_UP
   *st = SB200_OK;
