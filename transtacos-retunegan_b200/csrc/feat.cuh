@@ -77,6 +77,51 @@ __device__ __forceinline__ float apply_scale(const ScaleDev& s, float v) {
   return s.log ? fmaf(s.a, fast_lg2(fmaxf(s.floor, v)), s.b) : v;
 }
 
+// Table fill: up to NS segments of 16-byte chunks copied global -> shared as ONE index space, four chunks per thread in flight
+// (all loads of a batch before its stores).  A CTA of the mstft kernels lives for one pass per warp, so the latency of its table
+// fill is on every warp's critical path (profiles: 10-13 % of the warp time with one scalar loop per table).
+struct CopySeg {
+  const uint4* src;
+  uint4* dst;
+  int n16;
+};
+template <class T>
+__device__ __forceinline__ CopySeg copy_seg(T* dst, const T* src, int count) {
+  return CopySeg{reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), static_cast<int>(count * sizeof(T) / 16)};
+}
+template <int NS>
+__device__ __forceinline__ void copy_segments(const CopySeg (&seg)[NS], int ns) {
+  int total = 0;
+#pragma unroll
+  for (int s = 0; s < NS; ++s) total += s < ns ? seg[s].n16 : 0;
+  constexpr int kBatch = 4;
+  for (int i0 = threadIdx.x; i0 < total; i0 += kBatch * blockDim.x) {
+    uint4 r[kBatch];
+    uint4* d[kBatch];
+#pragma unroll
+    for (int j = 0; j < kBatch; ++j) {
+      int i = i0 + j * blockDim.x;
+      d[j] = nullptr;
+      if (i < total) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          if (s < ns && d[j] == nullptr) {
+            if (i < seg[s].n16) {
+              r[j] = __ldg(seg[s].src + i);
+              d[j] = seg[s].dst + i;
+            } else {
+              i -= seg[s].n16;
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kBatch; ++j)
+      if (d[j] != nullptr) *d[j] = r[j];
+  }
+}
+
 // Shared-memory table block common to all FFT kernels.
 template <int N>
 struct SmemTables {
@@ -100,6 +145,16 @@ struct SmemTables {
     melw = reinterpret_cast<float*>(ws + kWsCount);
     mel_lo = reinterpret_cast<int*>(melw + p.melw_count);
     bufs = reinterpret_cast<float2*>(mel_lo + 32 * p.mel_rounds);
+  }
+  // the same fill as copy segments (every table is a whole number of 16-byte chunks); returns the number of segments
+  __device__ __forceinline__ int segments(const PlanDev& p, const float* win_src, bool with_mel, CopySeg* out) {
+    out[0] = copy_seg(win, win_src, C::kWin);
+    out[1] = copy_seg(tw, p.tw, kTwCount);
+    out[2] = copy_seg(ws, p.ws, kWsCount);
+    if (!with_mel) return 3;
+    out[3] = copy_seg(melw, p.melw, p.melw_count);
+    out[4] = copy_seg(mel_lo, p.mel_lo, 32 * p.mel_rounds);
+    return 5;
   }
   // which: analysis window (p.window) or any other [win] table
   __device__ __forceinline__ void fill(const PlanDev& p, const float* win_src, bool with_mel) {

@@ -19,6 +19,12 @@ namespace sb200 {
 constexpr float kRefPI = 3.14159265358979f;   // retunegan/utils.py:12
 constexpr int kMstftWarps = 8;
 constexpr int kMaxRes = 4;
+// unroll factor of the rolled Hermitian-pair / mel-tap loops of the backward kernels (independent iterations in flight per warp
+// against instruction-cache footprint: every warp runs the body once)
+#ifndef SB200_MSTFT_UNROLL
+#define SB200_MSTFT_UNROLL 2
+#endif
+constexpr int kMstftUnroll = SB200_MSTFT_UNROLL;
 
 struct MstftFwdArgs {
   const float* y;
@@ -62,7 +68,7 @@ __device__ __forceinline__ void mstft_analyse(const PlanDev& p, const SmemTables
         split_fwd(zq[k], zq[km], sm.ws[k], Ak, Am);
         const float2 Xk = rot_fwd(Ak, rk), Xm = rot_fwd(Am, rm);
         const float rek = Xk.x + 1e-9f, rem = Xm.x + 1e-9f;
-        const float sk = sqrtf(fmaf(rek, rek, Xk.y * Xk.y)), smg = sqrtf(fmaf(rem, rem, Xm.y * Xm.y));
+        const float sk = fast_sqrt(fmaf(rek, rek, Xk.y * Xk.y)), smg = fast_sqrt(fmaf(rem, rem, Xm.y * Xm.y));
         zq[k].x = sk;
         if (k != 0) zq[km].x = smg;
         emit(Xk, k, sk);
@@ -74,7 +80,7 @@ __device__ __forceinline__ void mstft_analyse(const PlanDev& p, const SmemTables
         split_fwd(zq[k], zq[k], sm.ws[k], Ak, Am);
         const float2 Xk = rot_fwd(Ak, k);
         const float rek = Xk.x + 1e-9f;
-        const float sk = sqrtf(fmaf(rek, rek, Xk.y * Xk.y));
+        const float sk = fast_sqrt(fmaf(rek, rek, Xk.y * Xk.y));
         zq[k].x = sk;
         emit(Xk, k, sk);
       }
@@ -90,7 +96,10 @@ __device__ __forceinline__ void mstft_fwd_body(const PlanDev& p, const MstftFwdA
   using C = FftCfg<N>;
   SmemTables<N> sm;
   sm.carve(smem_raw, p);
-  sm.fill(p, p.window, true);
+  {
+    CopySeg seg[5];
+    copy_segments(seg, sm.segments(p, p.window, true, seg));
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float2* buf = sm.bufs + warp * C::kBufF2;
@@ -154,7 +163,10 @@ __global__ void __launch_bounds__(kMstftWarps * 32, 2) stft_smp_kernel(const Pla
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemTables<N> sm;
   sm.carve(smem_raw, p);
-  sm.fill(p, p.window, a.M != nullptr);
+  {
+    CopySeg seg[5];
+    copy_segments(seg, sm.segments(p, p.window, a.M != nullptr, seg));
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float2* buf = sm.bufs + warp * C::kBufF2;
@@ -224,10 +236,11 @@ struct MstftBwdArgs {
 };
 
 // Shared-memory bytes of mstft_bwd_kernel: the tables and per-warp FFT buffers of the forward kernel plus, per warp, the
-// mel-row gradients [Q][128].
+// mel-row gradients [Q][128], and the column view of the mel basis ({c0, c1} and the first row per bin).
 template <int N>
 inline size_t mstft_bwd_smem_bytes(const PlanDev& p) {
-  return feat_smem_bytes<N>(p) + sizeof(float) * kMstftWarps * FftCfg<N>::kQ * 128;
+  return feat_smem_bytes<N>(p) + sizeof(float) * kMstftWarps * FftCfg<N>::kQ * 128 + sizeof(float2) * ((FftCfg<N>::kF + 1) & ~1) +
+         ((FftCfg<N>::kF + 15) & ~15);
 }
 
 // mel projection of |X + 1e-9| with the complex spectrum X in buf (natural bin order), magnitudes taken on the fly
@@ -244,7 +257,7 @@ __device__ __forceinline__ void mel_project_cplx(const PlanDev& p, const float* 
     float acc[C::kQ];
 #pragma unroll
     for (int q = 0; q < C::kQ; ++q) acc[q] = 0.f;
-#pragma unroll 2
+#pragma unroll kMstftUnroll
     for (int it = 0; it < n; ++it) {
       const float w = wr[it * 32];
       const int idx = min(lo + it, C::kNz - 1);
@@ -252,7 +265,7 @@ __device__ __forceinline__ void mel_project_cplx(const PlanDev& p, const float* 
       for (int q = 0; q < C::kQ; ++q) {
         const float2 X = buf[q * C::kZS + idx];
         const float re = X.x + 1e-9f;
-        acc[q] = fmaf(w, sqrtf(fmaf(re, re, X.y * X.y)), acc[q]);
+        acc[q] = fmaf(w, fast_sqrt(fmaf(re, re, X.y * X.y)), acc[q]);
       }
     }
 #pragma unroll
@@ -272,11 +285,21 @@ __device__ __forceinline__ void mstft_bwd_body(const PlanDev& p, const MstftBwdA
   using C = FftCfg<N>;
   SmemTables<N> sm;
   sm.carve(smem_raw, p);
-  sm.fill(p, p.window, true);
-  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float2* buf = sm.bufs + warp * C::kBufF2;
   float* gmbuf = reinterpret_cast<float*>(sm.bufs + kMstftWarps * C::kBufF2) + warp * C::kQ * 128;   // [Q][128] mel-row gradients
+  // column view of the mel basis: gS[k] = c0[k] gM[r0[k]] + c1[k] gM[r0[k] + 1].  In shared memory: read from global inside the
+  // pair loop it was the largest stall of the kernel (long scoreboard, 20 % of the warp time).
+  float2* colc = reinterpret_cast<float2*>(reinterpret_cast<float*>(sm.bufs + kMstftWarps * C::kBufF2) + kMstftWarps * C::kQ * 128);
+  unsigned char* colr = reinterpret_cast<unsigned char*>(colc + ((C::kF + 1) & ~1));
+  {
+    CopySeg seg[7];
+    const int ns = sm.segments(p, p.window, true, seg);
+    seg[ns] = copy_seg(colc, p.col_c01, (C::kF + 1) & ~1);
+    seg[ns + 1] = copy_seg(colr, p.col_r8, (C::kF + 15) & ~15);
+    copy_segments(seg, ns + 2);
+  }
+  __syncthreads();
   // bin Nz (Nyquist) of frame q: the pad slot behind the row where rows are padded, else behind the last row
   auto nyq = [](int q) { return C::kZS > C::kNz ? q * C::kZS + C::kNz : C::kQ * C::kZS + q; };
   static_assert(C::kZS > C::kNz || C::kQ * C::kZS + C::kQ <= C::kBufF2, "no room for the Nyquist bins");
@@ -306,26 +329,44 @@ __device__ __forceinline__ void mstft_bwd_body(const PlanDev& p, const MstftBwdA
 #pragma unroll 1
       for (int q = 0; q < C::kQ; ++q) {
         float2* zq = buf + q * C::kZS;
-#pragma unroll 2
+#pragma unroll kMstftUnroll
         for (int i = 0; i < C::kPairIters; ++i) {
           const int k = lane + 32 * i;
           const int km = (C::kNz - k) & (C::kNz - 1);
           float2 Ak, Am;
           split_fwd(zq[k], zq[km], sm.ws[k], Ak, Am);
           const float2 xk = rot_fwd(Ak, rk), xm = rot_fwd(Am, rm);
-          zq[k] = xk;
-          if (k != 0) zq[km] = xm;
-          else buf[nyq(q)] = xm;
+          if (FUSED && side == 0) {   // the real signal: only |X + 1e-9| is needed (the Nyquist bin carries no mel weight)
+            const float rek = xk.x + 1e-9f, rem = xm.x + 1e-9f;
+            zq[k].x = fast_sqrt(fmaf(rek, rek, xk.y * xk.y));
+            if (k != 0) zq[km].x = fast_sqrt(fmaf(rem, rem, xm.y * xm.y));
+          } else {
+            zq[k] = xk;
+            if (k != 0) zq[km] = xm;
+            else buf[nyq(q)] = xm;
+          }
         }
         if (lane == 0) {
           constexpr int k = C::kNz / 2;
           float2 Ak, Am;
           split_fwd(zq[k], zq[k], sm.ws[k], Ak, Am);
-          zq[k] = rot_fwd(Ak, k);
+          const float2 xk = rot_fwd(Ak, k);
+          if (FUSED && side == 0) {
+            const float rek = xk.x + 1e-9f;
+            zq[k].x = fast_sqrt(fmaf(rek, rek, xk.y * xk.y));
+          } else {
+            zq[k] = xk;
+          }
         }
       }
       __syncwarp();
-      // side 0: mel of the real signal; side 1: mel of the generated signal -> gradient of the loss w.r.t. each mel row
+      // side 0: mel of the real signal from the stored magnitudes (one square root per bin instead of one per filter tap)
+      if (FUSED && side == 0) {
+        mel_project_smem<N>(p, sm.melw, sm.mel_lo, buf, lane, [&](int q, int rd, int, float val) { mr[rd][q] = val; });
+        __syncwarp();
+        continue;
+      }
+      // side 1: mel of the generated signal -> gradient of the loss w.r.t. each mel row
       mel_project_cplx<N>(p, sm.melw, sm.mel_lo, buf, lane, [&](int q, int rd, int m, float mg) {
 #pragma unroll
         for (int r2 = 0; r2 < kMaxMelRounds; ++r2) {
@@ -345,7 +386,7 @@ __device__ __forceinline__ void mstft_bwd_body(const PlanDev& p, const MstftBwdA
                 r = __ldg(a.mel_r + (it.frame_base + it.t0 + q) * p.n_mel + m);
               }
               const float sgn = (mg > r) ? 1.f : ((mg < r) ? -1.f : 0.f);
-              g = gl * (sgn + sgn / mg);
+              g = gl * (sgn + __fdividef(sgn, mg));
             }
             gm[r2][q] = g;
           }
@@ -370,7 +411,7 @@ __device__ __forceinline__ void mstft_bwd_body(const PlanDev& p, const MstftBwdA
       float2 G = make_float2(0.f, 0.f);
       if (t < it.T) {
         const float re = X.x + 1e-9f;
-        const float S = sqrtf(fmaf(re, re, X.y * X.y));
+        const float S = fast_sqrt(fmaf(re, re, X.y * X.y));
         float gS = fmaf(c0, gmbuf[q * 128 + r0], c1 * gmbuf[q * 128 + r0 + 1]);
         float gP = 0.f;
         if (a.raw) {
@@ -379,11 +420,13 @@ __device__ __forceinline__ void mstft_bwd_body(const PlanDev& p, const MstftBwdA
           if (a.g_p_raw) gP = __ldg(a.g_p_raw + idx);
         } else if (a.g_spec) {
           const long long idx = (static_cast<long long>(it.b) * 2 * a.Tf + t) * C::kF + k;
-          if (!a.phd_phase) gS += __ldg(a.g_spec + idx) / S;
-          gP = __ldg(a.g_spec + idx + chs) / kRefPI;
+          if (!a.phd_phase) gS += __fdividef(__ldg(a.g_spec + idx), S);
+          gP = __ldg(a.g_spec + idx + chs) * (1.f / kRefPI);
         }
         const float d2 = fmaf(X.x, X.x, X.y * X.y);
-        const float gs = S > 0.f ? gS / S : 0.f, gp = d2 > 0.f ? gP / d2 : 0.f;   // abs / angle backward are 0 at 0
+        // abs / angle backward are 0 at 0.  div.approx (2 ulp) instead of the IEEE division: its slow-path subroutine was 10 % of
+        // the warp time, and the gradient tolerance is 1e-4
+        const float gs = S > 0.f ? __fdividef(gS, S) : 0.f, gp = d2 > 0.f ? __fdividef(gP, d2) : 0.f;
         // gS (X + 1e-9)/S + gP i X / |X|^2
         G = make_float2(half * fmaf(gs, re, -gp * X.y), half * fmaf(gs, X.y, gp * X.x));
       }
@@ -393,16 +436,15 @@ __device__ __forceinline__ void mstft_bwd_body(const PlanDev& p, const MstftBwdA
 #pragma unroll 1
     for (int q = 0; q < C::kQ; ++q) {
       float2* zq = buf + q * C::kZS;
-#pragma unroll 2
+#pragma unroll kMstftUnroll
       for (int i = 0; i < C::kPairIters; ++i) {
         const int k = lane + 32 * i;
         const int km = (C::kNz - k) & (C::kNz - 1);
         const float half = k == 0 ? 1.f : 0.5f;
-        const int r0k = __ldg(p.col_r0 + k), r0m = __ldg(p.col_r0 + C::kNz - k);
-        const float c0k = __ldg(p.col_c0 + k), c1k = __ldg(p.col_c1 + k);
-        const float c0m = __ldg(p.col_c0 + C::kNz - k), c1m = __ldg(p.col_c1 + C::kNz - k);
-        const float2 Gk = grad_bin(zq[k], q, k, half, r0k, c0k, c1k);
-        const float2 Gm = grad_bin(k != 0 ? zq[km] : buf[nyq(q)], q, C::kNz - k, half, r0m, c0m, c1m);
+        const int r0k = colr[k], r0m = colr[C::kNz - k];
+        const float2 ck = colc[k], cm = colc[C::kNz - k];
+        const float2 Gk = grad_bin(zq[k], q, k, half, r0k, ck.x, ck.y);
+        const float2 Gm = grad_bin(k != 0 ? zq[km] : buf[nyq(q)], q, C::kNz - k, half, r0m, cm.x, cm.y);
         float2 Bk = rot_inv(Gk, rk), Bm = rot_inv(Gm, rm);
         if (k == 0) { Bk.y = 0.f; Bm.y = 0.f; }
         float2 Zk, Zr;
@@ -412,7 +454,7 @@ __device__ __forceinline__ void mstft_bwd_body(const PlanDev& p, const MstftBwdA
       }
       if (lane == 0) {
         constexpr int k = C::kNz / 2;
-        const float2 B = rot_inv(grad_bin(zq[k], q, k, 0.5f, __ldg(p.col_r0 + k), __ldg(p.col_c0 + k), __ldg(p.col_c1 + k)), k);
+        const float2 B = rot_inv(grad_bin(zq[k], q, k, 0.5f, colr[k], colc[k].x, colc[k].y), k);
         float2 Zk, Zr;
         split_inv(B, B, sm.ws[k], Zk, Zr);
         zq[k] = Zk;
@@ -486,11 +528,31 @@ __device__ __forceinline__ float4 grad_ola_quad(const GradOlaArgs& a, int b, lon
     const float* fb = a.gfb[r] + static_cast<long long>(b) * Tf * win;
     const long long pp = N / 4 + j0;                         // (h + j0) - N/4
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int tp = static_cast<int>(min(static_cast<long long>(Tf - 1), pp / hop)); tp >= 0; --tp) {
-      const long long off = pp - static_cast<long long>(tp) * hop;
-      if (off >= win) break;
-      const float4 v = *reinterpret_cast<const float4*>(fb + static_cast<long long>(tp) * win + off);
-      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    // frames tp_lo .. tp_hi cover the position (offset pp - tp hop in [0, win)); their loads are issued together, six at a time
+    // (win / hop <= 5 at the reference's resolutions), and summed in the order of the rolled loop
+    int tp_hi, tp_lo;
+    if (pp < (1LL << 30)) {   // 32-bit divisions (the 64-bit one is a subroutine)
+      const int q = static_cast<int>(pp);
+      tp_hi = min(Tf - 1, q / hop);
+      tp_lo = q < win ? 0 : (q - win) / hop + 1;
+    } else {
+      tp_hi = static_cast<int>(min(static_cast<long long>(Tf - 1), pp / hop));
+      tp_lo = static_cast<int>((pp - win) / hop) + 1;
+    }
+    constexpr int kFrames = 6;
+    for (int t1 = tp_hi; t1 >= tp_lo; t1 -= kFrames) {
+      float4 v[kFrames];
+#pragma unroll
+      for (int j = 0; j < kFrames; ++j) {
+        const int tp = t1 - j;
+        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tp >= tp_lo)
+          v[j] = *reinterpret_cast<const float4*>(fb + static_cast<long long>(tp) * win + (pp - static_cast<long long>(tp) * hop));
+      }
+#pragma unroll
+      for (int j = 0; j < kFrames; ++j) {
+        if (t1 - j >= tp_lo) { s.x += v[j].x; s.y += v[j].y; s.z += v[j].z; s.w += v[j].w; }
+      }
     }
     acc.x += s.x; acc.y += s.y; acc.z += s.z; acc.w += s.w;
   }

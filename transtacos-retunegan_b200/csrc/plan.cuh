@@ -60,6 +60,10 @@ struct PlanDev {
   const int* col_r0;      // [F]
   const float* col_c0;    // [F]
   const float* col_c1;    // [F]
+  // the same view packed for shared memory (mstft backward): {c0, c1} per bin, padded to an even count, and r0 as one byte per bin,
+  // padded to a multiple of 16 (n_mel <= 128)
+  const float2* col_c01;  // [(F + 1) & ~1]
+  const unsigned char* col_r8;   // [(F + 15) & ~15]
   // pseudo-inverse ("linear") basis of transtacos/audio.py:167-175: lin[k, m] = basis[m, k] * dinv[m] with
   // dinv = 1 / column sums of basis basis^T; in the column view: lin[k, r0[k]] = lin_c0[k], lin[k, r0[k]+1] = lin_c1[k]
   const float* lin_c0;    // [F]
@@ -392,6 +396,12 @@ inline std::string build_plan(const sb200_config& c, sb200_plan* p, int* st) {
       c1[k] = (r0[k] + 1 < c.n_mel) ? mb[static_cast<size_t>(r0[k] + 1) * F + k] : 0.f;
     }
   }
+  std::vector<float2> c01((F + 1) & ~1, make_float2(0.f, 0.f));
+  std::vector<unsigned char> r8((F + 15) & ~15, 0);
+  for (int k = 0; k < F; ++k) {
+    c01[k] = make_float2(c0[k], c1[k]);
+    r8[k] = static_cast<unsigned char>(r0[k]);
+  }
   // _get_linear_basis: p = m m^T (float32 like np.matmul on the float32 basis), d = 1 / column sums where |x| > 1e-8
   std::vector<float> lc0(F, 0.f), lc1(F, 0.f);
   {
@@ -416,7 +426,7 @@ inline std::string build_plan(const sb200_config& c, sb200_plan* p, int* st) {
   if ((e = upload(p, vec, &d.field)) != cudaSuccess) return std::string("cuda upload: ") + cudaGetErrorString(e);
   SB200_UP(wf, window) SB200_UP(wout, wout) SB200_UP(wnorm, wnorm) SB200_UP(wsq, wsq) SB200_UP(wedge, wedge) SB200_UP(tw, tw) SB200_UP(ws, ws) SB200_UP(sp2, sp2) SB200_UP(spn, spn)
   SB200_UP(seg_slot, seg_slot) SB200_UP(seg_coef, seg_coef) SB200_UP(enorm, mel_enorm)
-  SB200_UP(melw, melw) SB200_UP(slots, mel_lo) SB200_UP(r0, col_r0) SB200_UP(c0, col_c0) SB200_UP(c1, col_c1) SB200_UP(lc0, lin_c0) SB200_UP(lc1, lin_c1)
+  SB200_UP(melw, melw) SB200_UP(slots, mel_lo) SB200_UP(r0, col_r0) SB200_UP(c0, col_c0) SB200_UP(c1, col_c1) SB200_UP(lc0, lin_c0) SB200_UP(lc1, lin_c1) SB200_UP(c01, col_c01) SB200_UP(r8, col_r8)
 #undef SB200_UP
   *st = SB200_OK;
   return "";
