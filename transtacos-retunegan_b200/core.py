@@ -25,10 +25,28 @@ _plans = {}
 _plans_lock = threading.Lock()
 
 
+_cuda_ok = False
+_devices = {}
+
+
 def require_cuda() -> torch.device:
-    if not torch.cuda.is_available():
-        raise RuntimeError("transtacos-retunegan_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
-    return torch.device("cuda", torch.cuda.current_device())
+    """The current CUDA device.  (`torch.cuda.is_available()` is asked until it first says yes, and the `torch.device` objects are
+    kept: on the host-bound training step these two calls were a tenth of the host time.)"""
+    global _cuda_ok
+    if not _cuda_ok:
+        if not torch.cuda.is_available():
+            raise RuntimeError("transtacos-retunegan_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        _cuda_ok = True
+    i = torch.cuda.current_device()
+    d = _devices.get(i)
+    if d is None:
+        d = _devices[i] = torch.device("cuda", i)
+    return d
+
+
+def raw_stream(device_index: int) -> int:
+    """cudaStream_t of torch's current stream on that device as an integer (no Stream object is built)."""
+    return torch._C._cuda_getCurrentRawStream(device_index)
 
 
 class Plan:
@@ -79,7 +97,7 @@ def get_plan(cfg: SpectralConfig, n_fft=None, win_length=None, hop_length=None, 
 
 
 def stream_ptr() -> C.c_void_p:
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(raw_stream(torch.cuda.current_device()))
 
 
 def ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
@@ -355,7 +373,7 @@ def _workspace(nbytes: int, device, tag: str) -> torch.Tensor:
     cache = getattr(_tls, "ws", None)
     if cache is None:
         cache = _tls.ws = {}
-    key = (device.index, int(torch.cuda.current_stream(device).cuda_stream), tag)
+    key = (device.index, raw_stream(device.index), tag)
     buf = cache.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(int(nbytes), device=device, dtype=torch.uint8)

@@ -26,6 +26,28 @@ constexpr int kMaxRes = 4;
 #endif
 constexpr int kMstftUnroll = SB200_MSTFT_UNROLL;
 
+// atan2f to ~3e-7 rad: octant reduction with one approximate division, degree-7 minimax polynomial in a^2 (fitted in double,
+// evaluated in float: max error 1.4e-7 on [0, 1]), same results as atan2f at the axes and for signed zeros.  The library atan2f
+// (IEEE division with a slow path) and logf were a seventh of the forward kernel's instructions at two calls per bin.
+__device__ __forceinline__ float fast_atan2(float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  const float a = mx > 0.f ? __fdividef(mn, mx) : 0.f;
+  const float s = a * a;
+  float r = -0.0040545654483139515f;
+  r = fmaf(r, s, 0.021862952038645744f);
+  r = fmaf(r, s, -0.0559123195707798f);
+  r = fmaf(r, s, 0.0964219719171524f);
+  r = fmaf(r, s, -0.1390862911939621f);
+  r = fmaf(r, s, 0.19946566224098206f);
+  r = fmaf(r, s, -0.33329859375953674f);
+  r = fmaf(r, s, 0.9999993443489075f);
+  r *= a;
+  if (ay > ax) r = 1.57079632679489662f - r;
+  if (__float_as_int(x) < 0) r = 3.14159265358979324f - r;   // sign bit: atan2f(+-0, -0) = +-pi
+  return copysignf(r, y);
+}
+
 struct MstftFwdArgs {
   const float* y;
   const float* yg;
@@ -56,9 +78,9 @@ __device__ __forceinline__ void mstft_analyse(const PlanDev& p, const SmemTables
       float2* zq = buf + q * C::kZS;
       const long long row = row0 + static_cast<long long>(q) * C::kF;
       auto emit = [&](float2 X, int k, float S) {
-        if (ch0) ch0[row + k] = RAW ? S : logf(S);
-        if (ch0_alias) ch0_alias[row + k] = logf(S);
-        if (ch1) ch1[row + ch_stride + k] = RAW ? atan2f(X.y, X.x) : atan2f(X.y, X.x) / kRefPI;
+        if (ch0) ch0[row + k] = RAW ? S : __logf(S);
+        if (ch0_alias) ch0_alias[row + k] = __logf(S);
+        if (ch1) ch1[row + ch_stride + k] = RAW ? fast_atan2(X.y, X.x) : fast_atan2(X.y, X.x) * (1.f / kRefPI);
       };
 #pragma unroll 2
       for (int i = 0; i < C::kPairIters; ++i) {
@@ -194,25 +216,34 @@ struct MstftFinArgs {
   float inv_count[kMaxRes];   // 1 / (B * n_mel * Tf)
   float* loss;
 };
-// loss = 1/n_res * sum_res (sum of partials) / count   (F.l1_loss reduction='mean', loss.py:51-54); one CTA, fixed order
+// loss = 1/n_res * sum_res (sum of partials) / count   (F.l1_loss reduction='mean', loss.py:51-54); one CTA, fixed order:
+// thread i sums partials i, i + blockDim, ... of every resolution (all loads independent), warps reduce by shuffle, thread 0 adds
+// the warp sums in warp order.  One barrier.
 __device__ __forceinline__ void mstft_finalize_body(const MstftFinArgs& a) {
-  __shared__ float red[32];
-  float total = 0.f;
-  for (int r = 0; r < a.n_res; ++r) {
-    float s = 0.f;
-    for (int i = threadIdx.x; i < a.n_partials[r]; i += blockDim.x) s += __ldcg(a.partials[r] + i);
+  __shared__ float red[kMaxRes][32];
+  float s[kMaxRes];
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(kFullMask, s, d);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
+  for (int r = 0; r < kMaxRes; ++r) {
+    s[r] = 0.f;
+    if (r < a.n_res)
+      for (int i = threadIdx.x; i < a.n_partials[r]; i += blockDim.x) s[r] += __ldcg(a.partials[r] + i);
+  }
+#pragma unroll
+  for (int r = 0; r < kMaxRes; ++r) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s[r] += __shfl_xor_sync(kFullMask, s[r], d);
+    if ((threadIdx.x & 31) == 0) red[r][threadIdx.x >> 5] = s[r];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float total = 0.f;
+    for (int r = 0; r < a.n_res; ++r) {
       float t = 0.f;
-      for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) t += red[w];
+      for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) t += red[r][w];
       total += t * a.inv_count[r];
     }
-    __syncthreads();
+    *a.loss = total / a.n_res;
   }
-  if (threadIdx.x == 0) *a.loss = total / a.n_res;
 }
 __global__ void mstft_finalize_kernel(const MstftFinArgs a) { mstft_finalize_body(a); }
 
@@ -403,58 +434,91 @@ __device__ __forceinline__ void mstft_bwd_body(const PlanDev& p, const MstftBwdA
         if (row < 128) gmbuf[q * 128 + row] = gm[rd][q];
       }
     __syncwarp();
-    // gD of one bin, scaled for the adjoint: interior bins / 2, DC and Nyquist real
-    // (r0, c0, c1): column view of the mel basis at bin k, loaded by the caller ahead of the branch (both bins of a pair at
-    // once: inside the conditional the two L2 round trips would be taken one after the other)
-    auto grad_bin = [&](float2 X, int q, int k, float half, int r0, float c0, float c1) -> float2 {
-      const long long t = it.t0 + q;
+    // gD of one bin, scaled for the adjoint: interior bins / 2, DC and Nyquist real.  (r0, c0, c1): column view of the mel basis at
+    // bin k; (us, up): upstream gradients of the bin's magnitude / phase outputs (not FUSED: spec stacks or get_stft_torch outputs).
+    const bool s_div = !a.raw;                              // spec stacks hold ln S: d ln S / dS = 1 / S
+    const float p_scale = a.raw ? 1.f : 1.f / kRefPI;       // and angle / PI
+    auto grad_bin = [&](float2 X, int q, float half, int r0, float c0, float c1, float us, float up) -> float2 {
       float2 G = make_float2(0.f, 0.f);
-      if (t < it.T) {
+      if (it.t0 + q < it.T) {
         const float re = X.x + 1e-9f;
         const float S = fast_sqrt(fmaf(re, re, X.y * X.y));
         float gS = fmaf(c0, gmbuf[q * 128 + r0], c1 * gmbuf[q * 128 + r0 + 1]);
         float gP = 0.f;
-        if (a.raw) {
-          const long long idx = (it.frame_base + t) * C::kF + k;
-          if (a.g_s_raw) gS += __ldg(a.g_s_raw + idx);
-          if (a.g_p_raw) gP = __ldg(a.g_p_raw + idx);
-        } else if (a.g_spec) {
-          const long long idx = (static_cast<long long>(it.b) * 2 * a.Tf + t) * C::kF + k;
-          if (!a.phd_phase) gS += __fdividef(__ldg(a.g_spec + idx), S);
-          gP = __ldg(a.g_spec + idx + chs) * (1.f / kRefPI);
+        if constexpr (!FUSED) {
+          gS += s_div ? __fdividef(us, S) : us;
+          gP = up * p_scale;
         }
         const float d2 = fmaf(X.x, X.x, X.y * X.y);
         // abs / angle backward are 0 at 0.  div.approx (2 ulp) instead of the IEEE division: its slow-path subroutine was 10 % of
         // the warp time, and the gradient tolerance is 1e-4
-        const float gs = S > 0.f ? __fdividef(gS, S) : 0.f, gp = d2 > 0.f ? __fdividef(gP, d2) : 0.f;
+        const float gs = S > 0.f ? __fdividef(gS, S) : 0.f, gp = (!FUSED && d2 > 0.f) ? __fdividef(gP, d2) : 0.f;
         // gS (X + 1e-9)/S + gP i X / |X|^2
         G = make_float2(half * fmaf(gs, re, -gp * X.y), half * fmaf(gs, X.y, gp * X.x));
       }
       return G;
     };
-    // gradient of every Hermitian pair and inverse split, in place: X[k], X[Nz-k] -> Z'[k], Z'[Nz-k]
+    // upstream gradients of the pair (k, Nz - k), k = lane + 32 i, of frame q: loaded TWO iterations ahead of their use (they come
+    // from L2 / HBM, and inside the iteration their latency sat on the dependent chain of the pair)
+    struct Up { float sk, pk, sm, pm; };
+    auto load_up = [&](int q, int k) -> Up {
+      Up u{0.f, 0.f, 0.f, 0.f};
+      if constexpr (!FUSED) {
+        const long long t = it.t0 + q;
+        if (k < C::kNz && t < it.T) {
+          if (a.raw) {
+            const long long idx = (it.frame_base + t) * C::kF;
+            if (a.g_s_raw) { u.sk = __ldg(a.g_s_raw + idx + k); u.sm = __ldg(a.g_s_raw + idx + C::kNz - k); }
+            if (a.g_p_raw) { u.pk = __ldg(a.g_p_raw + idx + k); u.pm = __ldg(a.g_p_raw + idx + C::kNz - k); }
+          } else if (a.g_spec) {
+            const long long idx = (static_cast<long long>(it.b) * 2 * a.Tf + t) * C::kF;
+            if (!a.phd_phase) { u.sk = __ldg(a.g_spec + idx + k); u.sm = __ldg(a.g_spec + idx + C::kNz - k); }
+            u.pk = __ldg(a.g_spec + idx + chs + k);
+            u.pm = __ldg(a.g_spec + idx + chs + C::kNz - k);
+          }
+        }
+      }
+      return u;
+    };
+    // gradient of one Hermitian pair and inverse split, in place: X[k], X[Nz-k] -> Z'[k], Z'[Nz-k]
+    auto pair_iter = [&](float2* zq, int q, int i, const Up& u) {
+      const int k = lane + 32 * i;
+      const int km = (C::kNz - k) & (C::kNz - 1);
+      const float half = k == 0 ? 1.f : 0.5f;
+      const int r0k = colr[k], r0m = colr[C::kNz - k];
+      const float2 ck = colc[k], cm = colc[C::kNz - k];
+      const float2 Gk = grad_bin(zq[k], q, half, r0k, ck.x, ck.y, u.sk, u.pk);
+      const float2 Gm = grad_bin(k != 0 ? zq[km] : buf[nyq(q)], q, half, r0m, cm.x, cm.y, u.sm, u.pm);
+      float2 Bk = rot_inv(Gk, rk), Bm = rot_inv(Gm, rm);
+      if (k == 0) { Bk.y = 0.f; Bm.y = 0.f; }
+      float2 Zk, Zr;
+      split_inv(Bk, Bm, sm.ws[k], Zk, Zr);
+      if (k != 0) zq[km] = Zr;
+      zq[k] = Zk;
+    };
 #pragma unroll 1
     for (int q = 0; q < C::kQ; ++q) {
       float2* zq = buf + q * C::kZS;
+      if constexpr (FUSED) {
 #pragma unroll kMstftUnroll
-      for (int i = 0; i < C::kPairIters; ++i) {
-        const int k = lane + 32 * i;
-        const int km = (C::kNz - k) & (C::kNz - 1);
-        const float half = k == 0 ? 1.f : 0.5f;
-        const int r0k = colr[k], r0m = colr[C::kNz - k];
-        const float2 ck = colc[k], cm = colc[C::kNz - k];
-        const float2 Gk = grad_bin(zq[k], q, k, half, r0k, ck.x, ck.y);
-        const float2 Gm = grad_bin(k != 0 ? zq[km] : buf[nyq(q)], q, C::kNz - k, half, r0m, cm.x, cm.y);
-        float2 Bk = rot_inv(Gk, rk), Bm = rot_inv(Gm, rm);
-        if (k == 0) { Bk.y = 0.f; Bm.y = 0.f; }
-        float2 Zk, Zr;
-        split_inv(Bk, Bm, sm.ws[k], Zk, Zr);
-        if (k != 0) zq[km] = Zr;
-        zq[k] = Zk;
+        for (int i = 0; i < C::kPairIters; ++i) pair_iter(zq, q, i, Up{0.f, 0.f, 0.f, 0.f});
+      } else {
+        static_assert(C::kPairIters % 2 == 0, "pair loop is unrolled by two");
+        Up u0 = load_up(q, lane), u1 = load_up(q, lane + 32);
+#pragma unroll 1
+        for (int i = 0; i < C::kPairIters; i += 2) {
+          const Up n0 = load_up(q, lane + 32 * (i + 2) + (i + 2 < C::kPairIters ? 0 : C::kNz));
+          const Up n1 = load_up(q, lane + 32 * (i + 3) + (i + 3 < C::kPairIters ? 0 : C::kNz));
+          pair_iter(zq, q, i, u0);
+          pair_iter(zq, q, i + 1, u1);
+          u0 = n0;
+          u1 = n1;
+        }
       }
       if (lane == 0) {
         constexpr int k = C::kNz / 2;
-        const float2 B = rot_inv(grad_bin(zq[k], q, k, 0.5f, colr[k], colc[k].x, colc[k].y), k);
+        const Up u = load_up(q, k);   // the self pair: sm / pm address the same bin
+        const float2 B = rot_inv(grad_bin(zq[k], q, 0.5f, colr[k], colc[k].x, colc[k].y, u.sk, u.pk), k);
         float2 Zk, Zr;
         split_inv(B, B, sm.ws[k], Zk, Zr);
         zq[k] = Zk;
@@ -562,7 +626,13 @@ __device__ __forceinline__ float4 grad_ola_quad(const GradOlaArgs& a, int b, lon
 // One thread per 4 samples; block (0, 0) first reduces the loss partial sums when fin.loss is set (the loss-only step: saves the
 // separate one-block launch, which sat between the analysis kernels and this one).
 __global__ void __launch_bounds__(256) grad_ola_kernel(const GradOlaArgs a, const MstftFinArgs fin) {
-  if (fin.loss != nullptr && blockIdx.x == 0 && blockIdx.y == 0) mstft_finalize_body(fin);
+  // fin.loss set: the grid carries one extra column of blocks; the first of them reduces the loss partial sums and none of them
+  // takes overlap-add work (the reduction is a chain of dependent round trips: inside a working block it was the kernel's tail)
+  const int gx = static_cast<int>(gridDim.x) - (fin.loss != nullptr ? 1 : 0);
+  if (static_cast<int>(blockIdx.x) == gx) {
+    if (blockIdx.y == 0) mstft_finalize_body(fin);
+    return;
+  }
   const int b = blockIdx.y;
   int hmax = 0;
   bool vec = (a.T >= 8);
@@ -572,13 +642,60 @@ __global__ void __launch_bounds__(256) grad_ola_kernel(const GradOlaArgs a, cons
   }
   float* g = a.g + static_cast<long long>(b) * a.T;
   for (long long j0 = 4 * (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x); j0 < a.T;
-       j0 += 4 * static_cast<long long>(gridDim.x) * blockDim.x) {
+       j0 += 4 * static_cast<long long>(gx) * blockDim.x) {
     if (vec && j0 > hmax && j0 + 3 <= a.T - 2 - hmax) {
       const float4 v = grad_ola_quad(a, b, j0);
       g[j0] = v.x; g[j0 + 1] = v.y; g[j0 + 2] = v.z; g[j0 + 3] = v.w;
     } else {
       for (long long j = j0; j < min(j0 + 4, a.T); ++j) g[j] = grad_ola_sample<false>(a, b, j);
     }
+  }
+}
+
+// ---- all resolutions as ONE grid (default) ----------------------------------------------------------------------------------
+// The per-resolution kernels are each well under one wave of the GPU.  Running them on three streams costs a fork event, two
+// stream waits, two join events and two more waits per phase, and once the kernels themselves were tuned the eager training step
+// was bound by the host issuing those calls.  Here the grids are simply concatenated: CTA c belongs to the resolution whose
+// [cta_end[r - 1], cta_end[r]) range holds it and works exactly like CTA c - cta_end[r - 1] of that resolution's own kernel (one
+// pass per warp, same numbers bit for bit).  No cooperative launch, no grid barrier: the reduction / overlap-add stay a second launch.
+struct MstftMultiFwdArgs {
+  int n_res;
+  int cta_end[kMaxRes];
+  PlanDev plan[kMaxRes];
+  MstftFwdArgs f[kMaxRes];
+};
+struct MstftMultiBwdArgs {
+  int n_res;
+  int cta_end[kMaxRes];
+  PlanDev plan[kMaxRes];
+  MstftBwdArgs b[kMaxRes];
+};
+__device__ __forceinline__ void mstft_multi_locate(int n_res, const int* cta_end, int* r, int* vb, int* nvb) {
+  int i = 0, base = 0;
+  while (i + 1 < n_res && static_cast<int>(blockIdx.x) >= cta_end[i]) base = cta_end[i++];
+  *r = i;
+  *vb = static_cast<int>(blockIdx.x) - base;
+  *nvb = cta_end[i] - base;
+}
+__global__ void __launch_bounds__(kMstftWarps * 32, 2) mstft_multi_fwd_kernel(const __grid_constant__ MstftMultiFwdArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int r, vb, nvb;
+  mstft_multi_locate(A.n_res, A.cta_end, &r, &vb, &nvb);
+  switch (A.plan[r].n_fft) {
+    case 2048: mstft_fwd_body<2048>(A.plan[r], A.f[r], smem_raw, vb, nvb); break;
+    case 1024: mstft_fwd_body<1024>(A.plan[r], A.f[r], smem_raw, vb, nvb); break;
+    default: mstft_fwd_body<512>(A.plan[r], A.f[r], smem_raw, vb, nvb); break;
+  }
+}
+template <bool FUSED>
+__global__ void __launch_bounds__(kMstftWarps * 32, 2) mstft_multi_bwd_kernel(const __grid_constant__ MstftMultiBwdArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int r, vb, nvb;
+  mstft_multi_locate(A.n_res, A.cta_end, &r, &vb, &nvb);
+  switch (A.plan[r].n_fft) {
+    case 2048: mstft_bwd_body<2048, FUSED>(A.plan[r], A.b[r], smem_raw, vb, nvb); break;
+    case 1024: mstft_bwd_body<1024, FUSED>(A.plan[r], A.b[r], smem_raw, vb, nvb); break;
+    default: mstft_bwd_body<512, FUSED>(A.plan[r], A.b[r], smem_raw, vb, nvb); break;
   }
 }
 

@@ -110,6 +110,64 @@ static bool mstft_single_enabled() {
   return v != 0;
 }
 
+// SB200_MSTFT_STREAMS=1 selects round 1's formulation, one launch per resolution on library-owned side streams (fork / join
+// events): the kernels' own time is the same, the step pays nine more driver calls per phase (tools/ab_mstft.sh).
+static bool mstft_streams_enabled() {
+  static const int v = [] {
+    const char* e = std::getenv("SB200_MSTFT_STREAMS");
+    return e ? std::atoi(e) : 0;
+  }();
+  return v != 0;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per device and sticky: set it when a device first needs more than it has had
+// (a driver call per launch otherwise).  The race between two host threads is benign (both set the same value).
+static bool mstft_smem_grow(size_t (&have)[64], size_t smem) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  if (smem <= have[dev]) return false;
+  have[dev] = smem;
+  return true;
+}
+
+// Grids of the concatenated launch.  Every resolution gets ceil(sub-items / warps) CTAs: one pass per warp, 552 CTAs against 296
+// resident slots at the training size, packed by the hardware scheduler.  SB200_MSTFT_RESIDENT=1 scales the grids down to the
+// resident count instead and lets the CTAs loop (one table fill per CTA instead of two, second pass from a warm instruction
+// cache): measured SLOWER, 105 against 100 us of GPU time per loss-only step and 216 against 208 us with spec stacks
+// (tools/probe_mstft_graph.py, CUDA-graph replay) -- a warp's second pass starts only when its own first one ends, while a
+// fresh CTA starts as soon as any slot frees up.  Off by default.
+static void mstft_multi_grids(const long long* subs, int n_res, int resident, int* grid) {
+  static const int on = [] {
+    const char* e = std::getenv("SB200_MSTFT_RESIDENT");
+    return e ? std::atoi(e) : 0;
+  }();
+  long long need[kMaxRes], total = 0;
+  for (int r = 0; r < n_res; ++r) {
+    need[r] = (subs[r] + kMstftWarps - 1) / kMstftWarps;
+    total += need[r];
+  }
+  for (int r = 0; r < n_res; ++r) {
+    grid[r] = static_cast<int>(std::min<long long>(need[r], 2LL * sm_count()));
+    if (on && resident > 0 && total > resident)
+      grid[r] = static_cast<int>(std::max<long long>(1, std::min<long long>(need[r], need[r] * resident / total)));
+  }
+}
+template <class Kern>
+static int mstft_resident(Kern kern, size_t smem, int (&cache)[64]) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  if (cache[dev] == 0) {
+    int per_sm = 0;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kMstftWarps * 32, smem) != cudaSuccess) {
+      cudaGetLastError();
+      per_sm = 0;
+    }
+    cache[dev] = per_sm > 0 ? per_sm * sm_count() : -1;
+  }
+  return cache[dev] > 0 ? cache[dev] : 0;
+}
+
 static size_t mstft_all_smem(const sb200_plan* const* plans, int32_t n_res, bool bwd) {
   size_t smem = 0;
   for (int r = 0; r < n_res; ++r) {
@@ -272,6 +330,51 @@ int sb200_mstft_forward(const sb200_plan* const* plans, int32_t n_res, const flo
       return check_launch("mstft_all_fwd_kernel");
     }
   }
+  if (!mstft_streams_enabled()) {   // default: the resolutions' grids concatenated into one launch
+    MstftMultiFwdArgs A{};
+    MstftFinArgs fin{};
+    A.n_res = fin.n_res = n_res;
+    fin.loss = loss;
+    int total = 0;
+    long long subs[kMaxRes];
+    for (int r = 0; r < n_res; ++r) {
+      const sb200_plan* plan = plans[r];
+      MstftFwdArgs& a = A.f[r];
+      A.plan[r] = plan->dev;
+      a.y = y;
+      a.yg = y_g;
+      a.bd = mstft_batch(plan, B, T);
+      a.Tf = static_cast<int>(a.bd.frames_per_row);
+      a.spec_r = specs_r ? specs_r[r] : nullptr;
+      a.spec_g = specs_g ? specs_g[r] : nullptr;
+      a.phd_phase = phd_phase;
+      a.mel_r = reinterpret_cast<float*>(static_cast<char*>(saved) + mstft_saved_off(plans, r, B, T));
+      a.partials = reinterpret_cast<float*>(ws + part0 + r * mstft_partials_bytes());
+      a.want_loss = loss != nullptr;
+      subs[r] = 2 * a.bd.total_items;
+      fin.partials[r] = a.partials;
+      fin.inv_count[r] = static_cast<float>(1.0 / (static_cast<double>(B) * plan->cfg.n_mel * a.Tf));
+    }
+    const size_t smem = mstft_all_smem(plans, n_res, false);
+    static int resident[64] = {};
+    int grid[kMaxRes];
+    mstft_multi_grids(subs, n_res, mstft_resident(mstft_multi_fwd_kernel, smem, resident), grid);
+    for (int r = 0; r < n_res; ++r) {
+      total += grid[r];
+      A.cta_end[r] = total;
+      fin.n_partials[r] = grid[r] * kMstftWarps;
+    }
+    static size_t smem_set[64] = {};
+    if (mstft_smem_grow(smem_set, smem))
+      cudaFuncSetAttribute(mstft_multi_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    mstft_multi_fwd_kernel<<<total, kMstftWarps * 32, smem, st>>>(A);
+    if (int rc = check_launch("mstft_multi_fwd_kernel")) return rc;
+    if (loss) {
+      mstft_finalize_kernel<<<1, 256, 0, st>>>(fin);
+      if (int rc = check_launch("mstft_finalize_kernel")) return rc;
+    }
+    return SB200_OK;
+  }
   std::lock_guard<std::mutex> enqueue_lock(g_mstft_enqueue_mu);
   MstftFinArgs fin{};
   fin.n_res = n_res;
@@ -307,6 +410,69 @@ int sb200_mstft_forward(const sb200_plan* const* plans, int32_t n_res, const flo
   return SB200_OK;
 }
 
+// Backward (g_specs / g_loss) or fused loss + gradient of all resolutions as one concatenated grid, then the overlap-add (which
+// also reduces the loss partial sums when `loss` is set).
+static int mstft_multi_bwd(const sb200_plan* const* plans, int32_t n_res, const float* y, const float* y_g, int32_t B, int64_t T,
+                           int32_t phd_phase, const float* g_loss, const float* const* g_specs_g, const void* saved, float* loss,
+                           float* g_yg, char* ws, bool fused, cudaStream_t st) {
+  MstftMultiBwdArgs A{};
+  MstftFinArgs fin{};
+  GradOlaArgs o{};
+  A.n_res = fin.n_res = o.n_res = n_res;
+  fin.loss = loss;
+  o.B = B;
+  o.T = T;
+  o.g = g_yg;
+  const int64_t part0 = mstft_ws_gfb_off(plans, n_res, B, T);
+  int total = 0;
+  long long subs[kMaxRes];
+  for (int r = 0; r < n_res; ++r) {
+    const sb200_plan* plan = plans[r];
+    MstftBwdArgs& a = A.b[r];
+    A.plan[r] = plan->dev;
+    a.y = y;
+    a.yg = y_g;
+    a.bd = mstft_batch(plan, B, T);
+    a.Tf = static_cast<int>(a.bd.frames_per_row);
+    a.mel_r = saved ? reinterpret_cast<const float*>(static_cast<const char*>(saved) + mstft_saved_off(plans, r, B, T)) : nullptr;
+    a.g_loss = g_loss;
+    a.loss_scale = static_cast<float>(1.0 / (static_cast<double>(n_res) * B * plan->cfg.n_mel * a.Tf));
+    a.g_spec = g_specs_g ? g_specs_g[r] : nullptr;
+    a.phd_phase = phd_phase;
+    a.gfb = reinterpret_cast<float*>(ws + mstft_ws_gfb_off(plans, r, B, T));
+    a.partials = reinterpret_cast<float*>(ws + part0 + r * mstft_partials_bytes());
+    subs[r] = 2 * a.bd.total_items;
+    fin.partials[r] = a.partials;
+    fin.inv_count[r] = static_cast<float>(1.0 / (static_cast<double>(B) * plan->cfg.n_mel * a.Tf));
+    o.gfb[r] = a.gfb;
+    o.n_fft[r] = plan->cfg.n_fft;
+    o.hop[r] = plan->cfg.hop_length;
+    o.Tf[r] = a.Tf;
+  }
+  const size_t smem = mstft_all_smem(plans, n_res, true);
+  static int resident[2][64] = {};
+  int grid_r[kMaxRes];
+  mstft_multi_grids(subs, n_res,
+                    fused ? mstft_resident(mstft_multi_bwd_kernel<true>, smem, resident[1])
+                          : mstft_resident(mstft_multi_bwd_kernel<false>, smem, resident[0]), grid_r);
+  for (int r = 0; r < n_res; ++r) {
+    total += grid_r[r];
+    A.cta_end[r] = total;
+    fin.n_partials[r] = grid_r[r] * kMstftWarps;
+  }
+  static size_t smem_set[2][64] = {};
+  if (mstft_smem_grow(smem_set[fused], smem)) {
+    if (fused) cudaFuncSetAttribute(mstft_multi_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    else cudaFuncSetAttribute(mstft_multi_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  }
+  if (fused) mstft_multi_bwd_kernel<true><<<total, kMstftWarps * 32, smem, st>>>(A);
+  else mstft_multi_bwd_kernel<false><<<total, kMstftWarps * 32, smem, st>>>(A);
+  if (int rc = check_launch(fused ? "mstft_multi_bwd_kernel<fused>" : "mstft_multi_bwd_kernel")) return rc;
+  dim3 grid(grid_for((T + 3) / 4, 256, 2) + (loss ? 1 : 0), B);
+  grad_ola_kernel<<<grid, 256, 0, st>>>(o, loss ? fin : MstftFinArgs{});
+  return check_launch("grad_ola_kernel");
+}
+
 int sb200_mstft_backward(const sb200_plan* const* plans, int32_t n_res, const float* y_g, int32_t B, int64_t T,
                          int32_t phd_phase, const float* g_loss, const float* const* g_specs_g, const void* saved,
                          float* g_yg, void* workspace, sb200_stream stream) {
@@ -318,6 +484,8 @@ int sb200_mstft_backward(const sb200_plan* const* plans, int32_t n_res, const fl
     const int rc = mstft_all_bwd(plans, n_res, nullptr, y_g, B, T, phd_phase, g_loss, g_specs_g, saved, nullptr, g_yg, ws, false, st);
     if (rc <= 0) return rc;
   }
+  if (!mstft_streams_enabled())
+    return mstft_multi_bwd(plans, n_res, nullptr, y_g, B, T, phd_phase, g_loss, g_specs_g, saved, nullptr, g_yg, ws, false, st);
   std::lock_guard<std::mutex> enqueue_lock(g_mstft_enqueue_mu);
   GradOlaArgs o{};
   o.n_res = n_res;
@@ -366,6 +534,8 @@ int sb200_mstft_loss_and_grad(const sb200_plan* const* plans, int32_t n_res, con
     const int rc = mstft_all_bwd(plans, n_res, y, y_g, B, T, 0, nullptr, nullptr, nullptr, loss, grad_yg, ws, true, st);
     if (rc <= 0) return rc;
   }
+  if (!mstft_streams_enabled())
+    return mstft_multi_bwd(plans, n_res, y, y_g, B, T, 0, nullptr, nullptr, nullptr, loss, grad_yg, ws, true, st);
   std::lock_guard<std::mutex> enqueue_lock(g_mstft_enqueue_mu);
   const int64_t part0 = mstft_ws_gfb_off(plans, n_res, B, T);
   MstftFinArgs fin{};
@@ -401,8 +571,8 @@ int sb200_mstft_loss_and_grad(const sb200_plan* const* plans, int32_t n_res, con
     o.Tf[r] = a.Tf;
   }
   mstft_join(side, n_res, st);
-  dim3 grid(grid_for((T + 3) / 4, 256, 2), B);
-  grad_ola_kernel<<<grid, 256, 0, st>>>(o, fin);   // block (0, 0) also reduces the loss partial sums
+  dim3 grid(grid_for((T + 3) / 4, 256, 2) + 1, B);
+  grad_ola_kernel<<<grid, 256, 0, st>>>(o, fin);   // the extra block column reduces the loss partial sums
   return check_launch("grad_ola_kernel");
 }
 

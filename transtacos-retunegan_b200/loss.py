@@ -56,14 +56,25 @@ def _ptr_array(tensors):
     return arr
 
 
+def _as_rows(t: torch.Tensor, dev) -> torch.Tensor:
+    """[B, T] / [B, 1, T] (any device / float dtype) -> contiguous float32 [B, T] on `dev`, without touching a tensor that already
+    is one (the training step is bound by the host: every avoidable tensor op counts)."""
+    if t.dtype is not torch.float32 or t.device != dev or not t.is_contiguous():
+        t = t.detach().to(device=dev, dtype=torch.float32).contiguous()
+    return t
+
+
 class _MultiStftFn(torch.autograd.Function):
+    """y, y_g: [B, T] or [B, 1, T] (the reference squeezes the depth axis itself, loss.py:27-28; here the two extra views and the
+    backward node they add are skipped: the kernels only need the row pointer, B and T)."""
+
     @staticmethod
     def forward(ctx, y, y_g, cfg: SpectralConfig, want_loss: bool, want_specs: bool):
         lib = _lib.load()
         dev = core.require_cuda()
-        yc = y.detach().to(device=dev, dtype=torch.float32).contiguous()
-        gc = y_g.detach().to(device=dev, dtype=torch.float32).contiguous()
-        B, T = gc.shape
+        yc = _as_rows(y, dev)
+        gc = _as_rows(y_g, dev)
+        B, T = gc.shape[0], gc.shape[-1]
         plans, handles, saved_bytes, ws_bytes = _setup(cfg, dev, B, T)
         n_res = len(plans)
         ctx.fused = bool(want_loss and not want_specs and ctx.needs_input_grad[1])
@@ -106,8 +117,11 @@ class _MultiStftFn(torch.autograd.Function):
     def backward(ctx, *grads):
         if ctx.fused:
             (grad,) = ctx.saved_tensors
-            g = grads[0].to(device=grad.device, dtype=torch.float32) * grad
-            return None, g.to(ctx.in_dtype).reshape(ctx.in_shape), None, None, None
+            g0 = grads[0]
+            if g0.dtype is not torch.float32 or g0.device != grad.device:
+                g0 = g0.to(device=grad.device, dtype=torch.float32)
+            g = (g0 * grad).view(ctx.in_shape)
+            return None, (g if ctx.in_dtype is torch.float32 else g.to(ctx.in_dtype)), None, None, None
         lib = _lib.load()
         gc, saved = ctx.saved_tensors
         B, T = ctx.shape
@@ -130,7 +144,8 @@ class _MultiStftFn(torch.autograd.Function):
         _lib.check(lib.sb200_mstft_backward(ctx.handles, n_res, core.ptr(gc), B, T, ctx.phd_phase, core.ptr(g_loss),
                                             _ptr_array(g_specs) if g_specs is not None else None, core.ptr(saved),
                                             core.ptr(g_yg), core.ptr(ws), core.stream_ptr()), "mstft_backward")
-        return None, g_yg.to(ctx.in_dtype).reshape(ctx.in_shape), None, None, None
+        g_yg = g_yg.view(ctx.in_shape)
+        return None, (g_yg if ctx.in_dtype is torch.float32 else g_yg.to(ctx.in_dtype)), None, None, None
 
 
 class _GlobalMean(torch.autograd.Function):
@@ -154,9 +169,7 @@ def multi_stft_loss(y, y_g, ret_loss=False, ret_specs=False, ddp_reduce=False):
         raise RuntimeError("multi_stft_loss: neither ret_loss nor ret_specs")   # bare `raise` at loss.py:62
     if hp.phd_input not in ("stft", "phase"):
         raise RuntimeError(f"unknown phd_input {hp.phd_input!r}")               # bare `raise` at loss.py:48
-    if y.dim() == 3:                                                            # [B, 1, T] => [B, T]
-        y, y_g = y.squeeze(1), y_g.squeeze(1)
-    if y.shape != y_g.shape or y.dim() != 2:
+    if y.shape != y_g.shape or not (y.dim() == 2 or (y.dim() == 3 and y.shape[1] == 1)):   # [B, 1, T] is taken as [B, T]
         raise ValueError(f"expected matching [B, T] / [B, 1, T] inputs, got {tuple(y.shape)} and {tuple(y_g.shape)}")
     outs = _MultiStftFn.apply(y, y_g, hp, bool(ret_loss), bool(ret_specs))
     n_res = len(hp.multi_stft_params)
