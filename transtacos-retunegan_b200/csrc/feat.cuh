@@ -122,6 +122,48 @@ __device__ __forceinline__ void copy_segments(const CopySeg (&seg)[NS], int ns) 
   }
 }
 
+// The same fill without blocking: cp.async (LDGSTS) copies the chunks of segments [s0, s1) straight into shared memory and the
+// thread's copies arrive on an mbarrier (initialised with one arrival per thread of the CTA) when they have landed.  A warp waits on
+// the barrier of a table group where it first needs one of its tables (tbl_wait), so the fill runs under whatever comes before:
+// the window / twiddle group under the item decode, everything else under the frame gather and the first FFT.
+__device__ __forceinline__ unsigned tbl_smem_addr(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void tbl_bar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tbl_smem_addr(bar)), "r"(count) : "memory");
+}
+template <int NS>
+__device__ __forceinline__ void copy_segments_async(const CopySeg (&seg)[NS], int s0, int s1, unsigned long long* bar) {
+  int total = 0;
+#pragma unroll
+  for (int s = 0; s < NS; ++s) total += (s >= s0 && s < s1) ? seg[s].n16 : 0;
+  for (int i0 = threadIdx.x; i0 < total; i0 += blockDim.x) {
+    int i = i0;
+    bool done = false;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      if (s >= s0 && s < s1 && !done) {
+        if (i < seg[s].n16) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tbl_smem_addr(seg[s].dst + i)), "l"(seg[s].src + i) : "memory");
+          done = true;
+        } else {
+          i -= seg[s].n16;
+        }
+      }
+    }
+  }
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tbl_smem_addr(bar)) : "memory");
+}
+// wait for phase 0 of the barrier (returns at once when it has completed: the barrier is used for one fill per CTA)
+__device__ __forceinline__ void tbl_wait(unsigned long long* bar) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "TBL_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+      "@p bra TBL_DONE;\n\t"
+      "bra TBL_WAIT;\n\t"
+      "TBL_DONE:\n\t}" ::"r"(tbl_smem_addr(bar))
+      : "memory");
+}
+
 // Shared-memory table block common to all FFT kernels.
 template <int N>
 struct SmemTables {
@@ -251,13 +293,34 @@ __device__ __forceinline__ void mel_project_smem(const PlanDev& p, const float* 
 // (ld.global.cg), never through the non-coherent L1 / read-only path.
 template <bool L2 = false>
 __device__ __forceinline__ float ola_gather(const float* __restrict__ fb, int n_frames, int hop, int win, long long pp) {
-  int tp = static_cast<int>(min(static_cast<long long>(n_frames - 1), pp / hop));
+  // frames tp_lo .. tp_hi cover the position (offset pp - tp hop in [0, win)).  Their loads are issued together, six at a time, and
+  // summed from the last frame backwards (as a rolled loop with an early exit the loads went out one by one: the border
+  // samples of the gradient overlap-add, which take this path, were the tail of that launch)
+  int tp_hi, tp_lo;
+  if (pp < (1LL << 30)) {   // 32-bit divisions (the 64-bit one is a subroutine)
+    const int q = static_cast<int>(pp);
+    tp_hi = min(n_frames - 1, q / hop);
+    tp_lo = q < win ? 0 : (q - win) / hop + 1;
+  } else {
+    tp_hi = static_cast<int>(min(static_cast<long long>(n_frames - 1), pp / hop));
+    tp_lo = static_cast<int>((pp - win) / hop) + 1;
+  }
   float acc = 0.f;
-  for (; tp >= 0; --tp) {
-    const long long off = pp - static_cast<long long>(tp) * hop;
-    if (off >= win) break;
-    const float* q = fb + static_cast<long long>(tp) * win + off;
-    acc += L2 ? __ldcg(q) : *q;
+  constexpr int kFrames = 6;
+  for (int t1 = tp_hi; t1 >= tp_lo; t1 -= kFrames) {
+    float v[kFrames];
+#pragma unroll
+    for (int j = 0; j < kFrames; ++j) {
+      const int tp = t1 - j;
+      v[j] = 0.f;
+      if (tp >= tp_lo) {
+        const float* q = fb + static_cast<long long>(tp) * win + (pp - static_cast<long long>(tp) * hop);
+        v[j] = L2 ? __ldcg(q) : *q;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kFrames; ++j)
+      if (t1 - j >= tp_lo) acc += v[j];
   }
   return acc;
 }

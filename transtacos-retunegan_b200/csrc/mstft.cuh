@@ -66,11 +66,14 @@ template <int N, bool RAW = false>
 __device__ __forceinline__ void mstft_analyse(const PlanDev& p, const SmemTables<N>& sm, float2* buf, float2 (&v)[32],
                                               const float* x, long long L, int t0, int T, int lane, float* ch0,
                                               float* ch0_alias, float* ch1, long long row0 /* (b*2*Tf + t0) * F */,
-                                              long long ch_stride /* Tf*F */) {
+                                              long long ch_stride /* Tf*F */, unsigned long long* tbl_bar = nullptr) {
   // analysis of Q frames; leaves S = |D + 1e-9| in buf[q*ZS + k].x; optionally writes ln S (ch0, ch0_alias) and angle/PI (ch1)
+  // tbl_bar: barriers of an asynchronous table fill ([0] window + FFT twiddles, [1] the rest), waited on at first use
   using C = FftCfg<N>;
+  if (tbl_bar) tbl_wait(tbl_bar);
   load_frames<N, false>(v, x, L, t0, T, p.hop, 0.f, sm.win, lane);
   fft_forward<N>(v, buf, sm.tw, lane);
+  if (tbl_bar) tbl_wait(tbl_bar + 1);
   const int rk = lane & 3, rm = (4 - rk) & 3;
   static_for<0, C::kQ>([&](auto qc) {
     constexpr int q = decltype(qc)::value;
@@ -118,11 +121,18 @@ __device__ __forceinline__ void mstft_fwd_body(const PlanDev& p, const MstftFwdA
   using C = FftCfg<N>;
   SmemTables<N> sm;
   sm.carve(smem_raw, p);
-  {
-    CopySeg seg[5];
-    copy_segments(seg, sm.segments(p, p.window, true, seg));
+  __shared__ unsigned long long tbl_bar[2];   // [0] window + FFT twiddles, [1] split twiddles + mel tables
+  if (threadIdx.x == 0) {
+    tbl_bar_init(tbl_bar, blockDim.x);
+    tbl_bar_init(tbl_bar + 1, blockDim.x);
   }
   __syncthreads();
+  {
+    CopySeg seg[5];
+    const int ns = sm.segments(p, p.window, true, seg);
+    copy_segments_async(seg, 0, 2, tbl_bar);
+    copy_segments_async(seg, 2, ns, tbl_bar + 1);
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float2* buf = sm.bufs + warp * C::kBufF2;
   float acc = 0.f;
@@ -144,7 +154,7 @@ __device__ __forceinline__ void mstft_fwd_body(const PlanDev& p, const MstftFwdA
       float* ch0 = side ? (a.phd_phase ? nullptr : a.spec_g) : a.spec_r;
       float* ch0_alias = side ? nullptr : (a.phd_phase ? a.spec_g : nullptr);
       float* ch1 = side ? a.spec_g : a.spec_r;
-      mstft_analyse<N>(p, sm, buf, v, x + it.sig_base, it.L, it.t0, it.T, lane, ch0, ch0_alias, ch1, row0, chs);
+      mstft_analyse<N>(p, sm, buf, v, x + it.sig_base, it.L, it.t0, it.T, lane, ch0, ch0_alias, ch1, row0, chs, tbl_bar);
       mel_project_smem<N>(p, sm.melw, sm.mel_lo, buf, lane, [&](int q, int rd, int m, float val) {
         if (side == 0) {
           mr[rd][q] = val;
@@ -161,6 +171,7 @@ __device__ __forceinline__ void mstft_fwd_body(const PlanDev& p, const MstftFwdA
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(kFullMask, acc, d);
   if (lane == 0) a.partials[vb * kMstftWarps + warp] = acc;
+  asm volatile("cp.async.wait_all;" ::: "memory");   // a warp without an item never waited: its copies land before it exits
 }
 
 template <int N>
@@ -323,14 +334,20 @@ __device__ __forceinline__ void mstft_bwd_body(const PlanDev& p, const MstftBwdA
   // pair loop it was the largest stall of the kernel (long scoreboard, 20 % of the warp time).
   float2* colc = reinterpret_cast<float2*>(reinterpret_cast<float*>(sm.bufs + kMstftWarps * C::kBufF2) + kMstftWarps * C::kQ * 128);
   unsigned char* colr = reinterpret_cast<unsigned char*>(colc + ((C::kF + 1) & ~1));
+  __shared__ unsigned long long tbl_bar[2];   // [0] window + FFT twiddles, [1] split twiddles + mel tables (asynchronous fill)
+  if (threadIdx.x == 0) {
+    tbl_bar_init(tbl_bar, blockDim.x);
+    tbl_bar_init(tbl_bar + 1, blockDim.x);
+  }
+  __syncthreads();
   {
     CopySeg seg[7];
     const int ns = sm.segments(p, p.window, true, seg);
     seg[ns] = copy_seg(colc, p.col_c01, (C::kF + 1) & ~1);
     seg[ns + 1] = copy_seg(colr, p.col_r8, (C::kF + 15) & ~15);
-    copy_segments(seg, ns + 2);
+    copy_segments_async(seg, 0, 2, tbl_bar);
+    copy_segments_async(seg, 2, ns + 2, tbl_bar + 1);
   }
-  __syncthreads();
   // bin Nz (Nyquist) of frame q: the pad slot behind the row where rows are padded, else behind the last row
   auto nyq = [](int q) { return C::kZS > C::kNz ? q * C::kZS + C::kNz : C::kQ * C::kZS + q; };
   static_assert(C::kZS > C::kNz || C::kQ * C::kZS + C::kQ <= C::kBufF2, "no room for the Nyquist bins");
@@ -354,8 +371,10 @@ __device__ __forceinline__ void mstft_bwd_body(const PlanDev& p, const MstftBwdA
     // analysis code.  Not fused: side 1 only.
 #pragma unroll 1
     for (int side = FUSED ? 0 : 1; side < 2; ++side) {
+      tbl_wait(tbl_bar);
       load_frames<N, false>(v, (side ? a.yg : a.y) + it.sig_base, it.L, it.t0, it.T, p.hop, 0.f, sm.win, lane);
       fft_forward<N>(v, buf, sm.tw, lane);
+      tbl_wait(tbl_bar + 1);
       // forward split in place: Z[k], Z[Nz-k] -> X[k], X[Nz-k] (bin Nz to its own slot)
 #pragma unroll 1
       for (int q = 0; q < C::kQ; ++q) {
@@ -547,6 +566,7 @@ __device__ __forceinline__ void mstft_bwd_body(const PlanDev& p, const MstftBwdA
     for (int d = 16; d > 0; d >>= 1) loss_acc += __shfl_xor_sync(kFullMask, loss_acc, d);
     if (lane == 0) a.partials[vb * kMstftWarps + warp] = loss_acc;
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");   // a warp without an item never waited: its copies land before it exits
 }
 
 template <int N, bool FUSED>
@@ -565,35 +585,43 @@ struct GradOlaArgs {
   long long T;
   float* g;
 };
+// the mirror images of sample j in the reflected borders of resolution r (zero for an interior sample)
+template <bool L2>
+__device__ __forceinline__ float grad_ola_mirrors(const GradOlaArgs& a, int r, const float* fb, long long j) {
+  const int N = a.n_fft[r], h = N / 2, win = N / 2, hop = a.hop[r], Tf = a.Tf[r];
+  // padded position P -> offset coordinate P - N/4; positions outside every window contribute 0
+  auto gp = [&](long long P) -> float {
+    const long long pp = P - N / 4;
+    return pp >= 0 ? ola_gather<L2>(fb, Tf, hop, win, pp) : 0.f;
+  };
+  float m = 0.f;
+  if (j >= 1 && j <= h) m += gp(h - j);
+  if (j > a.T - 2 - h && j <= a.T - 2) m += gp(h + 2 * a.T - 2 - j);
+  return m;
+}
 template <bool L2>
 __device__ __forceinline__ float grad_ola_sample(const GradOlaArgs& a, int b, long long j) {
   float acc = 0.f;
   for (int r = 0; r < a.n_res; ++r) {
     const int N = a.n_fft[r], h = N / 2, win = N / 2, hop = a.hop[r], Tf = a.Tf[r];
     const float* fb = a.gfb[r] + static_cast<long long>(b) * Tf * win;
-    // padded position P -> offset coordinate P - N/4; positions outside every window contribute 0
-    auto gp = [&](long long P) -> float {
-      const long long pp = P - N / 4;
-      return pp >= 0 ? ola_gather<L2>(fb, Tf, hop, win, pp) : 0.f;
-    };
-    acc += gp(h + j);
-    if (j >= 1 && j <= h) acc += gp(h - j);
-    if (j > a.T - 2 - h && j <= a.T - 2) acc += gp(h + 2 * a.T - 2 - j);
+    const long long pp = h + j - N / 4;
+    acc += ola_gather<L2>(fb, Tf, hop, win, pp);
+    acc += grad_ola_mirrors<L2>(a, r, fb, j);
   }
   return acc;
 }
-// Four consecutive samples j0 .. j0+3 (j0 % 4 == 0) away from the reflected borders of every resolution: with hop % 4 == 0 they are
-// covered by the same frames at offsets that are multiples of 4, so each frame contributes one 16-byte load (same summation
-// order per sample as grad_ola_sample: resolutions in order, frames from the last covering one backwards).
+// Four consecutive samples j0 .. j0+3 (j0 % 4 == 0): with hop % 4 == 0 their own positions are covered by the same frames at offsets
+// that are multiples of 4, so each frame contributes one 16-byte load; samples inside a reflected border of a resolution add that
+// resolution's mirror terms one by one.  Same summation order per sample as grad_ola_sample: resolutions in order; the position
+// itself (frames from the last covering one backwards), then the mirrors.
 __device__ __forceinline__ float4 grad_ola_quad(const GradOlaArgs& a, int b, long long j0) {
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int r = 0; r < a.n_res; ++r) {
-    const int N = a.n_fft[r], win = N / 2, hop = a.hop[r], Tf = a.Tf[r];
+    const int N = a.n_fft[r], h = N / 2, win = N / 2, hop = a.hop[r], Tf = a.Tf[r];
     const float* fb = a.gfb[r] + static_cast<long long>(b) * Tf * win;
     const long long pp = N / 4 + j0;                         // (h + j0) - N/4
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    // frames tp_lo .. tp_hi cover the position (offset pp - tp hop in [0, win)); their loads are issued together, six at a time
-    // (win / hop <= 5 at the reference's resolutions), and summed in the order of the rolled loop
     int tp_hi, tp_lo;
     if (pp < (1LL << 30)) {   // 32-bit divisions (the 64-bit one is a subroutine)
       const int q = static_cast<int>(pp);
@@ -603,7 +631,7 @@ __device__ __forceinline__ float4 grad_ola_quad(const GradOlaArgs& a, int b, lon
       tp_hi = static_cast<int>(min(static_cast<long long>(Tf - 1), pp / hop));
       tp_lo = static_cast<int>((pp - win) / hop) + 1;
     }
-    constexpr int kFrames = 6;
+    constexpr int kFrames = 6;   // win / hop <= 5 at the reference's resolutions: one round of loads, all in flight together
     for (int t1 = tp_hi; t1 >= tp_lo; t1 -= kFrames) {
       float4 v[kFrames];
 #pragma unroll
@@ -619,6 +647,12 @@ __device__ __forceinline__ float4 grad_ola_quad(const GradOlaArgs& a, int b, lon
       }
     }
     acc.x += s.x; acc.y += s.y; acc.z += s.z; acc.w += s.w;
+    if (j0 <= h || j0 + 3 > a.T - 2 - h) {   // some sample of the quad lies in a reflected border of this resolution
+      acc.x += grad_ola_mirrors<false>(a, r, fb, j0);
+      acc.y += grad_ola_mirrors<false>(a, r, fb, j0 + 1);
+      acc.z += grad_ola_mirrors<false>(a, r, fb, j0 + 2);
+      acc.w += grad_ola_mirrors<false>(a, r, fb, j0 + 3);
+    }
   }
   return acc;
 }
@@ -634,18 +668,17 @@ __global__ void __launch_bounds__(256) grad_ola_kernel(const GradOlaArgs a, cons
     return;
   }
   const int b = blockIdx.y;
-  int hmax = 0;
   bool vec = (a.T >= 8);
-  for (int r = 0; r < a.n_res; ++r) {
-    hmax = max(hmax, a.n_fft[r] / 2);
-    vec = vec && (a.hop[r] % 4 == 0) && (a.n_fft[r] % 16 == 0);
-  }
+  for (int r = 0; r < a.n_res; ++r) vec = vec && (a.hop[r] % 4 == 0) && (a.n_fft[r] % 16 == 0);
   float* g = a.g + static_cast<long long>(b) * a.T;
   for (long long j0 = 4 * (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x); j0 < a.T;
        j0 += 4 * static_cast<long long>(gx) * blockDim.x) {
-    if (vec && j0 > hmax && j0 + 3 <= a.T - 2 - hmax) {
+    if (vec) {
       const float4 v = grad_ola_quad(a, b, j0);
-      g[j0] = v.x; g[j0 + 1] = v.y; g[j0 + 2] = v.z; g[j0 + 3] = v.w;
+      g[j0] = v.x;
+      if (j0 + 1 < a.T) g[j0 + 1] = v.y;
+      if (j0 + 2 < a.T) g[j0 + 2] = v.z;
+      if (j0 + 3 < a.T) g[j0 + 3] = v.w;
     } else {
       for (long long j = j0; j < min(j0 + 4, a.T); ++j) g[j] = grad_ola_sample<false>(a, b, j);
     }

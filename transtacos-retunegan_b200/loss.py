@@ -72,6 +72,7 @@ class _MultiStftFn(torch.autograd.Function):
     def forward(ctx, y, y_g, cfg: SpectralConfig, want_loss: bool, want_specs: bool):
         lib = _lib.load()
         dev = core.require_cuda()
+        ctx.set_materialize_grads(False)   # no zero-filled gradients for outputs nobody differentiated (the real-audio stacks)
         yc = _as_rows(y, dev)
         gc = _as_rows(y_g, dev)
         B, T = gc.shape[0], gc.shape[-1]
@@ -118,6 +119,8 @@ class _MultiStftFn(torch.autograd.Function):
         if ctx.fused:
             (grad,) = ctx.saved_tensors
             g0 = grads[0]
+            if g0 is None:
+                return None, None, None, None, None
             if g0.dtype is not torch.float32 or g0.device != grad.device:
                 g0 = g0.to(device=grad.device, dtype=torch.float32)
             g = (g0 * grad).view(ctx.in_shape)
@@ -133,12 +136,12 @@ class _MultiStftFn(torch.autograd.Function):
             g_loss = grads[0]
             i = 1
             if g_loss is not None:
-                g_loss = g_loss.to(device=dev, dtype=torch.float32).contiguous()
+                g_loss = _as_rows(g_loss, dev)
         g_specs = None
         if ctx.want_specs:
             gs = grads[i + n_res: i + 2 * n_res]
             if any(g is not None for g in gs):
-                g_specs = [None if g is None else g.to(torch.float32).contiguous() for g in gs]
+                g_specs = [None if g is None else _as_rows(g, dev) for g in gs]
         g_yg = torch.empty((B, T), device=dev, dtype=torch.float32)
         ws = core._workspace(ctx.ws_bytes, dev, "mstft")
         _lib.check(lib.sb200_mstft_backward(ctx.handles, n_res, core.ptr(gc), B, T, ctx.phd_phase, core.ptr(g_loss),
