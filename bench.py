@@ -275,6 +275,31 @@ def make_griffinlim(sb, torch, B=1, form="rtg", rot=4):
     return w
 
 
+def graph_replay_ms(torch, step, n=100):
+    """ms per replay of step(0) captured as one CUDA graph (the step must be capturable: no host synchronisation inside)."""
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(3):
+            step(0)
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        step(0)
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    del g
+    return e0.elapsed_time(e1) / n
+
+
 def make_mstft(sb, torch, B=16, T=22050, specs=False, rot=4, ddp=False):
     w = Workload()
     w.name = f"mstft_fwd_bwd_{B}x{T}" + ("_specs" if specs else "_lossonly")
@@ -713,6 +738,15 @@ def main():
             if mkey.startswith("mstft") and world > 1:
                 ddp_cached = ddp_cached or ddp_probe()
                 ent["ddp"] = ddp_cached
+            if mkey.startswith("mstft") and world == 1:
+                # the eager step is bound by the host (Python, autograd engine, driver calls); the same step replayed as ONE CUDA
+                # graph is its GPU time
+                try:
+                    ent["graph_replay_ms_per_step"] = graph_replay_ms(torch, ww.step)
+                    ent["graph_replay_note"] = ("whole step (forward, backward, the autograd wrapper's ops) captured once with "
+                                                "torch.cuda.graph and replayed 100 times: GPU time of the step; ms_per_step is the eager API")
+                except Exception as ex:
+                    ent["graph_replay_error"] = repr(ex)[:200]
             extra[key] = ent
             del ww
             torch.cuda.empty_cache()

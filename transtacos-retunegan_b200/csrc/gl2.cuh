@@ -26,6 +26,16 @@ constexpr int kGl2Warps = 8;        // warps per CTA
 constexpr int kGl2GroupWarps = 4;   // warps per tile group: a CTA runs kGl2Warps / kGl2GroupWarps tiles concurrently, each
                                     // group synchronising on its own named barrier so their phases interleave
 constexpr int kGl2Groups = kGl2Warps / kGl2GroupWarps;
+// Unroll factor of the Hermitian-pair loop of the spectrum pass: the loop carries the next trip's operands (24 registers per pair)
+// in a register rotation, which a rolled loop pays as ~50 MOVs per trip.  Batches (one launch per iteration, code warm after the
+// first tile): 4 (1.105 -> 1.035 ms per 64 x 5 s x 4 iterations).  The persistent single-utterance kernel takes the same factor (0.410 -> 0.402 ms per 1 x 5 s x 30 iterations; 2 measured 0.399): with different factors ptxas contracts the scalar parts differently and a ragged batch is no longer bit-equal to single calls (tests).
+#ifndef SB200_GL2_PAIR_UNROLL
+#define SB200_GL2_PAIR_UNROLL 4
+#endif
+#ifndef SB200_GL2_PAIR_UNROLL_COH
+#define SB200_GL2_PAIR_UNROLL_COH 4
+#endif
+constexpr int kGl2PairUnroll = SB200_GL2_PAIR_UNROLL, kGl2PairUnrollCoh = SB200_GL2_PAIR_UNROLL_COH;
 #ifdef kGl2TprevAheadOverride
 constexpr bool kGl2TprevAhead = kGl2TprevAheadOverride;
 #else
@@ -46,11 +56,19 @@ struct Gl2Args {
   const float* yb_in;
   float* ya_out;
   float* yb_out;
-  float2* tprev;             // [frames, F] (mode 3): previous rebuilt spectrum in the engine's internal (rotated) form
+  ulonglong2* tprev;         // (mode 3) previous rebuilt spectrum in the engine's internal (rotated) form, PACKED per frame pair the
+                             // way the registers hold it: element (pair slot, bin) = {re of frames (2m, 2m+1), im of (2m, 2m+1)}, 16 bytes;
+                             // pair slot of frames (2m, 2m+1) of utterance b = gl2_pair_base(frame_base, b) + m
   float alpha;               // momentum / (1 + momentum)
   int first;                 // mode 3: tprev not yet written (rebuilt = 0)
   int groups_active;         // tile groups of a CTA that take tiles (0 = all): 1 gives a small batch one tile per SM
 };
+
+// First pair slot of utterance b in the packed previous-spectrum array: utterances with an odd number of frames leave half a slot
+// unused, so slot bases are rounded up from frame_base + 2 b + 1 (consecutive utterances never share a slot; at most
+// (total_frames + 2 B + 1) / 2 + 1 slots in all).
+__host__ __device__ __forceinline__ long long gl2_pair_base(long long frame_base, int b) { return (frame_base + 2LL * b + 1) >> 1; }
+__host__ __device__ __forceinline__ long long gl2_pair_slots(long long total_frames, long long B) { return (total_frames + 2 * B + 1) / 2 + 1; }
 
 // first element of utterance b in the signal buffers; an utterance owns (T - 1) * hop + win elements
 __device__ __forceinline__ long long gl2_sig_base(const GlRow& row, int b, int hop, int win) {
@@ -107,9 +125,9 @@ __device__ __forceinline__ float gl2_rcp(float x) {
 }
 
 // Phase update of one held spectral value X of both frames of a pair (modes 2 / 3): magnitudes sA / sB, previous
-// spectrum tA / tB.  rot = bin index mod 4, conj_held = b side (value held conjugated): only used for the exact-zero case.
+// spectrum T (packed like X).  rot = bin index mod 4, conj_held = b side (value held conjugated): only used for the exact-zero case.
 template <int MODE>
-__device__ __forceinline__ PC gl2_update(const PC& X, float sA, float sB, float2 tA, float2 tB, float alpha, int first, int rot,
+__device__ __forceinline__ PC gl2_update(const PC& X, float sA, float sB, const PC& T, float alpha, int first, int rot,
                                          bool conj_held) {
   PC o;
   if constexpr (MODE == 2) {   // transtacos/audio.py:137-138: angles = exp(1j * angle(X))
@@ -128,8 +146,8 @@ __device__ __forceinline__ PC gl2_update(const PC& X, float sA, float sB, float2
   } else {                     // librosa.griffinlim: c = rebuilt - alpha * tprev; angles = c / (|c| + 1e-16)
     // tprev is loaded as zero on the first iteration (rebuilt = 0): the update is then exactly X, without a select
     PC c;
-    c.re = fma2s(pk(tA.x, tB.x), -alpha, X.re);
-    c.im = fma2s(pk(tA.y, tB.y), -alpha, X.im);
+    c.re = fma2s(T.re, -alpha, X.re);
+    c.im = fma2s(T.im, -alpha, X.im);
     const pf n2 = norm2(c);
     // MUFU sqrt / reciprocal (~1e-7 relative): far inside the Griffin-Lim tolerance, and branch-free
     const pf sc = pk(sA * gl2_rcp(fast_sqrt(plo(n2)) + 1e-16f), sB * gl2_rcp(fast_sqrt(phi(n2)) + 1e-16f));
@@ -275,8 +293,9 @@ __device__ __forceinline__ void gl2_pass(const PlanDev& p, const Gl2Args& a, Gl2
         for (int o = lane * 128; o < nfr * C::kF * 4; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(sp0 + o));
         if constexpr (MODE == 3) {
           if (!a.first) {
-            const char* tp0 = reinterpret_cast<const char*>(a.tprev + r0);
-            for (int o = lane * 128; o < nfr * C::kF * 8; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(tp0 + o));
+            const char* tp0 = reinterpret_cast<const char*>(
+                a.tprev + (gl2_pair_base(row.frame_base, b) + (min(item_t0, row.T - 1) >> 1)) * C::kF);
+            for (int o = lane * 128; o < ((nfr + 1) >> 1) * C::kF * 16; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(tp0 + o));
           }
         }
       }
@@ -321,12 +340,15 @@ __device__ __forceinline__ void gl2_pass(const PlanDev& p, const Gl2Args& a, Gl2
         // frames past the end are clamped to the last one (loads stay in bounds) and masked
         const long long rowA = (row.frame_base + min(fA, row.T - 1)) * C::kF, rowB = (row.frame_base + min(fA + 1, row.T - 1)) * C::kF;
         const float mA = okA ? 1.f : 0.f, mB = okB ? 1.f : 0.f;
+        // packed previous spectrum of this pair (a pair past the end is clamped to the last one: loads stay in bounds and finite)
+        ulonglong2* const tpp = a.tprev + (gl2_pair_base(row.frame_base, b) + (min(fA, row.T - 1) >> 1)) * C::kF;
         ulonglong2* const zp = xz + pp * C::kNz;
         // everything one Hermitian pair (k, Nz - k) reads, fetched one trip ahead of its use
         struct PairLd {
           ulonglong2 zk, zr;
           float sAa, sBa, sAb, sBb;
-          float2 tAa, tBa, tAb, tBb;
+          float2 tAa, tBa, tAb, tBb;   // modes 0 / 1: input spectrum / initial phase
+          ulonglong2 ta, tb;           // mode 3: previous rebuilt spectrum of bins k / Nz - k, packed (re pair, im pair)
         };
         auto ld_pair = [&](int k) -> PairLd {
           PairLd L;
@@ -357,13 +379,11 @@ __device__ __forceinline__ void gl2_pass(const PlanDev& p, const Gl2Args& a, Gl2
             L.sBa = __ldg(a.S + rowB + k);
             L.sAb = __ldg(a.S + rowA + kb);
             L.sBb = __ldg(a.S + rowB + kb);
-            L.tAa = L.tBa = L.tAb = L.tBb = make_float2(0.f, 0.f);
+            L.ta = L.tb = make_ulonglong2(0ull, 0ull);
             if constexpr (MODE == 3) {
               if (!a.first) {
-                L.tAa = a.tprev[rowA + k];
-                L.tBa = a.tprev[rowB + k];
-                L.tAb = a.tprev[rowA + kb];
-                L.tBb = a.tprev[rowB + kb];
+                L.ta = tpp[k];
+                L.tb = tpp[kb];
               }
             }
           }
@@ -380,18 +400,17 @@ __device__ __forceinline__ void gl2_pass(const PlanDev& p, const Gl2Args& a, Gl2
             Zk.re = L.zk.x; Zk.im = L.zk.y;
             Zr.re = L.zr.x; Zr.im = L.zr.y;
             split2<SINFORM>(Zk, Zr, tws, P, Q);
-            if constexpr (MODE == 3) {   // the rebuilt spectrum becomes the next iteration's tprev
-              if (okA) {
-                a.tprev[rowA + k] = make_float2(plo(P.re), plo(P.im));
-                a.tprev[rowA + kb] = make_float2(plo(Q.re), plo(Q.im));
-              }
-              if (okB) {
-                a.tprev[rowB + k] = make_float2(phi(P.re), phi(P.im));
-                a.tprev[rowB + kb] = make_float2(phi(Q.re), phi(Q.im));
+            if constexpr (MODE == 3) {   // the rebuilt spectrum becomes the next iteration's tprev (both frames of the pair: the
+              if (okA) {                 // second half of an odd utterance's last pair is the spectrum of a zero frame, finite)
+                tpp[k] = make_ulonglong2(P.re, P.im);
+                tpp[kb] = make_ulonglong2(Q.re, Q.im);
               }
             }
-            P = gl2_update<MODE>(P, L.sAa * mA, L.sBa * mB, L.tAa, L.tBa, a.alpha, a.first, k & 3, false);
-            Q = gl2_update<MODE>(Q, L.sAb * mA, L.sBb * mB, L.tAb, L.tBb, a.alpha, a.first, (4 - (k & 3)) & 3, true);
+            PC Ta, Tb;
+            Ta.re = L.ta.x; Ta.im = L.ta.y;
+            Tb.re = L.tb.x; Tb.im = L.tb.y;
+            P = gl2_update<MODE>(P, L.sAa * mA, L.sBa * mB, Ta, a.alpha, a.first, k & 3, false);
+            Q = gl2_update<MODE>(Q, L.sAb * mA, L.sBb * mB, Tb, a.alpha, a.first, (4 - (k & 3)) & 3, true);
           } else {
             if constexpr (MODE == 0) {
               P = gl2_fetch_v<MODE>(0.f, 0.f, make_float2(L.tAa.x * mA, L.tAa.y * mA), make_float2(L.tBa.x * mB, L.tBa.y * mB), k & 3, false);
@@ -416,8 +435,8 @@ __device__ __forceinline__ void gl2_pass(const PlanDev& p, const Gl2Args& a, Gl2
         {
           constexpr int kTrips = C::kNz / 128;
           PairLd c0 = ld_pair(lane), c1 = ld_pair(lane + C::kNz / 4);
-#pragma unroll 1
-          for (int ii = 0; ii < kTrips; ++ii) {   // rolled on purpose: a single-tile launch runs this code once, from a cold instruction cache
+#pragma unroll (COH ? kGl2PairUnrollCoh : kGl2PairUnroll)
+          for (int ii = 0; ii < kTrips; ++ii) {   // rolled: a single-tile launch runs this code once, from a cold instruction cache
             const int k = lane + 32 * ii;
             PairLd n0 = c0, n1 = c1;
             if (ii + 1 < kTrips) {
@@ -438,21 +457,21 @@ __device__ __forceinline__ void gl2_pass(const PlanDev& p, const Gl2Args& a, Gl2
           if constexpr (MODE >= 2) {
             const ulonglong2 zk = zp[k];
             const float sAa = __ldg(a.S + rowA + k) * mA, sBa = __ldg(a.S + rowB + k) * mB;
-            float2 tAa = make_float2(0.f, 0.f), tBa = tAa;
+            PC Ta;
+            Ta.re = Ta.im = 0ull;
             if constexpr (MODE == 3) {
               if (!a.first) {
-                tAa = a.tprev[rowA + k];
-                tBa = a.tprev[rowB + k];
+                const ulonglong2 t = tpp[k];
+                Ta.re = t.x; Ta.im = t.y;
               }
             }
             PC Zk;
             Zk.re = zk.x; Zk.im = zk.y;
             split2<true>(Zk, Zk, tws, P, Q);
             if constexpr (MODE == 3) {
-              if (lane == 0 && okA) a.tprev[rowA + k] = make_float2(plo(P.re), plo(P.im));
-              if (lane == 0 && okB) a.tprev[rowB + k] = make_float2(phi(P.re), phi(P.im));
+              if (lane == 0 && okA) tpp[k] = make_ulonglong2(P.re, P.im);
             }
-            P = gl2_update<MODE>(P, sAa, sBa, tAa, tBa, a.alpha, a.first, 0, false);
+            P = gl2_update<MODE>(P, sAa, sBa, Ta, a.alpha, a.first, 0, false);
           } else {
             P = gl2_fetch<MODE>(a, rowA, rowB, okA, okB, k, 0, false);
           }

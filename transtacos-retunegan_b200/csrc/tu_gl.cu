@@ -53,7 +53,7 @@ int64_t sb200_griffinlim_workspace_bytes(const sb200_plan* plan, int64_t total_f
   if (!plan || total_frames < 1 || n_rows < 1) return -1;
   const int64_t F = plan->cfg.n_fft / 2 + 1;
   int64_t bytes = 4 * gl2_sig_elems(plan, total_frames, n_rows) * 4;
-  if (form == 1) bytes += total_frames * F * 8;        // tprev (complex64)
+  if (form == 1) bytes += gl2_pair_slots(total_frames, n_rows) * F * 16;   // tprev: complex64 of both frames of a pair per bin
   return bytes + 512;
 }
 
@@ -182,11 +182,11 @@ int sb200_griffinlim(const sb200_plan* plan, const float* S, const float* init_p
   a.alpha = momentum / (1.f + momentum);
   const long long sig_elems = gl2_sig_elems(plan, total_frames, a.g.bd.B);
   float* sig = static_cast<float*>(workspace);
-  a.tprev = reinterpret_cast<float2*>(sig + 4 * sig_elems);
+  a.tprev = reinterpret_cast<ulonglong2*>(sig + 4 * sig_elems);
   int rc = 0;
   // grid-barrier counter: first 256-byte boundary behind the signal buffers and tprev (inside the workspace's 512 bytes of slack)
   const size_t used = static_cast<size_t>(4) * sig_elems * sizeof(float) +
-                      (form == 1 ? static_cast<size_t>(total_frames) * (plan->cfg.n_fft / 2 + 1) * 8 : 0);
+                      (form == 1 ? static_cast<size_t>(gl2_pair_slots(total_frames, a.g.bd.B)) * (plan->cfg.n_fft / 2 + 1) * 16 : 0);
   unsigned* counter = reinterpret_cast<unsigned*>(static_cast<char*>(workspace) + (used + 255) / 256 * 256);
   SB200_DISPATCH_N(plan, rc = launch_gl2<kN>(plan, a, n_iter, form, y, inv_preemph, sig, sig_elems, max_len,
                                              static_cast<cudaStream_t>(stream), counter));
