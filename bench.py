@@ -329,7 +329,8 @@ def make_mstft(sb, torch, B=16, T=22050, specs=False, rot=4, ddp=False):
     w.alg_bytes = (4.23e6 if not specs else 113e6) * (B / 16) * (T / 22050)
     w.dominant = "mstft_fwd_kernel+mstft_bwd_kernel (3 resolutions)"
     w.note = ("loss-only" if not specs else "training variant: spec stacks written, dense upstream spec grads") + \
-        ("; the reported loss is averaged over the ranks with one NCCL all-reduce of a scalar inside the step" if ddp else "")
+        ("; the reported loss is averaged over the ranks inside the step (multi_stft_loss(ddp_reduce=True): " +
+         sb.loss.ddp_reduce_path() + ")" if ddp else "")
     w.flops = (0.49e9 + 0.25e9) * (B / 16) * (T / 22050)
 
     def check():
@@ -704,7 +705,8 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         return {"generator_grad_allreduce_ms": allmax(e0.elapsed_time(e1) / 50), "generator_grad_bytes": gbuf.numel() * 4,
-                "loss_allreduce": "one fp32 scalar per step, inside the timed step (multi_stft_loss(ddp_reduce=True))"}
+                "loss_allreduce": "one fp32 scalar per step, inside the timed step (multi_stft_loss(ddp_reduce=True)): " +
+                                  sb.loss.ddp_reduce_path()}
 
     ddp_info = ddp_probe() if (world > 1 and a.workload.startswith("mstft")) else None
 

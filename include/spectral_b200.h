@@ -231,6 +231,38 @@ int sb200_stft_smp_backward(const sb200_plan* plan, const float* y, int32_t B, i
 int sb200_mstft_loss_and_grad(const sb200_plan* const* plans, int32_t n_res, const float* y, const float* y_g, int32_t B,
                               int64_t T, float* loss, float* grad_yg, void* workspace, sb200_stream stream);
 
+/* ---- DDP: the loss averaged over the ranks of one box INSIDE the reducing kernel --------------------------------------------
+ * Under DDP every rank computes l_mstft on its own segments (retunegan/train.py:165 inside the DDP-wrapped step); what is logged
+ * is its mean over the ranks.  Instead of an NCCL all-reduce of one scalar after the step (a host call and a launch on a step
+ * that is itself bound by the host), the block that reduces the rank's loss exchanges it with the other ranks over NVLink peer
+ * memory: it stores the value into every rank's exchange buffer, publishes it with a release store of an epoch counter, waits
+ * for the other ranks' flags and adds the values in rank order (same result on every rank).  No launch, no host call, CUDA-graph
+ * safe (the epoch lives in device memory).  A wait longer than 2 s yields NaN instead of hanging.
+ *
+ * Every rank creates one exchange buffer (sb200_peer_buffer_create: cudaMalloc + zero fill + CUDA IPC handle, 64 bytes), the
+ * handles are exchanged by the caller (e.g. torch.distributed.all_gather_object) and opened with sb200_peer_buffer_open.
+ * peer[q] = exchange buffer of rank q as a device pointer valid in THIS process (the own buffer at [rank]); all ranks must make
+ * the same sequence of *_ddp calls.  world <= SB200_MAX_PEERS (one NVSwitch box); larger jobs reduce with NCCL instead. */
+#define SB200_MAX_PEERS 8
+typedef struct {
+  void* peer[SB200_MAX_PEERS];
+  int32_t rank, world;
+  float* loss_global; /* device scalar out: mean of the ranks' losses */
+} sb200_peer_reduce;
+int64_t sb200_peer_buffer_bytes(void);
+int sb200_peer_buffer_create(void** buf, void* ipc_handle_out_64_bytes /* may be NULL: single-process use */);
+int sb200_peer_buffer_open(const void* ipc_handle_64_bytes, void** buf);
+int sb200_peer_buffer_close(void* buf);   /* a buffer obtained from sb200_peer_buffer_open */
+int sb200_peer_buffer_destroy(void* buf); /* a buffer obtained from sb200_peer_buffer_create */
+/* sb200_mstft_forward / sb200_mstft_loss_and_grad (loss required) + the reduction described above; `loss` still receives the
+ * rank-local value (the one the gradient belongs to), peers->loss_global the mean over the ranks. */
+int sb200_mstft_forward_ddp(const sb200_plan* const* plans, int32_t n_res, const float* y, const float* y_g, int32_t B,
+                            int64_t T, int32_t phd_phase, float* loss, float* const* specs_r, float* const* specs_g,
+                            void* saved, void* workspace, const sb200_peer_reduce* peers, sb200_stream stream);
+int sb200_mstft_loss_and_grad_ddp(const sb200_plan* const* plans, int32_t n_res, const float* y, const float* y_g, int32_t B,
+                                  int64_t T, float* loss, float* grad_yg, void* workspace, const sb200_peer_reduce* peers,
+                                  sb200_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -681,3 +681,48 @@ def test_host_pipeline_and_phase_cache_stay_bounded(sb):
     u = np.random.RandomState(114514).rand(1025, 21)                    # librosa.griffinlim(random_state=114514) draws this afresh
     ref = O.rtg_inv_mag(mag[:, :21].astype(np.float32), wavlen=256 * 21 - 1, init_angles=np.exp(2j * np.pi * u))
     assert rel_fro(first, ref) <= 1e-3
+
+
+# ------------------------------------------------------------------ DDP: loss reduced inside the launch -----------
+
+@pytest.mark.parametrize("specs", [False, True])
+def test_in_kernel_loss_reduction_two_ranks_on_one_device(sb, specs):
+    """include/spectral_b200.h, sb200_mstft_*_ddp: two "ranks" (two exchange buffers, two streams) on ONE device exchange their
+    losses inside the reducing block: both get the same mean, bit for bit, equal to the mean of the two local losses; gradients
+    stay the local ones.  Four calls in a row: the epoch counter and both slot parities."""
+    L = sb.loss
+    bufs = [L.PeerLossReducer.create_buffer() for _ in range(2)]
+    try:
+        reds = [L.PeerLossReducer(r, 2, peers=bufs) for r in range(2)]
+        B, T = 4, 8192
+        streams = [torch.cuda.Stream() for _ in range(2)]
+        for it in range(4):
+            ys = [torch.from_numpy(np.stack([O.synth_noise(T, 900 + 10 * it + 2 * r + b) for b in range(B)])).cuda() for r in range(2)]
+            ygs = [torch.tanh(1.1 * y).requires_grad_(True) for y in ys]
+            local, local_grad = [], []
+            for r in range(2):                                   # the plain path, one "rank" at a time
+                l = sb.multi_stft_loss(ys[r], ygs[r], ret_loss=True, ret_specs=specs)
+                l = l[0] if specs else l
+                (g,) = torch.autograd.grad(l, ygs[r])
+                local.append(l.detach().clone())
+                local_grad.append(g)
+            torch.cuda.synchronize()
+            outs = []
+            for r in range(2):
+                streams[r].wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(streams[r]):
+                    outs.append(L._MultiStftFn.apply(ys[r], ygs[r], L.hp, True, specs, reds[r]))
+            grads = []
+            for r in range(2):
+                with torch.cuda.stream(streams[r]):
+                    grads.append(torch.autograd.grad(outs[r][0], ygs[r])[0])
+            torch.cuda.synchronize()
+            m0, m1 = outs[0][0].item(), outs[1][0].item()
+            assert np.isfinite(m0) and m0 == m1, (it, m0, m1)
+            assert m0 == (np.float32(local[0].item()) + np.float32(local[1].item())) / np.float32(2), (it, m0, local)
+            for r in range(2):
+                assert torch.equal(grads[r], local_grad[r])
+    finally:
+        torch.cuda.synchronize()
+        for b in bufs:
+            L.PeerLossReducer.destroy_buffer(b)

@@ -31,6 +31,14 @@ class Scale(C.Structure):
 
 RAW = Scale(0, 1.0, 0.0, 0.0)
 
+MAX_PEERS = 8
+
+
+class PeerReduce(C.Structure):
+    """sb200_peer_reduce: exchange buffers of the ranks of one box (in-kernel loss reduction under DDP)."""
+    _fields_ = [("peer", C.c_void_p * MAX_PEERS), ("rank", C.c_int32), ("world", C.c_int32), ("loss_global", C.c_void_p)]
+
+
 # name -> (restype, argtypes); every symbol declared in include/spectral_b200.h
 _P, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 SIGNATURES = {
@@ -65,6 +73,14 @@ SIGNATURES = {
                                       C.POINTER(_P), _P, _P, _P]),
     "sb200_mstft_loss_and_grad": (C.c_int, [C.POINTER(_P), _I32, _P, _P, _I32, _I64, _P, _P, _P, _P]),
     "sb200_mstft_backward": (C.c_int, [C.POINTER(_P), _I32, _P, _I32, _I64, _I32, _P, C.POINTER(_P), _P, _P, _P, _P]),
+    "sb200_peer_buffer_bytes": (_I64, []),
+    "sb200_peer_buffer_create": (C.c_int, [C.POINTER(_P), _P]),
+    "sb200_peer_buffer_open": (C.c_int, [_P, C.POINTER(_P)]),
+    "sb200_peer_buffer_close": (C.c_int, [_P]),
+    "sb200_peer_buffer_destroy": (C.c_int, [_P]),
+    "sb200_mstft_forward_ddp": (C.c_int, [C.POINTER(_P), _I32, _P, _P, _I32, _I64, _I32, _P, C.POINTER(_P),
+                                          C.POINTER(_P), _P, _P, C.POINTER(PeerReduce), _P]),
+    "sb200_mstft_loss_and_grad_ddp": (C.c_int, [C.POINTER(_P), _I32, _P, _P, _I32, _I64, _P, _P, _P, C.POINTER(PeerReduce), _P]),
 }
 
 _lib = None

@@ -220,12 +220,70 @@ __global__ void __launch_bounds__(kMstftWarps * 32, 2) stft_smp_kernel(const Pla
   }
 }
 
+// ---- loss reduction over the ranks of one box, inside the reducing block (DDP) -----------------------------------------------
+// Every rank owns one exchange buffer (PeerBuf, cudaMalloc + CUDA IPC: all of them are mapped in every process, reached over
+// NVLink / NVSwitch peer access).  The thread that has just reduced the rank's loss stores it into slot [rank] of EVERY rank's
+// buffer, publishes it with a release store of the call's epoch into the matching flag, waits until all flags of its own
+// buffer carry the epoch and adds the slots in rank order: every rank gets the same mean, bit for bit, with no extra launch and
+// no host call.  The epoch is a counter in the rank's own buffer incremented by the kernel itself (CUDA-graph replay safe);
+// slots are double-buffered by epoch parity: a rank can only be one call ahead of the slowest one, because its next call waits
+// for that rank's flag.  A wait that exceeds kPeerTimeoutNs gives up and yields NaN instead of hanging the GPU.
+constexpr int kMaxPeers = 8;
+constexpr unsigned long long kPeerTimeoutNs = 2000000000ull;
+struct PeerBuf {
+  unsigned epoch;
+  unsigned pad[31];
+  float vals[2][kMaxPeers];
+  unsigned flags[2][kMaxPeers];
+};
+struct PeerDev {
+  void* buf[kMaxPeers];
+  int rank, world;   // world <= 1: no reduction
+  float* out;        // device scalar: mean over the ranks
+};
+__device__ __forceinline__ unsigned long long peer_now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void peer_allreduce_mean(const PeerDev& pd, float local) {
+  PeerBuf* me = static_cast<PeerBuf*>(pd.buf[pd.rank]);
+  const unsigned e = me->epoch + 1;   // written by this thread of this rank only
+  me->epoch = e;
+  const int par = e & 1;
+  for (int q = 0; q < pd.world; ++q) {
+    PeerBuf* pb = static_cast<PeerBuf*>(pd.buf[q]);
+    asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(&pb->vals[par][pd.rank]), "f"(local) : "memory");
+  }
+  __threadfence_system();
+  for (int q = 0; q < pd.world; ++q) {
+    PeerBuf* pb = static_cast<PeerBuf*>(pd.buf[q]);
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&pb->flags[par][pd.rank]), "r"(e) : "memory");
+  }
+  const unsigned long long t0 = peer_now_ns();
+  float sum = 0.f;
+  bool ok = true;
+  for (int q = 0; q < pd.world && ok; ++q) {
+    unsigned seen;
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(&me->flags[par][q]) : "memory");
+      if (seen == e) break;
+      if (peer_now_ns() - t0 > kPeerTimeoutNs) { ok = false; break; }
+    }
+    float v;
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(&me->vals[par][q]) : "memory");
+    sum += v;
+  }
+  *pd.out = ok ? sum / static_cast<float>(pd.world) : __int_as_float(0x7fc00000);
+}
+
 struct MstftFinArgs {
   int n_res;
   const float* partials[kMaxRes];
   int n_partials[kMaxRes];
   float inv_count[kMaxRes];   // 1 / (B * n_mel * Tf)
   float* loss;
+  PeerDev peer;               // DDP: the rank's loss is also averaged over the box (peer.world > 1)
 };
 // loss = 1/n_res * sum_res (sum of partials) / count   (F.l1_loss reduction='mean', loss.py:51-54); one CTA, fixed order:
 // thread i sums partials i, i + blockDim, ... of every resolution (all loads independent), warps reduce by shuffle, thread 0 adds
@@ -253,7 +311,9 @@ __device__ __forceinline__ void mstft_finalize_body(const MstftFinArgs& a) {
       for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) t += red[r][w];
       total += t * a.inv_count[r];
     }
-    *a.loss = total / a.n_res;
+    const float local = total / a.n_res;
+    *a.loss = local;
+    if (a.peer.world > 1) peer_allreduce_mean(a.peer, local);
   }
 }
 __global__ void mstft_finalize_kernel(const MstftFinArgs a) { mstft_finalize_body(a); }

@@ -1,5 +1,6 @@
 // C-ABI entry points: multi-resolution STFT loss forward / backward (include/spectral_b200.h).
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 
 #include "capi_common.cuh"
@@ -287,16 +288,35 @@ static int mstft_all_bwd(const sb200_plan* const* plans, int32_t n_res, const fl
   return check_launch(fused ? "mstft_all_bwd_kernel<fused>" : "mstft_all_bwd_kernel");
 }
 
-int sb200_mstft_forward(const sb200_plan* const* plans, int32_t n_res, const float* y, const float* y_g, int32_t B,
-                        int64_t T, int32_t phd_phase, float* loss, float* const* specs_r, float* const* specs_g,
-                        void* saved, void* workspace, sb200_stream stream) {
+// sb200_peer_reduce -> device view, or world = 0 (no reduction)
+static int peer_dev(const sb200_peer_reduce* pr, PeerDev* out) {
+  *out = PeerDev{};
+  if (pr == nullptr) return SB200_OK;
+  if (pr->world < 1 || pr->world > kMaxPeers || pr->rank < 0 || pr->rank >= pr->world || !pr->loss_global)
+    return fail(SB200_ERR_INVALID, "peer reduce: need 1 <= world <= 8, 0 <= rank < world and a loss_global pointer");
+  for (int q = 0; q < pr->world; ++q) {
+    if (!pr->peer[q]) return fail(SB200_ERR_INVALID, "peer reduce: null exchange buffer");
+    out->buf[q] = pr->peer[q];
+  }
+  out->rank = pr->rank;
+  out->world = pr->world;
+  out->out = pr->loss_global;
+  return SB200_OK;
+}
+
+static int mstft_forward_impl(const sb200_plan* const* plans, int32_t n_res, const float* y, const float* y_g, int32_t B,
+                              int64_t T, int32_t phd_phase, float* loss, float* const* specs_r, float* const* specs_g,
+                              void* saved, void* workspace, const sb200_peer_reduce* pr, sb200_stream stream) {
   if (int rc = mstft_check(plans, n_res, B, T)) return rc;
+  PeerDev peer;
+  if (int rc = peer_dev(pr, &peer)) return rc;
+  if (pr && !loss) return fail(SB200_ERR_INVALID, "mstft_forward_ddp: the loss reduction needs the loss");
   if (!y || !y_g || !saved || !workspace) return fail(SB200_ERR_INVALID, "mstft_forward: null argument");
   if (!loss && !specs_r && !specs_g) return fail(SB200_ERR_INVALID, "mstft_forward: neither loss nor specs requested (loss.py:62 raises)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   char* ws = static_cast<char*>(workspace);
   const int64_t part0 = mstft_ws_gfb_off(plans, n_res, B, T);
-  if (mstft_single_enabled()) {
+  if (mstft_single_enabled() && !pr) {
     MstftAllFwdArgs A{};
     A.n_res = n_res;
     A.fin.n_res = n_res;
@@ -330,11 +350,12 @@ int sb200_mstft_forward(const sb200_plan* const* plans, int32_t n_res, const flo
       return check_launch("mstft_all_fwd_kernel");
     }
   }
-  if (!mstft_streams_enabled()) {   // default: the resolutions' grids concatenated into one launch
+  if (!mstft_streams_enabled() || pr) {   // default: the resolutions' grids concatenated into one launch
     MstftMultiFwdArgs A{};
     MstftFinArgs fin{};
     A.n_res = fin.n_res = n_res;
     fin.loss = loss;
+    fin.peer = peer;
     int total = 0;
     long long subs[kMaxRes];
     for (int r = 0; r < n_res; ++r) {
@@ -414,12 +435,13 @@ int sb200_mstft_forward(const sb200_plan* const* plans, int32_t n_res, const flo
 // also reduces the loss partial sums when `loss` is set).
 static int mstft_multi_bwd(const sb200_plan* const* plans, int32_t n_res, const float* y, const float* y_g, int32_t B, int64_t T,
                            int32_t phd_phase, const float* g_loss, const float* const* g_specs_g, const void* saved, float* loss,
-                           float* g_yg, char* ws, bool fused, cudaStream_t st) {
+                           float* g_yg, char* ws, bool fused, cudaStream_t st, const PeerDev& peer = PeerDev{}) {
   MstftMultiBwdArgs A{};
   MstftFinArgs fin{};
   GradOlaArgs o{};
   A.n_res = fin.n_res = o.n_res = n_res;
   fin.loss = loss;
+  fin.peer = peer;
   o.B = B;
   o.T = T;
   o.g = g_yg;
@@ -524,18 +546,21 @@ int sb200_mstft_backward(const sb200_plan* const* plans, int32_t n_res, const fl
 // Loss value AND d loss / d y_g in one pass (one launch per resolution + overlap-add + reduction): the loss-only training
 // step of retunegan/train.py:165,192 without a second analysis in backward.  grad_yg [B, T] is the gradient for a unit
 // upstream gradient; the autograd wrapper scales it by the incoming gradient.
-int sb200_mstft_loss_and_grad(const sb200_plan* const* plans, int32_t n_res, const float* y, const float* y_g, int32_t B,
-                              int64_t T, float* loss, float* grad_yg, void* workspace, sb200_stream stream) {
+static int mstft_loss_and_grad_impl(const sb200_plan* const* plans, int32_t n_res, const float* y, const float* y_g, int32_t B,
+                                    int64_t T, float* loss, float* grad_yg, void* workspace, const sb200_peer_reduce* pr,
+                                    sb200_stream stream) {
   if (int rc = mstft_check(plans, n_res, B, T)) return rc;
   if (!y || !y_g || !loss || !grad_yg || !workspace) return fail(SB200_ERR_INVALID, "mstft_loss_and_grad: null argument");
+  PeerDev peer;
+  if (int rc = peer_dev(pr, &peer)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   char* ws = static_cast<char*>(workspace);
-  {
+  if (!pr) {
     const int rc = mstft_all_bwd(plans, n_res, y, y_g, B, T, 0, nullptr, nullptr, nullptr, loss, grad_yg, ws, true, st);
     if (rc <= 0) return rc;
   }
-  if (!mstft_streams_enabled())
-    return mstft_multi_bwd(plans, n_res, y, y_g, B, T, 0, nullptr, nullptr, nullptr, loss, grad_yg, ws, true, st);
+  if (!mstft_streams_enabled() || pr)
+    return mstft_multi_bwd(plans, n_res, y, y_g, B, T, 0, nullptr, nullptr, nullptr, loss, grad_yg, ws, true, st, peer);
   std::lock_guard<std::mutex> enqueue_lock(g_mstft_enqueue_mu);
   const int64_t part0 = mstft_ws_gfb_off(plans, n_res, B, T);
   MstftFinArgs fin{};
@@ -574,6 +599,77 @@ int sb200_mstft_loss_and_grad(const sb200_plan* const* plans, int32_t n_res, con
   dim3 grid(grid_for((T + 3) / 4, 256, 2) + 1, B);
   grad_ola_kernel<<<grid, 256, 0, st>>>(o, fin);   // the extra block column reduces the loss partial sums
   return check_launch("grad_ola_kernel");
+}
+
+int sb200_mstft_forward(const sb200_plan* const* plans, int32_t n_res, const float* y, const float* y_g, int32_t B,
+                        int64_t T, int32_t phd_phase, float* loss, float* const* specs_r, float* const* specs_g,
+                        void* saved, void* workspace, sb200_stream stream) {
+  return mstft_forward_impl(plans, n_res, y, y_g, B, T, phd_phase, loss, specs_r, specs_g, saved, workspace, nullptr, stream);
+}
+int sb200_mstft_forward_ddp(const sb200_plan* const* plans, int32_t n_res, const float* y, const float* y_g, int32_t B,
+                            int64_t T, int32_t phd_phase, float* loss, float* const* specs_r, float* const* specs_g,
+                            void* saved, void* workspace, const sb200_peer_reduce* peers, sb200_stream stream) {
+  if (!peers) return fail(SB200_ERR_INVALID, "mstft_forward_ddp: null peer descriptor");
+  return mstft_forward_impl(plans, n_res, y, y_g, B, T, phd_phase, loss, specs_r, specs_g, saved, workspace, peers, stream);
+}
+int sb200_mstft_loss_and_grad(const sb200_plan* const* plans, int32_t n_res, const float* y, const float* y_g, int32_t B,
+                              int64_t T, float* loss, float* grad_yg, void* workspace, sb200_stream stream) {
+  return mstft_loss_and_grad_impl(plans, n_res, y, y_g, B, T, loss, grad_yg, workspace, nullptr, stream);
+}
+int sb200_mstft_loss_and_grad_ddp(const sb200_plan* const* plans, int32_t n_res, const float* y, const float* y_g, int32_t B,
+                                  int64_t T, float* loss, float* grad_yg, void* workspace, const sb200_peer_reduce* peers,
+                                  sb200_stream stream) {
+  if (!peers) return fail(SB200_ERR_INVALID, "mstft_loss_and_grad_ddp: null peer descriptor");
+  return mstft_loss_and_grad_impl(plans, n_res, y, y_g, B, T, loss, grad_yg, workspace, peers, stream);
+}
+
+// ---- exchange buffers of the in-kernel loss reduction (mstft.cuh: PeerBuf) ---------------------------------------------------
+int64_t sb200_peer_buffer_bytes(void) { return static_cast<int64_t>(sizeof(PeerBuf)); }
+int sb200_peer_buffer_create(void** buf, void* ipc_handle) {
+  if (!buf) return fail(SB200_ERR_INVALID, "peer_buffer_create: null argument");
+  void* d = nullptr;
+  cudaError_t e = cudaMalloc(&d, sizeof(PeerBuf));   // cudaMalloc, not a pool: the allocation is exported through CUDA IPC
+  if (e == cudaSuccess) e = cudaMemset(d, 0, sizeof(PeerBuf));
+  if (e == cudaSuccess && ipc_handle) {
+    cudaIpcMemHandle_t h;
+    static_assert(sizeof(h) == 64, "CUDA IPC handle size");
+    e = cudaIpcGetMemHandle(&h, d);
+    if (e == cudaSuccess) std::memcpy(ipc_handle, &h, sizeof(h));
+  }
+  if (e != cudaSuccess) {
+    if (d) cudaFree(d);
+    cudaGetLastError();
+    return fail(SB200_ERR_CUDA, std::string("peer_buffer_create: ") + cudaGetErrorString(e));
+  }
+  *buf = d;
+  return SB200_OK;
+}
+int sb200_peer_buffer_open(const void* ipc_handle, void** buf) {
+  if (!ipc_handle || !buf) return fail(SB200_ERR_INVALID, "peer_buffer_open: null argument");
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, ipc_handle, sizeof(h));
+  void* d = nullptr;
+  const cudaError_t e = cudaIpcOpenMemHandle(&d, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(SB200_ERR_CUDA, std::string("peer_buffer_open: ") + cudaGetErrorString(e));
+  }
+  *buf = d;
+  return SB200_OK;
+}
+int sb200_peer_buffer_close(void* buf) {
+  if (buf && cudaIpcCloseMemHandle(buf) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(SB200_ERR_CUDA, "peer_buffer_close failed");
+  }
+  return SB200_OK;
+}
+int sb200_peer_buffer_destroy(void* buf) {
+  if (buf && cudaFree(buf) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(SB200_ERR_CUDA, "peer_buffer_destroy failed");
+  }
+  return SB200_OK;
 }
 
 // ---- get_stft_torch, differentiable (retunegan/audio.py:150-170) ------------------------------------------------------------

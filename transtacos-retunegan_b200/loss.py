@@ -49,6 +49,104 @@ def _setup(cfg: SpectralConfig, dev, B: int, T: int):
     return hit
 
 
+class PeerLossReducer:
+    """Exchange buffers for the in-kernel mean of the loss over the ranks of one box (include/spectral_b200.h, "DDP: the loss
+    averaged over the ranks ... INSIDE the reducing kernel").  Building one is a COLLECTIVE over the default process group: every
+    rank allocates its buffer, the CUDA IPC handles travel by ``all_gather_object`` and each rank maps the others' buffers
+    (NVLink peer access).  ``peers`` (single-process use, tests): the buffers of all ranks as raw device pointers."""
+
+    def __init__(self, rank: int, world: int, peers=None):
+        lib = _lib.load()
+        self.rank, self.world = int(rank), int(world)
+        if not 1 <= self.world <= _lib.MAX_PEERS:
+            raise ValueError(f"in-kernel loss reduction needs 1 <= world <= {_lib.MAX_PEERS}")
+        self._own, self._opened = None, []
+        if peers is not None:
+            self.ptrs = [int(p) for p in peers]
+            return
+        import socket
+        import torch.distributed as dist
+        own, handle = C.c_void_p(), (C.c_ubyte * 64)()
+        _lib.check(lib.sb200_peer_buffer_create(C.byref(own), handle), "peer_buffer_create")
+        self._own = own
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, (socket.gethostname(), bytes(handle)))
+        ok, self.ptrs = len({h for h, _ in gathered}) == 1, []          # CUDA IPC: one host
+        for q, (_, hb) in enumerate(gathered):
+            if q == self.rank:
+                self.ptrs.append(own.value)
+                continue
+            p = C.c_void_p()
+            if ok and lib.sb200_peer_buffer_open((C.c_ubyte * 64).from_buffer_copy(hb), C.byref(p)) == 0:
+                self._opened.append(p)
+                self.ptrs.append(p.value)
+            else:
+                ok = False
+                self.ptrs.append(0)
+        flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)                       # every rank mapped every buffer, or nobody uses them
+        if flag.item() < 1.0:
+            self.close()
+            raise RuntimeError("peer exchange buffers could not be mapped on every rank")
+
+    @staticmethod
+    def create_buffer() -> int:
+        """One zeroed exchange buffer in this process (single-process use); free it with ``destroy_buffer``."""
+        p = C.c_void_p()
+        _lib.check(_lib.load().sb200_peer_buffer_create(C.byref(p), None), "peer_buffer_create")
+        return p.value
+
+    @staticmethod
+    def destroy_buffer(ptr: int) -> None:
+        _lib.check(_lib.load().sb200_peer_buffer_destroy(C.c_void_p(ptr)), "peer_buffer_destroy")
+
+    def descriptor(self, loss_global: torch.Tensor) -> "_lib.PeerReduce":
+        d = _lib.PeerReduce()
+        for q, p in enumerate(self.ptrs):
+            d.peer[q] = p
+        d.rank, d.world, d.loss_global = self.rank, self.world, loss_global.data_ptr()
+        return d
+
+    def close(self) -> None:
+        lib = _lib.load()
+        for p in self._opened:
+            lib.sb200_peer_buffer_close(p)
+        self._opened = []
+        if self._own is not None:
+            lib.sb200_peer_buffer_destroy(self._own)
+            self._own = None
+
+
+_peer_reducers = {}
+
+
+def ddp_loss_reducer():
+    """The process group's PeerLossReducer on the current device, built on first use (collectively: every rank calls
+    ``multi_stft_loss(..., ddp_reduce=True)`` the same way), or None when the job is not one NCCL box of <= 8 ranks or the
+    mapping failed -- then the loss is reduced with an NCCL all-reduce of a scalar.  ``SB200_DDP_PEER=0`` forces that path."""
+    import os
+    import torch.distributed as dist
+    if os.environ.get("SB200_DDP_PEER", "1") == "0" or not (dist.is_available() and dist.is_initialized()):
+        return None
+    if dist.get_backend() != "nccl" or not torch.cuda.is_available():
+        return None
+    key = torch.cuda.current_device()
+    if key not in _peer_reducers:
+        red = None
+        if 1 < dist.get_world_size() <= _lib.MAX_PEERS:
+            try:
+                red = PeerLossReducer(dist.get_rank(), dist.get_world_size())
+            except Exception:      # not one box, no peer access, IPC unavailable: every rank lands here together (MIN all-reduce)
+                red = None
+        _peer_reducers[key] = red
+    return _peer_reducers[key]
+
+
+def ddp_reduce_path() -> str:
+    """Which way ``ddp_reduce=True`` takes in this process (for logs / bench.py)."""
+    return "in-kernel exchange over NVLink peer memory" if ddp_loss_reducer() is not None else "NCCL all-reduce of one scalar"
+
+
 def _ptr_array(tensors):
     arr = (C.c_void_p * len(tensors))()
     for i, t in enumerate(tensors):
@@ -69,7 +167,7 @@ class _MultiStftFn(torch.autograd.Function):
     backward node they add are skipped: the kernels only need the row pointer, B and T)."""
 
     @staticmethod
-    def forward(ctx, y, y_g, cfg: SpectralConfig, want_loss: bool, want_specs: bool):
+    def forward(ctx, y, y_g, cfg: SpectralConfig, want_loss: bool, want_specs: bool, reducer=None):
         lib = _lib.load()
         dev = core.require_cuda()
         ctx.set_materialize_grads(False)   # no zero-filled gradients for outputs nobody differentiated (the real-audio stacks)
@@ -84,8 +182,15 @@ class _MultiStftFn(torch.autograd.Function):
             ws = core._workspace(int(ws_bytes), dev, "mstft")
             loss = torch.empty((), device=dev, dtype=torch.float32)
             grad = torch.empty((B, T), device=dev, dtype=torch.float32)
-            _lib.check(lib.sb200_mstft_loss_and_grad(handles, n_res, core.ptr(yc), core.ptr(gc), B, T, core.ptr(loss),
-                                                     core.ptr(grad), core.ptr(ws), core.stream_ptr()), "mstft_loss_and_grad")
+            if reducer is None:
+                _lib.check(lib.sb200_mstft_loss_and_grad(handles, n_res, core.ptr(yc), core.ptr(gc), B, T, core.ptr(loss),
+                                                         core.ptr(grad), core.ptr(ws), core.stream_ptr()), "mstft_loss_and_grad")
+            else:   # DDP: the value handed out is the mean over the ranks (reduced inside the launch), the gradient the local one
+                mean = torch.empty((), device=dev, dtype=torch.float32)
+                _lib.check(lib.sb200_mstft_loss_and_grad_ddp(handles, n_res, core.ptr(yc), core.ptr(gc), B, T, core.ptr(loss),
+                                                             core.ptr(grad), core.ptr(ws), C.byref(reducer.descriptor(mean)),
+                                                             core.stream_ptr()), "mstft_loss_and_grad_ddp")
+                loss = mean
             ctx.in_shape, ctx.in_dtype = y_g.shape, y_g.dtype
             ctx.save_for_backward(grad)
             return (loss,)
@@ -97,10 +202,19 @@ class _MultiStftFn(torch.autograd.Function):
             specs_r = [torch.empty((B, 2, 1 + T // p.hop_length, p.F), device=dev, dtype=torch.float32) for p in plans]
             specs_g = [torch.empty_like(s) for s in specs_r]
         phd_phase = int(cfg.phd_input == "phase")
-        _lib.check(lib.sb200_mstft_forward(handles, n_res, core.ptr(yc), core.ptr(gc), B, T, phd_phase, core.ptr(loss),
-                                           _ptr_array(specs_r) if want_specs else None,
-                                           _ptr_array(specs_g) if want_specs else None,
-                                           core.ptr(saved), core.ptr(ws), core.stream_ptr()), "mstft_forward")
+        if reducer is None or not want_loss:
+            _lib.check(lib.sb200_mstft_forward(handles, n_res, core.ptr(yc), core.ptr(gc), B, T, phd_phase, core.ptr(loss),
+                                               _ptr_array(specs_r) if want_specs else None,
+                                               _ptr_array(specs_g) if want_specs else None,
+                                               core.ptr(saved), core.ptr(ws), core.stream_ptr()), "mstft_forward")
+        else:
+            mean = torch.empty((), device=dev, dtype=torch.float32)
+            _lib.check(lib.sb200_mstft_forward_ddp(handles, n_res, core.ptr(yc), core.ptr(gc), B, T, phd_phase, core.ptr(loss),
+                                                   _ptr_array(specs_r) if want_specs else None,
+                                                   _ptr_array(specs_g) if want_specs else None,
+                                                   core.ptr(saved), core.ptr(ws), C.byref(reducer.descriptor(mean)),
+                                                   core.stream_ptr()), "mstft_forward_ddp")
+            loss = mean
         ctx.cfg, ctx.plans, ctx.handles, ctx.ws_bytes = cfg, plans, handles, ws_bytes
         ctx.shape = (B, T)
         ctx.want_loss, ctx.want_specs, ctx.phd_phase = want_loss, want_specs, phd_phase
@@ -120,11 +234,11 @@ class _MultiStftFn(torch.autograd.Function):
             (grad,) = ctx.saved_tensors
             g0 = grads[0]
             if g0 is None:
-                return None, None, None, None, None
+                return None, None, None, None, None, None
             if g0.dtype is not torch.float32 or g0.device != grad.device:
                 g0 = g0.to(device=grad.device, dtype=torch.float32)
             g = (g0 * grad).view(ctx.in_shape)
-            return None, (g if ctx.in_dtype is torch.float32 else g.to(ctx.in_dtype)), None, None, None
+            return None, (g if ctx.in_dtype is torch.float32 else g.to(ctx.in_dtype)), None, None, None, None
         lib = _lib.load()
         gc, saved = ctx.saved_tensors
         B, T = ctx.shape
@@ -148,7 +262,7 @@ class _MultiStftFn(torch.autograd.Function):
                                             _ptr_array(g_specs) if g_specs is not None else None, core.ptr(saved),
                                             core.ptr(g_yg), core.ptr(ws), core.stream_ptr()), "mstft_backward")
         g_yg = g_yg.view(ctx.in_shape)
-        return None, (g_yg if ctx.in_dtype is torch.float32 else g_yg.to(ctx.in_dtype)), None, None, None
+        return None, (g_yg if ctx.in_dtype is torch.float32 else g_yg.to(ctx.in_dtype)), None, None, None, None
 
 
 class _GlobalMean(torch.autograd.Function):
@@ -174,14 +288,16 @@ def multi_stft_loss(y, y_g, ret_loss=False, ret_specs=False, ddp_reduce=False):
         raise RuntimeError(f"unknown phd_input {hp.phd_input!r}")               # bare `raise` at loss.py:48
     if y.shape != y_g.shape or not (y.dim() == 2 or (y.dim() == 3 and y.shape[1] == 1)):   # [B, 1, T] is taken as [B, T]
         raise ValueError(f"expected matching [B, T] / [B, 1, T] inputs, got {tuple(y.shape)} and {tuple(y_g.shape)}")
-    outs = _MultiStftFn.apply(y, y_g, hp, bool(ret_loss), bool(ret_specs))
+    ddp = bool(ddp_reduce and ret_loss and torch.distributed.is_available() and torch.distributed.is_initialized())
+    reducer = ddp_loss_reducer() if ddp else None
+    outs = _MultiStftFn.apply(y, y_g, hp, bool(ret_loss), bool(ret_specs), reducer)
     n_res = len(hp.multi_stft_params)
     i = 0
     loss = None
     if ret_loss:
         loss = outs[0]
         i = 1
-        if ddp_reduce and torch.distributed.is_available() and torch.distributed.is_initialized():
+        if ddp and reducer is None:
             loss = _GlobalMean.apply(loss)   # value = global mean, grad = local
     if ret_specs:
         stft_r = [s.transpose(2, 3) for s in outs[i:i + n_res]]
