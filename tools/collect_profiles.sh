@@ -17,8 +17,8 @@ cap() {   # name, kernel regex, skip, count, workload
 }
 cap feat3 stft_feature3 3 1 stft_mel
 cap gl2_batch gl2_kernel 8 2 griffinlim_batch
-cap mstft_fused mstft_bwd 9 3 mstft
-cap mstft_specs mstft_ 18 8 mstft_specs
+cap mstft_fused mstft_multi_bwd 3 1 mstft
+cap mstft_specs mstft_multi 6 2 mstft_specs
 # ablations of the feature kernel (variants built by tools/variants.py): what the analysis role costs on its own, and without the mel
 for v in noepi nomel; do
   r=$(SB200_BENCH_NO_CHECK=1 SB200_LIB=$PWD/scratch/var_$v.so python bench.py --no-extra --kernel-only --steps 300 2>/dev/null | python -c "import json,sys; print(round(json.loads(sys.stdin.read())['ms_per_step']*1e3,2))" 2>/dev/null)

@@ -9,7 +9,7 @@ rows = [("STFT+mel 64 × 5 s per GPU (weak), device resident", [L[n]["value"] fo
         ("same, end to end from / to pinned host memory", [L[n]["e2e"]["value"] for n in (1, 2, 8)])]
 for k, name in (("griffinlim_rtg_64x5s_4it", "Griffin-Lim 64 × 5 s × 4 it per GPU (weak)"),
                 ("griffinlim_tt_1x5s_30it", "Griffin-Lim 1 × 5 s × 30 it per GPU (weak)"),
-                ("mstft_fwd_bwd_16x22050_lossonly", "mstft loss-only, 16 × 1 s per GPU (weak; DDP scalar all-reduce inside the step at N > 1)"),
+                ("mstft_fwd_bwd_16x22050_lossonly", "mstft loss-only, 16 × 1 s per GPU (weak; at N > 1 the loss is averaged over the ranks inside the step, in-kernel over NVLink peer memory)"),
                 ("mstft_fwd_bwd_16x22050_specs", "mstft training variant (weak)"),
                 ("corpus_10000utt_specs+griffinlim", "corpus 10 000 utterances (STRONG), resident"),
                 ("corpus_10000utt_specs+griffinlim_d2h", "corpus (STRONG), features + wavs copied to pinned host memory")):

@@ -101,7 +101,7 @@ def main():
     traffic = {"_source": "ncu --set full --clock-control none captures of round 2 (tools/collect_profiles.sh, summarised by "
                           "tools/summarise_profiles.py): dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel"}
     dominant = {"feat3": ("stft_mel", "stft_feature3"), "gl2_batch": ("griffinlim_batch", "gl2_kernel"),
-                "mstft_fused": ("mstft", "mstft_bwd"), "mstft_specs": ("mstft_specs", "mstft_")}
+                "mstft_fused": ("mstft", "mstft_multi_bwd"), "mstft_specs": ("mstft_specs", "mstft_multi")}
     for cap, (workload, pat) in dominant.items():
         raw = os.path.join(EV, f"ncu_{cap}_raw.csv")
         if not os.path.exists(raw):
@@ -182,7 +182,7 @@ def main():
                      "fp32 (Blackwell), SYNCS = mbarrier, UTMALDG = bulk-tensor (TMA) load, USETMAXREG = setmaxnreg.\n\n")
             for (name, ops), dn in zip(funcs.items(), demangle):
                 if not any(k in name for k in ("stft_feature3", "stft_feature2_kernelILi1024", "gl2_kernelILi2048ELi3", "gl2_persistent",
-                                               "mstft_bwd_kernelILi2048", "mstft_fwd_kernelILi2048", "mstft_all", "stft_smp_kernelILi2048", "yin")):
+                                               "mstft_multi", "mstft_bwd_kernelILi2048", "mstft_fwd_kernelILi2048", "mstft_all", "stft_smp_kernelILi2048", "yin", "grad_ola")):
                     continue
                 fo.write(f"{short(dn)}  [{sum(ops.values())} instructions]\n  " + "  ".join(f"{k}:{v}" for k, v in ops.most_common(36)) + "\n\n")
     print("wrote", sorted(f for f in os.listdir(OUT) if f.startswith("r02_") or f == "traffic.json"))
