@@ -37,6 +37,10 @@ def _worker(rank, world, port, q):
     local_loss = torch.tensor(float(rank + 1))
     mean = sb.sharding.reduce_mean_scalar(local_loss)
     assert sb.sharding.rank_world() == (rank, world)
+    # the in-kernel exchange over NVLink peer memory is an NCCL-box path: on gloo / without CUDA ddp_reduce takes the all-reduce
+    assert sb.loss.ddp_loss_reducer() is None and sb.loss.ddp_reduce_path() == "NCCL all-reduce of one scalar"
+    red = sb.loss._GlobalMean.apply(local_loss.clone().requires_grad_(True))     # value = mean over the ranks, gradient = local
+    assert abs(float(red) - (world + 1) / 2) < 1e-12
     q.put((rank, mine, sums, lo, hi, float(mean)))
     dist.barrier()
     dist.destroy_process_group()
