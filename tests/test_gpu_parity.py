@@ -726,3 +726,21 @@ def test_in_kernel_loss_reduction_two_ranks_on_one_device(sb, specs):
         torch.cuda.synchronize()
         for b in bufs:
             L.PeerLossReducer.destroy_buffer(b)
+
+
+def test_spec_stacks_of_digital_silence(sb):
+    """torch.stft of an all-zero segment is all (+0): the reference's stacks hold ln|0 + 1e-9| and angle(0) = 0 there
+    (retunegan/audio.py:166-168, loss.py:38-40).  The rotation (-i)^k of the engine's internal form must not turn that into
+    angle(-0) = pi."""
+    T = 8192
+    y = torch.from_numpy(np.stack([O.synth_noise(T, 1), np.zeros(T, np.float32)])).cuda()
+    yg = torch.from_numpy(np.stack([np.zeros(T, np.float32), O.synth_noise(T, 2)])).cuda()
+    sr, sg = sb.multi_stft_loss(y, yg, ret_specs=True)
+    for st, row in ((sr, 1), (sg, 0)):
+        for s in st:
+            z = s[row].cpu().numpy()
+            assert np.all(z[1] == 0.0), np.abs(z[1]).max()                         # angle(0) / PI
+            np.testing.assert_allclose(z[0], np.log(1e-9), rtol=0, atol=2e-6)      # ln|0 + 1e-9|
+    n_fft, win, hop = O.HP.multi_stft_params[0]
+    S, M, P = sb.retunegan_audio.get_stft_torch(y, n_fft, win, hop)
+    assert torch.all(P[1] == 0) and torch.allclose(S[1], torch.full_like(S[1], 1e-9), rtol=1e-6, atol=0)

@@ -27,12 +27,12 @@ constexpr int kMaxRes = 4;
 constexpr int kMstftUnroll = SB200_MSTFT_UNROLL;
 
 // atan2f to ~3e-7 rad: octant reduction with one approximate division, degree-7 minimax polynomial in a^2 (fitted in double,
-// evaluated in float: max error 1.4e-7 on [0, 1]), same results as atan2f at the axes and for signed zeros.  The library atan2f
+// evaluated in float: max error 1.4e-7 on [0, 1]), same results as atan2f at the axes; atan2(+-0, -0) is taken as +-0.  The library atan2f
 // (IEEE division with a slow path) and logf were a seventh of the forward kernel's instructions at two calls per bin.
 __device__ __forceinline__ float fast_atan2(float y, float x) {
   const float ax = fabsf(x), ay = fabsf(y);
   const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-  const float a = mx > 0.f ? __fdividef(mn, mx) : 0.f;
+  const float a = __fdividef(mn, fmaxf(mx, 1e-37f));   // 0 / 1e-37 = 0 at the origin
   const float s = a * a;
   float r = -0.0040545654483139515f;
   r = fmaf(r, s, 0.021862952038645744f);
@@ -44,7 +44,8 @@ __device__ __forceinline__ float fast_atan2(float y, float x) {
   r = fmaf(r, s, 0.9999993443489075f);
   r *= a;
   if (ay > ax) r = 1.57079632679489662f - r;
-  if (__float_as_int(x) < 0) r = 3.14159265358979324f - r;   // sign bit: atan2f(+-0, -0) = +-pi
+  if (x < 0.f) r = 3.14159265358979324f - r;   // not the sign bit: a zero spectrum (digital silence) has phase 0 whatever the sign
+                                               // of its zeros, as torch.angle of the reference's all-(+0) torch.stft output
   return copysignf(r, y);
 }
 
@@ -85,6 +86,32 @@ __device__ __forceinline__ void mstft_analyse(const PlanDev& p, const SmemTables
         if (ch0_alias) ch0_alias[row + k] = __logf(S);
         if (ch1) ch1[row + ch_stride + k] = RAW ? fast_atan2(X.y, X.x) : fast_atan2(X.y, X.x) * (1.f / kRefPI);
       };
+      if (!RAW && ch0 != nullptr && ch1 != nullptr && ch0_alias == nullptr) {
+        // the training step's case (both channels of one stack): no per-bin pointer tests, the quarter-turn (-i)^k as a
+        // multiplication by the lane's constant (c, s) in {(1,0), (0,1), (-1,0), (0,-1)} instead of selects, two row pointers.
+        // Same values as the general loop below (products with 0 and +-1 are exact; only the sign of a zero can differ).
+        float* const p0 = ch0 + row;
+        float* const p1 = ch1 + row + ch_stride;
+        const float ck = (rk == 0) ? 1.f : (rk == 2 ? -1.f : 0.f), sk_ = (rk == 1) ? 1.f : (rk == 3 ? -1.f : 0.f);
+        const float cm = (rm == 0) ? 1.f : (rm == 2 ? -1.f : 0.f), sm_ = (rm == 1) ? 1.f : (rm == 3 ? -1.f : 0.f);
+#pragma unroll 2
+        for (int i = 0; i < C::kPairIters; ++i) {
+          const int k = lane + 32 * i;
+          const int km = (C::kNz - k) & (C::kNz - 1);
+          float2 Ak, Am;
+          split_fwd(zq[k], zq[km], sm.ws[k], Ak, Am);
+          const float2 Xk = make_float2(fmaf(sk_, Ak.y, ck * Ak.x), fmaf(-sk_, Ak.x, ck * Ak.y));
+          const float2 Xm = make_float2(fmaf(sm_, Am.y, cm * Am.x), fmaf(-sm_, Am.x, cm * Am.y));
+          const float rek = Xk.x + 1e-9f, rem = Xm.x + 1e-9f;
+          const float sk = fast_sqrt(fmaf(rek, rek, Xk.y * Xk.y)), smg = fast_sqrt(fmaf(rem, rem, Xm.y * Xm.y));
+          zq[k].x = sk;
+          if (k != 0) zq[km].x = smg;
+          p0[k] = __logf(sk);
+          p0[C::kNz - k] = __logf(smg);
+          p1[k] = fast_atan2(Xk.y, Xk.x) * (1.f / kRefPI);
+          p1[C::kNz - k] = fast_atan2(Xm.y, Xm.x) * (1.f / kRefPI);
+        }
+      } else {
 #pragma unroll 2
       for (int i = 0; i < C::kPairIters; ++i) {
         const int k = lane + 32 * i;
@@ -98,6 +125,7 @@ __device__ __forceinline__ void mstft_analyse(const PlanDev& p, const SmemTables
         if (k != 0) zq[km].x = smg;
         emit(Xk, k, sk);
         emit(Xm, C::kNz - k, smg);
+      }
       }
       if (lane == 0) {
         constexpr int k = C::kNz / 2;
