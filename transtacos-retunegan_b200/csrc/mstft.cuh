@@ -440,6 +440,9 @@ __device__ __forceinline__ void mstft_bwd_body(const PlanDev& p, const MstftBwdA
   auto nyq = [](int q) { return C::kZS > C::kNz ? q * C::kZS + C::kNz : C::kQ * C::kZS + q; };
   static_assert(C::kZS > C::kNz || C::kQ * C::kZS + C::kQ <= C::kBufF2, "no room for the Nyquist bins");
   const int rk = lane & 3, rm = (4 - rk) & 3;
+  // quarter turns as constants: (-i)^j (x + i y) = (c x + s y) + i (c y - s x), i^j (x + i y) = (c x - s y) + i (c y + s x)
+  const float rck = (rk == 0) ? 1.f : (rk == 2 ? -1.f : 0.f), rsk = (rk == 1) ? 1.f : (rk == 3 ? -1.f : 0.f);
+  const float rcm = (rm == 0) ? 1.f : (rm == 2 ? -1.f : 0.f), rsm = (rm == 1) ? 1.f : (rm == 3 ? -1.f : 0.f);
   const float gl = FUSED ? a.loss_scale : (a.g_loss ? __ldg(a.g_loss) * a.loss_scale : 0.f);
   float loss_acc = 0.f;
   const long long chs = static_cast<long long>(a.Tf) * C::kF;
@@ -473,7 +476,8 @@ __device__ __forceinline__ void mstft_bwd_body(const PlanDev& p, const MstftBwdA
           const int km = (C::kNz - k) & (C::kNz - 1);
           float2 Ak, Am;
           split_fwd(zq[k], zq[km], sm.ws[k], Ak, Am);
-          const float2 xk = rot_fwd(Ak, rk), xm = rot_fwd(Am, rm);
+          const float2 xk = make_float2(fmaf(rsk, Ak.y, rck * Ak.x), fmaf(-rsk, Ak.x, rck * Ak.y));
+          const float2 xm = make_float2(fmaf(rsm, Am.y, rcm * Am.x), fmaf(-rsm, Am.x, rcm * Am.y));
           if (FUSED && side == 0) {   // the real signal: only |X + 1e-9| is needed (the Nyquist bin carries no mel weight)
             const float rek = xk.x + 1e-9f, rem = xm.x + 1e-9f;
             zq[k].x = fast_sqrt(fmaf(rek, rek, xk.y * xk.y));
@@ -546,8 +550,8 @@ __device__ __forceinline__ void mstft_bwd_body(const PlanDev& p, const MstftBwdA
     const bool s_div = !a.raw;                              // spec stacks hold ln S: d ln S / dS = 1 / S
     const float p_scale = a.raw ? 1.f : 1.f / kRefPI;       // and angle / PI
     auto grad_bin = [&](float2 X, int q, float half, int r0, float c0, float c1, float us, float up) -> float2 {
-      float2 G = make_float2(0.f, 0.f);
-      if (it.t0 + q < it.T) {
+      float2 G;
+      {   // (the frame is valid: frames past the end of the utterance are zero-filled by the caller)
         const float re = X.x + 1e-9f;
         const float S = fast_sqrt(fmaf(re, re, X.y * X.y));
         float gS = fmaf(c0, gmbuf[q * 128 + r0], c1 * gmbuf[q * 128 + r0 + 1]);
@@ -568,21 +572,29 @@ __device__ __forceinline__ void mstft_bwd_body(const PlanDev& p, const MstftBwdA
     // upstream gradients of the pair (k, Nz - k), k = lane + 32 i, of frame q: loaded TWO iterations ahead of their use (they come
     // from L2 / HBM, and inside the iteration their latency sat on the dependent chain of the pair)
     struct Up { float sk, pk, sm, pm; };
-    auto load_up = [&](int q, int k) -> Up {
-      Up u{0.f, 0.f, 0.f, 0.f};
+    const float* ups = nullptr;   // rows of the current frame in the upstream magnitude-type / phase-type gradients (null: none)
+    const float* upp = nullptr;
+    auto set_up_rows = [&](int q) {
+      ups = upp = nullptr;
       if constexpr (!FUSED) {
         const long long t = it.t0 + q;
-        if (k < C::kNz && t < it.T) {
-          if (a.raw) {
-            const long long idx = (it.frame_base + t) * C::kF;
-            if (a.g_s_raw) { u.sk = __ldg(a.g_s_raw + idx + k); u.sm = __ldg(a.g_s_raw + idx + C::kNz - k); }
-            if (a.g_p_raw) { u.pk = __ldg(a.g_p_raw + idx + k); u.pm = __ldg(a.g_p_raw + idx + C::kNz - k); }
-          } else if (a.g_spec) {
-            const long long idx = (static_cast<long long>(it.b) * 2 * a.Tf + t) * C::kF;
-            if (!a.phd_phase) { u.sk = __ldg(a.g_spec + idx + k); u.sm = __ldg(a.g_spec + idx + C::kNz - k); }
-            u.pk = __ldg(a.g_spec + idx + chs + k);
-            u.pm = __ldg(a.g_spec + idx + chs + C::kNz - k);
-          }
+        if (a.raw) {
+          const long long idx = (it.frame_base + t) * C::kF;
+          if (a.g_s_raw) ups = a.g_s_raw + idx;
+          if (a.g_p_raw) upp = a.g_p_raw + idx;
+        } else if (a.g_spec) {
+          const long long idx = (static_cast<long long>(it.b) * 2 * a.Tf + t) * C::kF;
+          if (!a.phd_phase) ups = a.g_spec + idx;
+          upp = a.g_spec + idx + chs;
+        }
+      }
+    };
+    auto load_up = [&](int k) -> Up {
+      Up u{0.f, 0.f, 0.f, 0.f};
+      if constexpr (!FUSED) {
+        if (k < C::kNz) {
+          if (ups) { u.sk = __ldg(ups + k); u.sm = __ldg(ups + C::kNz - k); }
+          if (upp) { u.pk = __ldg(upp + k); u.pm = __ldg(upp + C::kNz - k); }
         }
       }
       return u;
@@ -596,7 +608,9 @@ __device__ __forceinline__ void mstft_bwd_body(const PlanDev& p, const MstftBwdA
       const float2 ck = colc[k], cm = colc[C::kNz - k];
       const float2 Gk = grad_bin(zq[k], q, half, r0k, ck.x, ck.y, u.sk, u.pk);
       const float2 Gm = grad_bin(k != 0 ? zq[km] : buf[nyq(q)], q, half, r0m, cm.x, cm.y, u.sm, u.pm);
-      float2 Bk = rot_inv(Gk, rk), Bm = rot_inv(Gm, rm);
+      // i^k G as a product with the lane's constant quarter turn (c, s): no selects
+      float2 Bk = make_float2(fmaf(-rsk, Gk.y, rck * Gk.x), fmaf(rsk, Gk.x, rck * Gk.y));
+      float2 Bm = make_float2(fmaf(-rsm, Gm.y, rcm * Gm.x), fmaf(rsm, Gm.x, rcm * Gm.y));
       if (k == 0) { Bk.y = 0.f; Bm.y = 0.f; }
       float2 Zk, Zr;
       split_inv(Bk, Bm, sm.ws[k], Zk, Zr);
@@ -606,16 +620,27 @@ __device__ __forceinline__ void mstft_bwd_body(const PlanDev& p, const MstftBwdA
 #pragma unroll 1
     for (int q = 0; q < C::kQ; ++q) {
       float2* zq = buf + q * C::kZS;
+      if (it.t0 + q >= it.T) {   // frame past the end of the utterance: no gradient (the inverse transform of zeros)
+#pragma unroll 1
+        for (int i = 0; i < C::kPairIters; ++i) {
+          const int k = lane + 32 * i;
+          zq[k] = make_float2(0.f, 0.f);
+          zq[(C::kNz - k) & (C::kNz - 1)] = make_float2(0.f, 0.f);
+        }
+        if (lane == 0) zq[C::kNz / 2] = make_float2(0.f, 0.f);
+        continue;
+      }
+      set_up_rows(q);
       if constexpr (FUSED) {
 #pragma unroll kMstftUnroll
         for (int i = 0; i < C::kPairIters; ++i) pair_iter(zq, q, i, Up{0.f, 0.f, 0.f, 0.f});
       } else {
         static_assert(C::kPairIters % 2 == 0, "pair loop is unrolled by two");
-        Up u0 = load_up(q, lane), u1 = load_up(q, lane + 32);
+        Up u0 = load_up(lane), u1 = load_up(lane + 32);
 #pragma unroll 1
         for (int i = 0; i < C::kPairIters; i += 2) {
-          const Up n0 = load_up(q, lane + 32 * (i + 2) + (i + 2 < C::kPairIters ? 0 : C::kNz));
-          const Up n1 = load_up(q, lane + 32 * (i + 3) + (i + 3 < C::kPairIters ? 0 : C::kNz));
+          const Up n0 = load_up(lane + 32 * (i + 2) + (i + 2 < C::kPairIters ? 0 : C::kNz));
+          const Up n1 = load_up(lane + 32 * (i + 3) + (i + 3 < C::kPairIters ? 0 : C::kNz));
           pair_iter(zq, q, i, u0);
           pair_iter(zq, q, i + 1, u1);
           u0 = n0;
@@ -624,7 +649,7 @@ __device__ __forceinline__ void mstft_bwd_body(const PlanDev& p, const MstftBwdA
       }
       if (lane == 0) {
         constexpr int k = C::kNz / 2;
-        const Up u = load_up(q, k);   // the self pair: sm / pm address the same bin
+        const Up u = load_up(k);   // the self pair: sm / pm address the same bin
         const float2 B = rot_inv(grad_bin(zq[k], q, 0.5f, colr[k], colc[k].x, colc[k].y, u.sk, u.pk), k);
         float2 Zk, Zr;
         split_inv(B, B, sm.ws[k], Zk, Zr);
