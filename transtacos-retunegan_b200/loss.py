@@ -197,21 +197,34 @@ class _MultiStftFn(torch.autograd.Function):
         saved = torch.empty(int(saved_bytes), device=dev, dtype=torch.uint8)
         ws = core._workspace(int(ws_bytes), dev, "mstft")
         loss = torch.empty((), device=dev, dtype=torch.float32) if want_loss else None
-        specs_r = specs_g = None
+        specs_r = specs_g = ptrs_r = ptrs_g = None
         if want_specs:
-            specs_r = [torch.empty((B, 2, 1 + T // p.hop_length, p.F), device=dev, dtype=torch.float32) for p in plans]
-            specs_g = [torch.empty_like(s) for s in specs_r]
+            # ONE allocation for the six stacks; each is handed out directly as the [B, 2, F, T'] view (strides (2 T' F, T' F, 1, F))
+            # of its frame-major [B, 2, T', F] block: no per-stack allocation, no transpose op per stack and no TransposeBackward
+            # node per stack in backward -- on a step that is bound by the host these were a fifth of it
+            tfs = [1 + T // p.hop_length for p in plans]
+            sizes = [B * 2 * tf * p.F for tf, p in zip(tfs, plans)]
+            total = sum(sizes)
+            big = torch.empty(2 * total, device=dev, dtype=torch.float32)
+            base, offs, o = big.data_ptr(), [], 0
+            for n in sizes:
+                offs.append(o)
+                o += n
+            view = lambda off, tf, p: big.as_strided((B, 2, p.F, tf), (2 * tf * p.F, tf * p.F, 1, p.F), off)
+            specs_r = [view(off, tf, p) for off, tf, p in zip(offs, tfs, plans)]
+            specs_g = [view(total + off, tf, p) for off, tf, p in zip(offs, tfs, plans)]
+            ptrs_r = (C.c_void_p * n_res)(*[base + 4 * off for off in offs])
+            ptrs_g = (C.c_void_p * n_res)(*[base + 4 * (total + off) for off in offs])
+            ctx.spec_dims = [(tf, p.F) for tf, p in zip(tfs, plans)]
         phd_phase = int(cfg.phd_input == "phase")
         if reducer is None or not want_loss:
             _lib.check(lib.sb200_mstft_forward(handles, n_res, core.ptr(yc), core.ptr(gc), B, T, phd_phase, core.ptr(loss),
-                                               _ptr_array(specs_r) if want_specs else None,
-                                               _ptr_array(specs_g) if want_specs else None,
+                                               ptrs_r, ptrs_g,
                                                core.ptr(saved), core.ptr(ws), core.stream_ptr()), "mstft_forward")
         else:
             mean = torch.empty((), device=dev, dtype=torch.float32)
             _lib.check(lib.sb200_mstft_forward_ddp(handles, n_res, core.ptr(yc), core.ptr(gc), B, T, phd_phase, core.ptr(loss),
-                                                   _ptr_array(specs_r) if want_specs else None,
-                                                   _ptr_array(specs_g) if want_specs else None,
+                                                   ptrs_r, ptrs_g,
                                                    core.ptr(saved), core.ptr(ws), C.byref(reducer.descriptor(mean)),
                                                    core.stream_ptr()), "mstft_forward_ddp")
             loss = mean
@@ -255,7 +268,14 @@ class _MultiStftFn(torch.autograd.Function):
         if ctx.want_specs:
             gs = grads[i + n_res: i + 2 * n_res]
             if any(g is not None for g in gs):
-                g_specs = [None if g is None else _as_rows(g, dev) for g in gs]
+                # the kernels read frame-major [B, 2, T', F] memory: a gradient that already has it behind its [B, 2, F, T'] shape
+                # is used in place, anything else (e.g. a contiguous [B, 2, F, T'] gradient out of a convolution) is copied over
+                g_specs = []
+                for g, (tf, F) in zip(gs, ctx.spec_dims):
+                    if g is not None and not (g.dtype is torch.float32 and g.device == dev and
+                                              g.stride() == (2 * tf * F, tf * F, 1, F)):
+                        g = g.to(device=dev, dtype=torch.float32).transpose(2, 3).contiguous()
+                    g_specs.append(g)
         g_yg = torch.empty((B, T), device=dev, dtype=torch.float32)
         ws = core._workspace(ctx.ws_bytes, dev, "mstft")
         _lib.check(lib.sb200_mstft_backward(ctx.handles, n_res, core.ptr(gc), B, T, ctx.phd_phase, core.ptr(g_loss),
@@ -300,8 +320,8 @@ def multi_stft_loss(y, y_g, ret_loss=False, ret_specs=False, ddp_reduce=False):
         if ddp and reducer is None:
             loss = _GlobalMean.apply(loss)   # value = global mean, grad = local
     if ret_specs:
-        stft_r = [s.transpose(2, 3) for s in outs[i:i + n_res]]
-        stft_g = [s.transpose(2, 3) for s in outs[i + n_res:i + 2 * n_res]]
+        stft_r = list(outs[i:i + n_res])          # [B, 2, F, T'] views of frame-major buffers (loss.py:44-45 stacks)
+        stft_g = list(outs[i + n_res:i + 2 * n_res])
     if ret_loss and ret_specs:
         return loss, (stft_r, stft_g)
     elif ret_loss:
