@@ -139,3 +139,20 @@ def test_numa_binding_is_a_no_op_without_nvml():
     if not ok:
         assert os.sched_getaffinity(0) == before
     os.sched_setaffinity(0, before)
+
+
+def test_peer_reduce_descriptor_layout():
+    """sb200_peer_reduce (include/spectral_b200.h): 8 buffer pointers, rank, world, the output pointer -- the ctypes mirror must
+    have the C layout, and the exchange buffer is the 256-byte PeerBuf of mstft.cuh.  No GPU needed."""
+    import ctypes as C
+    import transtacos_retunegan_b200 as sb
+    L = sb._lib
+    assert L.MAX_PEERS == 8 and C.sizeof(L.PeerReduce) == 8 * 8 + 4 + 4 + 8
+    assert L.PeerReduce.rank.offset == 64 and L.PeerReduce.world.offset == 68 and L.PeerReduce.loss_global.offset == 72
+    assert L.load().sb200_peer_buffer_bytes() == 256
+    red = sb.loss.PeerLossReducer(1, 2, peers=[4096, 8192])          # single-process form: raw pointers, nothing is allocated
+    t = __import__("torch").zeros(())
+    d = red.descriptor(t)
+    assert (d.rank, d.world, d.peer[0], d.peer[1], d.peer[2], d.loss_global) == (1, 2, 4096, 8192, None, t.data_ptr())
+    with pytest.raises(ValueError):
+        sb.loss.PeerLossReducer(0, 9, peers=[0] * 9)
