@@ -226,7 +226,7 @@ int sb200_stft_smp_backward(const sb200_plan* plan, const float* y, int32_t B, i
                             const float* g_P, float* g_y, void* workspace, sb200_stream stream);
 
 /* Loss value and d loss / d y_g for a unit upstream gradient in ONE pass (retunegan/train.py:165 multi_stft_loss(...,
- * ret_loss=True) followed by :192 backward, loss-only): one launch per resolution, no second analysis in backward.
+ * ret_loss=True) followed by :192 backward, loss-only): one launch for all resolutions, no second analysis in backward.
  * loss: device scalar; grad_yg: [B, T]; workspace: sb200_mstft_workspace_bytes(). */
 int sb200_mstft_loss_and_grad(const sb200_plan* const* plans, int32_t n_res, const float* y, const float* y_g, int32_t B,
                               int64_t T, float* loss, float* grad_yg, void* workspace, sb200_stream stream);

@@ -2,7 +2,9 @@
 // retunegan/audio.py:150-170; backward = the autograd graph of retunegan/train.py:192, closed form in
 // SURVEY.md 8a row L2).
 //
-// Forward, per resolution: one launch; a warp analyses the same Q frames of y and of y_g back to back,
+// All resolutions of a phase run as ONE launch (mstft_multi_*_kernel below: the per-resolution grids concatenated, a CTA works
+// for the resolution its index falls into, one pass per warp).
+// Forward, per resolution: a warp analyses the same Q frames of y and of y_g back to back,
 // keeps the real mel rows in registers, and accumulates |M - M_g| + |ln M - ln M_g| into a per-warp
 // partial (deterministic two-stage reduction, no atomics).  Optionally writes the [B,2,T',F]
 // (ln|D+1e-9|, angle(D)/PI) stacks for the STFT discriminator.
@@ -10,7 +12,9 @@
 // gD = gS (D+1e-9)/S + (gP/PI) i D/|D|^2 with gS = basis^T gM + g_lnS/S on the Hermitian pairs in
 // registers, runs the adjoint of the one-sided rFFT through the inverse engine, windows, and stores
 // gradient frames; grad_ola_kernel then overlap-adds all resolutions as a gather and folds the
-// reflect padding back.
+// reflect padding back.  The loss-only training step is one fused launch (value + gradient, no recomputation) + the overlap-add,
+// whose extra block reduces the loss partial sums and, under DDP, averages the loss over the ranks of the box in place
+// (peer_allreduce_mean: NVLink peer memory, no collective call).
 #pragma once
 #include "feat.cuh"
 

@@ -543,7 +543,7 @@ int sb200_mstft_backward(const sb200_plan* const* plans, int32_t n_res, const fl
   return check_launch("grad_ola_kernel");
 }
 
-// Loss value AND d loss / d y_g in one pass (one launch per resolution + overlap-add + reduction): the loss-only training
+// Loss value AND d loss / d y_g in one pass (one launch for all resolutions + the overlap-add, which carries the reduction): the loss-only training
 // step of retunegan/train.py:165,192 without a second analysis in backward.  grad_yg [B, T] is the gradient for a unit
 // upstream gradient; the autograd wrapper scales it by the incoming gradient.
 static int mstft_loss_and_grad_impl(const sb200_plan* const* plans, int32_t n_res, const float* y, const float* y_g, int32_t B,
