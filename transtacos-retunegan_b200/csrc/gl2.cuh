@@ -574,7 +574,47 @@ __device__ __forceinline__ void gl2_pass(const PlanDev& p, const Gl2Args& a, Gl2
       constexpr int kWarpStride = C::kXBytes / 4;   // floats between the staging buffers of consecutive warps
       const int nov = p.nov;
       // thread owns offsets o within a hop; sample j = q * hop + o is covered by frames q - d at offset o + d * hop, d <= nov
-      if (C::kWin % hop == 0 && (hop & 1) == 0) {
+      bool done = false;
+      if constexpr (N == 2048) {
+        if (C::kWin == 4 * hop && (hop & 1) == 0) {
+          // The reference's framing (n_fft 2048, win 1024, hop 256), fully unrolled: frame f of the tile adds its four hop-sized
+          // chunks to samples q = f .. f + 3 of the thread's offset o.  Every shared-memory address is the thread's base plus a
+          // compile-time constant and every accumulator a fixed register: 32 loads, 64 adds and the stores, where the rolled loops
+          // below spend ~1000 instructions per thread on index arithmetic and branches (the overlap-add was 15 % of the kernel's
+          // time for 64 useful additions).  Frames run from the last to the first, so each sample adds its terms in the order of the
+          // rolled loop (d ascending): same bits.
+          constexpr int ND = 4, NQ = FT + ND - 1, kHop = C::kWin / ND;
+          for (int o = 2 * gt; o < hop; o += 2 * GT) {
+            float2 acc[NQ];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) acc[q] = make_float2(0.f, 0.f);
+            const float* base = frames0 + o;
+            static_for<0, FT>([&](auto fc) {
+              constexpr int f = FT - 1 - decltype(fc)::value;
+              const float* fp = base + (f / C::kFrames) * kWarpStride + (f % C::kFrames) * C::kWin;
+              static_for<0, ND>([&](auto dc) {
+                constexpr int d = decltype(dc)::value;
+                const float2 t2 = *reinterpret_cast<const float2*>(fp + d * kHop);
+                acc[f + d].x += t2.x;
+                acc[f + d].y += t2.y;
+              });
+            });
+            static_for<0, NQ>([&](auto qc) {
+              constexpr int q = decltype(qc)::value;
+              const int j = q * kHop + o;
+              if (j < span) {
+                *reinterpret_cast<float2*>(mine + j) = acc[q];
+                constexpr bool interior = q >= ND - 1 && q < FT;   // j >= win - hop && j < FT * hop for every o < hop
+                if (interior || (tk == 0 && q < ND - 1) || (last_tile && q >= FT))
+                  *reinterpret_cast<float2*>(other + j) = make_float2(0.f, 0.f);
+              }
+            });
+          }
+          done = true;
+        }
+      }
+      if (done) {
+      } else if (C::kWin % hop == 0 && (hop & 1) == 0) {
         // win a multiple of hop (the reference framing): every d in [max(0, q - FT + 1), min(nov, q)] is a valid term, no
         // per-term tests; two neighbouring offsets per thread (8-byte shared loads and global stores; same summation order)
         for (int o = 2 * gt; o < hop; o += 2 * GT) {
