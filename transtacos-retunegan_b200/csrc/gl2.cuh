@@ -343,14 +343,23 @@ __device__ __forceinline__ void gl2_pass(const PlanDev& p, const Gl2Args& a, Gl2
         // packed previous spectrum of this pair (a pair past the end is clamped to the last one: loads stay in bounds and finite)
         ulonglong2* const tpp = a.tprev + (gl2_pair_base(row.frame_base, b) + (min(fA, row.T - 1) >> 1)) * C::kF;
         ulonglong2* const zp = xz + pp * C::kNz;
-        // everything one Hermitian pair (k, Nz - k) reads, fetched one trip ahead of its use
+        // everything one Hermitian pair (k, Nz - k) reads, fetched ahead of its use
         struct PairLd {
           ulonglong2 zk, zr;
           float sAa, sBa, sAb, sBb;
           float2 tAa, tBa, tAb, tBb;   // modes 0 / 1: input spectrum / initial phase
           ulonglong2 ta, tb;           // mode 3: previous rebuilt spectrum of bins k / Nz - k, packed (re pair, im pair)
         };
-        auto ld_pair = [&](int k) -> PairLd {
+        // ld_pair_g: what comes from global memory (S, previous spectrum / input spectrum / initial phase), fetched TWO trips ahead
+        // (L2 hits at ~700 cycles: one trip of lead left a third of the spectrum pass's stalls on the long scoreboard);
+        // ld_pair_s: the pair's analysed spectrum from the warp's shared-memory buffer, one trip ahead.
+        auto ld_pair_s = [&](int k, PairLd& L) {
+          if constexpr (MODE >= 2) {
+            L.zk = zp[k];
+            L.zr = zp[(C::kNz - k) & (C::kNz - 1)];
+          }
+        };
+        auto ld_pair_g = [&](int k) -> PairLd {
           PairLd L;
           if constexpr (MODE == 0) {   // the input spectrum, masked (rows past the end are clamped)
             const int kb = C::kNz - k;
@@ -372,9 +381,7 @@ __device__ __forceinline__ void gl2_pass(const PlanDev& p, const Gl2Args& a, Gl2
             L.tBb.x = __ldg(a.init_phase + rowB + kb);
           }
           if constexpr (MODE >= 2) {
-            const int km = (C::kNz - k) & (C::kNz - 1), kb = C::kNz - k;
-            L.zk = zp[k];
-            L.zr = zp[km];
+            const int kb = C::kNz - k;
             L.sAa = __ldg(a.S + rowA + k);    // raw: masked at the use (see above)
             L.sBa = __ldg(a.S + rowB + k);
             L.sAb = __ldg(a.S + rowA + kb);
@@ -434,19 +441,29 @@ __device__ __forceinline__ void gl2_pass(const PlanDev& p, const Gl2Args& a, Gl2
         // the loads of the next trip are issued before the current one is computed
         {
           constexpr int kTrips = C::kNz / 128;
-          PairLd c0 = ld_pair(lane), c1 = ld_pair(lane + C::kNz / 4);
+          static_assert(kTrips >= 2, "the pair loop runs two trips ahead");
+          PairLd c0 = ld_pair_g(lane), c1 = ld_pair_g(lane + C::kNz / 4);
+          PairLd d0 = ld_pair_g(lane + 32), d1 = ld_pair_g(lane + 32 + C::kNz / 4);
+          ld_pair_s(lane, c0);
+          ld_pair_s(lane + C::kNz / 4, c1);
 #pragma unroll (COH ? kGl2PairUnrollCoh : kGl2PairUnroll)
           for (int ii = 0; ii < kTrips; ++ii) {   // rolled: a single-tile launch runs this code once, from a cold instruction cache
             const int k = lane + 32 * ii;
-            PairLd n0 = c0, n1 = c1;
+            PairLd e0 = d0, e1 = d1;
+            if (ii + 2 < kTrips) {
+              e0 = ld_pair_g(k + 64);
+              e1 = ld_pair_g(k + 64 + C::kNz / 4);
+            }
             if (ii + 1 < kTrips) {
-              n0 = ld_pair(k + 32);
-              n1 = ld_pair(k + 32 + C::kNz / 4);
+              ld_pair_s(k + 32, d0);
+              ld_pair_s(k + 32 + C::kNz / 4, d1);
             }
             do_pair(k, c0, std::false_type{});
             do_pair(k + C::kNz / 4, c1, std::true_type{});
-            c0 = n0;
-            c1 = n1;
+            c0 = d0;
+            c1 = d1;
+            d0 = e0;
+            d1 = e1;
           }
         }
         // bin Nz/2 pairs with itself: Q = conj(P) (computed by every lane, stored by lane 0)
