@@ -156,3 +156,33 @@ def test_peer_reduce_descriptor_layout():
     assert (d.rank, d.world, d.peer[0], d.peer[1], d.peer[2], d.loss_global) == (1, 2, 4096, 8192, None, t.data_ptr())
     with pytest.raises(ValueError):
         sb.loss.PeerLossReducer(0, 9, peers=[0] * 9)
+
+
+def test_fast_atan2_polynomial_of_the_spec_stack_kernels():
+    """mstft.cuh fast_atan2 (phase channel of the spec stacks / get_stft_torch): the degree-7 minimax coefficients are read from the
+    source and the kernel's arithmetic is replayed in float32 numpy over all four quadrants, the axes and a range of magnitudes:
+    within 4e-7 rad of arctan2 (the header says ~3e-7), and a zero spectrum has phase 0 whatever the sign of its zeros."""
+    import re
+    src = open(os.path.join(ROOT, "transtacos-retunegan_b200", "csrc", "mstft.cuh")).read()
+    body = src[src.index("float fast_atan2(float y, float x)"):]
+    body = body[:body.index("return copysignf")]
+    coef = [np.float32(c) for c in re.findall(r"(-?\d\.\d+(?:e-?\d+)?)f\)?;", body) if abs(float(c)) < 1.01]
+    assert len(coef) == 8 and abs(coef[-1] - 1) < 1e-6, coef          # r = c7; r = fma(r, s, c6) ... ; last is ~1
+    rs = np.random.RandomState(0)
+    x = np.concatenate([rs.randn(200000) * 10 ** rs.uniform(-6, 3, 200000), [0, 0, 1, -1, 0, 0, -0.0, 3, -3]]).astype(np.float32)
+    y = np.concatenate([rs.randn(200000) * 10 ** rs.uniform(-6, 3, 200000), [1, -1, 0, 0, 0, -0.0, 0, 3, 3]]).astype(np.float32)
+    ax, ay = np.abs(x), np.abs(y)
+    mx, mn = np.maximum(ax, ay), np.minimum(ax, ay)
+    a = (mn / np.maximum(mx, np.float32(1e-37))).astype(np.float32)
+    s = (a * a).astype(np.float32)
+    r = np.full_like(a, coef[0])
+    for c in coef[1:]:
+        r = (r * s + c).astype(np.float32)
+    r = (r * a).astype(np.float32)
+    r = np.where(ay > ax, np.float32(1.57079632679489662) - r, r).astype(np.float32)
+    r = np.where(x < 0, np.float32(3.14159265358979324) - r, r).astype(np.float32)
+    r = np.copysign(r, y)
+    ref = np.arctan2(y.astype(np.float64), x.astype(np.float64))
+    keep = ~((x == 0) & (y == 0))
+    assert np.abs(r[keep] - ref[keep]).max() < 4e-7, np.abs(r[keep] - ref[keep]).max()
+    assert np.all(r[~keep] == 0)                                           # digital silence: angle(0) = 0 like torch.angle
